@@ -73,18 +73,40 @@ def run_mgm_case(ref, synth, sizes, seed, variant, univ_seed=0):
         return out
     ga.forward = fwd
     counts = {"hung": 0, "sk": 0}
+    trace = []                       # one record per GA-GM iteration: U_t, projector, tau
+    in_gagm = {"on": False}
     orig_h = ref.mgm.hungarian
 
     def hung(s, *a, **k):
         counts["hung"] += 1
+        if in_gagm["on"] and trace:
+            trace[-1]["proj"] = 1
         return orig_h(s, *a, **k)
     ref.mgm.hungarian = hung
     orig_chain = torch.chain_matmul
 
     def chain(*a):
         counts["sk"] += 1            # one chain_matmul per GA-GM iteration (HiPPI unused here)
+        trace.append({"U": a[3].detach().clone(), "proj": -1, "tau": 0.0})
         return orig_chain(*a)
     torch.chain_matmul = chain
+    orig_sk = ref.mgm.Sinkhorn
+
+    class SkSpy(orig_sk):            # gagm builds a fresh Sinkhorn(tau=...) per sinkhorn-projected iteration (mgm:333-349)
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            if in_gagm["on"] and trace:
+                trace[-1]["proj"], trace[-1]["tau"] = 0, float(k.get("tau"))
+    ref.mgm.Sinkhorn = SkSpy
+    orig_gagm = ga.gagm
+
+    def gagm_spy(*a, **k):
+        in_gagm["on"] = True
+        try:
+            return orig_gagm(*a, **k)
+        finally:
+            in_gagm["on"] = False
+    ga.gagm = gagm_spy
     try:
         nodes_g = [n.clone().requires_grad_(True) for n in nodes]
         loss = model(nodes_g, labels, U)
@@ -92,6 +114,7 @@ def run_mgm_case(ref, synth, sizes, seed, variant, univ_seed=0):
     finally:
         ref.mgm.hungarian = orig_h
         torch.chain_matmul = orig_chain
+        ref.mgm.Sinkhorn = orig_sk
     out = {
         "sizes": np.array(sizes), "seed": np.array(seed), "variant": np.array(variant),
         "input_checksum": np.array(checksum(nodes + [U] + masks)),
@@ -108,6 +131,22 @@ def run_mgm_case(ref, synth, sizes, seed, variant, univ_seed=0):
         out.update(summarise("grad_aff_" + k, p.grad))
     if sum(sizes) > 300:             # keep the fixture small
         del out["A"], out["Wds"], out["U0"]
+    elif variant == "pert":
+        # teacher-forcing samples of the reference's own fp32 trajectory: (U_t, projector, tau) -> U_{t+1}
+        # (the full trajectory is chaotic - see mgm_port.gagm - single steps are not)
+        T = len(trace)
+        sk_idx = [t for t in range(T) if trace[t]["proj"] == 0]
+        hg_idx = [t for t in range(T) if trace[t]["proj"] == 1]
+        pick = sorted(set(sk_idx[:2] + sk_idx[len(sk_idx) // 2:len(sk_idx) // 2 + 1] + sk_idx[-2:] +
+                          hg_idx[:2] + hg_idx[len(hg_idx) // 2:len(hg_idx) // 2 + 1] + hg_idx[-1:]))
+        nxt = lambda t: trace[t + 1]["U"] if t + 1 < T else cap["U"]
+        out["trace_iter"] = np.array(pick)
+        out["trace_proj"] = np.array([trace[t]["proj"] for t in pick])
+        out["trace_tau"] = np.array([trace[t]["tau"] for t in pick])
+        for k, t in enumerate(pick):
+            out[f"trace_Uin_{k}"] = trace[t]["U"].numpy()
+            out[f"trace_Uout_{k}"] = nxt(t).numpy()
+        out["trace_proj_all"] = np.array([r["proj"] for r in trace], dtype=np.int8)
     return out
 
 
