@@ -2,19 +2,19 @@
  * test-time-adaptation hot path.
  *
  * Conventions (last row):
- *   - every pointer is a DEVICE pointer unless its name ends in _h; tensors are dense row-major;
+ *   - every pointer is a DEVICE pointer unless its name ends in _h; tensors are dense row-major fp32
+ *     unless stated; "scratch" buffers are opaque device memory sized by the matching *_scratch_bytes();
  *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns at once;
  *   - return value: 0 = ok, >0 = cudaError_t of the launch, <0 = argument error (TTDG_E_*);
- *   - nothing is allocated and no pointer is retained: callers pass scratch buffers whose sizes come
- *     from the matching *_scratch_bytes() function (host-only, no GPU needed);
- *   - "ragged" batches are described by int32 offset arrays of length count+1 (prefix sums).
+ *   - nothing is allocated and no pointer is retained;
+ *   - ragged batches are described by small int32/int64 descriptor arrays in DEVICE memory.
  *
  * Each entry point cites the reference interface it replaces (paths relative to
  * /root/reference/adapteacher/modeling/GModule unless stated).
  *
  * Arithmetic contract of the matching stage ("precise mode"): fp32 in / fp32 out,
- * fp64 internally with a single rounding at each documented point, so results do not depend on
- * summation order and the discrete solver (LAP inside GA-GM) is reproducible bit for bit.
+ * fp64 internally, so results do not depend on summation order and the discrete solver (LAP inside
+ * GA-GM) is reproducible bit for bit.  The HBM-streaming Sinkhorn (large matrices) is fp32.
  */
 #ifndef TTDG_B200_H
 #define TTDG_B200_H
@@ -25,103 +25,120 @@
 extern "C" {
 #endif
 
-#define TTDG_E_ARG (-1)       /* bad argument (null pointer, negative size, ...)        */
-#define TTDG_E_LIMIT (-2)     /* size above a compiled-in limit (see ttdg_limits)        */
+#define TTDG_E_ARG (-1)   /* bad argument (null pointer, negative size, ...)  */
+#define TTDG_E_LIMIT (-2) /* size above a compiled-in limit (see ttdg_limit)  */
 
 /* library / build info; never touches the GPU */
-int ttdg_version(void);                         /* MAJOR*10000 + MINOR*100 + PATCH */
-const char *ttdg_build_info(void);              /* "sm_100a nvcc 12.9 ..." */
-int ttdg_limit(const char *name);               /* "lap_max_dim", "sinkhorn_small_max_dim", "gagm_max_graphs", ... ; -1 if unknown */
+int ttdg_version(void);            /* MAJOR*10000 + MINOR*100 + PATCH */
+const char *ttdg_build_info(void); /* "sm_100a nvcc 12.9 ..." */
+int ttdg_limit(const char *name);  /* "small_max_dim", "lap_max_dim", "gagm_max_graphs", "univ", "feat_dim"; -1 if unknown */
 
 /* ---------------------------------------------------------------------------------------------
  * Sinkhorn.  Replaces utils/sinkhorn.py:58-87 -> pygmtools.sinkhorn(backend='pytorch') (0.3.8).
- * Per-item semantics: the item is an n1 x n2 matrix stored with leading dimension
- * `ld` at `s + item_off[b]` (element offsets, int64).  If transpose[b] != 0 the stored matrix is read as its
- * transpose (so the working matrix always has rows <= cols); working matrix / tau; if dummy_row the
- * (cols-rows) missing rows are filled with -100; `max_iter` alternating normalisations (even = over the
- * columns of each row, odd = over the rows of each column); exp; written back in the stored layout.
+ * Per-item semantics: the stored n1 x n2 matrix is worked on in the orientation
+ * with rows <= cols (transposed when n2 < n1); divided by tau; if dummy_row the (cols-rows) missing rows
+ * are filled with -100; `max_iter` alternating normalisations (even = each row over its columns, odd =
+ * each column over its rows); exp; written back in the stored orientation.
  * --------------------------------------------------------------------------------------------- */
 
-/* small matrices (rows, cols <= ttdg_limit("sinkhorn_small_max_dim")): one CTA per item, matrix resident
- * in shared memory, fp64 internal.  dims[b] = {n1, n2, ld, transpose} as stored. */
-int ttdg_sinkhorn_small_fwd(const float *s, float *out, const int64_t *item_off, const int32_t *dims4,
-                            int n_items, double tau, int max_iter, int dummy_row, void *stream);
-/* backward of the above: grad_in = d(sum(out * grad_out)) / d s.  Recomputes the forward in-kernel. */
-int ttdg_sinkhorn_small_bwd(const float *s, const float *grad_out, float *grad_in, const int64_t *item_off,
-                            const int32_t *dims4, int n_items, double tau, int max_iter, int dummy_row,
-                            void *stream);
+/* Small matrices (n1, n2 <= ttdg_limit("small_max_dim")): one CTA per item, matrix resident in shared
+ * memory, fp64 internal.  items: int64[n_items][8] =
+ *   { s_off, out_off, mirror_off, n1, n2, ld_s, ld_out, ld_mirror }   (element offsets / leading dims)
+ * out receives the n1 x n2 result at out_off; if mirror_off >= 0 its TRANSPOSE (n2 x n1) is also written
+ * at mirror_off (MGM3_unsup stores both Wds[src,tgt] and Wds[tgt,src], mgm:523-525).
+ * max_dim: host-known upper bound of every n1, n2 (sizes the shared memory; items above it are skipped). */
+int ttdg_sinkhorn_small_fwd(const float *s, float *out, const int64_t *items, int n_items, int max_dim,
+                            double tau, int max_iter, int dummy_row, void *stream);
+/* Backward: grad_in = d(sum(out * grad_out)) / d s.  Recomputes the forward in-kernel.  items: int64[n][8] =
+ *   { s_off, gout_off, gin_off, n1, n2, ld_s, ld_gout, ld_gin }. */
+int ttdg_sinkhorn_small_bwd(const float *s, const float *grad_out, float *grad_in, const int64_t *items,
+                            int n_items, int max_dim, double tau, int max_iter, int dummy_row, void *stream);
 
-/* large matrices: HBM-streaming fp32 path (the N = 256/512/1024 microbenchmark of BASELINE.json).
- * Uniform batch of `batch` dense n1 x n2 matrices, n1 <= n2, no dummy rows needed (n1 == n2) or
- * dummy_row with n1 < n2.  scratch: ttdg_sinkhorn_stream_scratch_bytes(batch, n1, n2).
- * One launch of a persistent kernel: each CTA owns whole matrices and runs all iterations on them. */
+/* Large matrices: fp32 path for the N = 256/512/1024 micro-benchmark of BASELINE.json.  Uniform batch of
+ * dense n1 x n2 matrices (n1 <= n2; n1 < n2 needs dummy_row = 0 or 1 as in the reference; n2 % 4 == 0).
+ * One thread-block cluster per matrix keeps the matrix in distributed shared memory for all iterations
+ * (row/column potentials, one read pass per half-iteration, no intermediate HBM traffic) when it fits,
+ * otherwise re-reads the part that does not fit through L2.  scratch: ttdg_sinkhorn_stream_scratch_bytes. */
 int64_t ttdg_sinkhorn_stream_scratch_bytes(int batch, int n1, int n2);
 int ttdg_sinkhorn_stream_fwd(const float *s, float *out, int batch, int n1, int n2, float tau, int max_iter,
                              int dummy_row, void *scratch, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * LAP.  Replaces utils/hungarian.py:8-65 -> scipy.optimize.linear_sum_assignment(-s) (fp64, Crouse
- * shortest augmenting path, SciPy tie-breaking).  perm (same layout as s) receives
- * 0/1 float32.  One warp per item; rows, cols <= ttdg_limit("lap_max_dim").  dims3[b] = {n1, n2, ld}.
+ * shortest augmenting path, SciPy tie-breaking).  One warp per item;
+ * n1, n2 <= ttdg_limit("lap_max_dim").  items: int64[n][6] = { s_off, perm_off, n1, n2, ld_s, ld_perm };
+ * perm receives a 0/1 float32 matrix of the max-weight assignment.
  * --------------------------------------------------------------------------------------------- */
-int ttdg_lap_solve(const float *s, float *perm, const int64_t *item_off, const int32_t *dims3, int n_items,
-                   void *stream);
+int ttdg_lap_solve(const float *s, float *perm, const int64_t *items, int n_items, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Attention adjacency.  Replaces MGM3_unsup._forward_intra_graph (multi_graph_matching.py:571-574) ->
- * MultiHeadAttention.forward v2 (utils/attentions.py:60-86), keeping only the attention map that
- * mgm:498-502 uses:  A[blk g] = dropout(softmax((x Wq^T + bq)(x Wk^T + bk)^T / 16)), diagonal zeroed,
- * everything outside the diagonal blocks zeroed.  A is M x M (M = node_off[G]).
- * dropout: keep_mask != NULL -> explicit M-row ragged masks (mask_off[g] element offsets, n_g x n_g 0/1
- * floats); else if p_drop > 0 -> Philox4x32-10 keyed by (seed, offset); p_drop == 0 -> eval mode.
- * scratch: ttdg_attn_scratch_bytes(M).
+ * Y = X W^T (+ b): the small dense layers of the matching head (attention q/k projections
+ * attentions.py:66-69, affinity projections affinity.py:48-49, universe init mgm:531-532).
+ * X: m x k (ldx), W: n x k (ldw), Y: m x n (ldy), fp32 storage, fp64 accumulation, one rounding.
  * --------------------------------------------------------------------------------------------- */
-int64_t ttdg_attn_scratch_bytes(int M);
-int ttdg_attn_adjacency(const float *nodes, const int32_t *node_off, int G, const float *wq, const float *bq,
-                        const float *wk, const float *bk, const float *keep_mask, const int64_t *mask_off,
-                        float p_drop, uint64_t seed, uint64_t offset, float *A, void *scratch, void *stream);
+int ttdg_linear_f64acc(const float *X, int ldx, const float *W, int ldw, const float *b, float *Y, int ldy,
+                       int m, int n, int k, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention adjacency.  Replaces MGM3_unsup._forward_intra_graph (mgm:571-574) ->
+ * MultiHeadAttention.forward v2 (utils/attentions.py:60-86), keeping only the attention map that
+ * mgm:498-502 uses:  A[blk g] = dropout(softmax(q_g k_g^T * scale)), diagonal zeroed, zero outside the
+ * diagonal blocks.  S = q k^T (M x M fp32 logits; q, k from ttdg_linear_f64acc, product from
+ * ttdg_gemm_f64acc) - only its diagonal blocks are read.  scale = (256 // heads) ** -0.5 = 1/16.
+ * A: M x M, fully written.
+ * dropout: keep_mask != NULL -> explicit ragged masks (n_g x n_g 0/1 floats at mask_off[g]);
+ * else if p_drop > 0 -> Philox4x32-10 keyed by (seed, offset + element index); p_drop == 0 -> eval mode.
+ * --------------------------------------------------------------------------------------------- */
+int ttdg_attn_adjacency(const float *S, const int32_t *node_off, int G, int M, float scale,
+                        const float *keep_mask, const int64_t *mask_off, float p_drop, uint64_t seed,
+                        uint64_t offset, float *A, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Learned affinity.  Replaces MGM3_unsup._forward_aff (mgm:576-582) -> Affinity.forward
  * (utils/affinity.py:44-57) in separable form (no N1 x N2 x 512 tensor):
- *     a = (X Ps^T) W0a^T,  c = (Y Pt^T) W0b^T + b0,  M_ij = sum_k w1_k relu(a_ik + c_jk) + b1
- * for every listed (src, tgt) graph pair.  nodes: M x 256.  pairs: int32 {src, tgt} x n_pairs.
- * out_off[p]: element offset of pair p's n_src x n_tgt block in `out`.
- * scratch (fp64 a, c, projections): ttdg_affinity_scratch_bytes(M).
+ *     a = Xp W0a^T,  c = Yp W0b^T + b0,  M_ij = sum_k w1_k relu(a_ik + c_jk) + b1
+ * with Xp = X Ps^T, Yp = Y Pt^T (ttdg_linear_f64acc), W0 = [W0a | W0b] (hidden x 2 dim).
+ * ac: M x (2 hidden) fp64 = [a | c] per node, produced by ttdg_affinity_hidden.
+ * pairs: int64[n_pairs][4] = { src_row0, n_src, tgt_row0, n_tgt }; out_off[p] = element offset of pair p's
+ * n_src x n_tgt block in `out` (blocks stored back to back).  max_n_src: host-known max of n_src.
  * --------------------------------------------------------------------------------------------- */
-int64_t ttdg_affinity_scratch_bytes(int M);
-int ttdg_affinity_fwd(const float *nodes, const int32_t *node_off, int G, const float *w_sr, const float *w_tg,
-                      const float *w0, const float *b0, const float *w1, const float *b1, const int32_t *pairs,
-                      const int64_t *out_off, int n_pairs, float *out, void *scratch, void *stream);
-/* backward: given grad_out (same ragged layout as out) accumulates into grad_nodes (M x 256) and the six
- * parameter gradients (all fp32, must be zero-initialised or hold a running sum). `scratch` must be the
- * buffer the forward filled (a, c are reused). scratch2: ttdg_affinity_bwd_scratch_bytes(M). */
-int64_t ttdg_affinity_bwd_scratch_bytes(int M);
-int ttdg_affinity_bwd(const float *nodes, const int32_t *node_off, int G, const float *w_sr, const float *w_tg,
-                      const float *w0, const float *w1, const int32_t *pairs, const int64_t *out_off, int n_pairs,
-                      const float *grad_out, float *grad_nodes, float *g_w_sr, float *g_w_tg, float *g_w0,
-                      float *g_b0, float *g_w1, float *g_b1, void *scratch, void *scratch2, void *stream);
-
-/* U0 = nodes @ universe^T  (mgm:531-532): nodes M x 256, universe n_univ x 256 -> M x n_univ. */
-int ttdg_universe_init(const float *nodes, int M, const float *universe, int n_univ, int dim, float *U0,
-                       void *stream);
+int ttdg_affinity_hidden(const float *Xp, const float *Yp, const float *w0, const float *b0, int M, int dim,
+                         int hidden, double *ac, void *stream);
+int ttdg_affinity_pairs_fwd(const double *ac, const float *w1, const float *b1, const int64_t *pairs,
+                            const int64_t *out_off, int n_pairs, int max_n_src, int hidden, float *out,
+                            void *stream);
+/* backward of the pair stage: g_ac (M x 2 hidden fp64, fully written), g_w1 (hidden) and g_b1 (1) (fp32,
+ * overwritten).  Deterministic (no atomics): each node row gathers from the pairs it belongs to.
+ * grad_out has the layout of `out` (grad_out_total elements); max_n: host-known max graph size.
+ * scratch: ttdg_affinity_bwd_scratch_bytes(M, hidden). */
+int64_t ttdg_affinity_bwd_scratch_bytes(int M, int hidden);
+int ttdg_affinity_pairs_bwd(const double *ac, const float *w1, const int64_t *pairs, const int64_t *out_off,
+                            int n_pairs, int hidden, int M, int max_n, const float *grad_out,
+                            int64_t grad_out_total, double *g_ac, float *g_w1, float *g_b1, void *scratch,
+                            void *stream);
+/* dense helper (fp64 accumulation): C (m x n) = op(A) (m x k) op(B) (k x n) [+ C], row-major operands given
+ * as fp32 or fp64 (a_is_f64 ...), op = transpose when trans* != 0.  Used for the attention logits and the
+ * affinity autograd: g_w0 = g_ac^T [Xp | Yp], g_Xp = g_a W0a, g_Ps = g_Xp^T X, g_nodes = g_Xp Ps + g_Yp Pt. */
+int ttdg_gemm_f64acc(int transA, int transB, int m, int n, int k, const void *A, int a_is_f64, int lda,
+                     const void *B, int b_is_f64, int ldb, void *C, int c_is_f64, int ldc, int accumulate,
+                     void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * GA-GM solver.  Replaces GA_GM.forward + gagm (multi_graph_matching.py:223-244, 300-389) for the
  * configuration the hot path uses (num_clusters = 1, projector0 = 'sinkhorn', hung_iter = True) including
  * the per-iteration projector: batched Sinkhorn (mgm:330-353) or per-graph Hungarian (mgm:324-328), the
  * G == 2 identity quirk (mgm:358-359) and both convergence tests (mgm:361) - all on the device, no
- * host round trip.  One persistent CTA.  A, W: M x M; U0, U: M x 32; ms: int32[G].
+ * host round trip.  One thread-block cluster (one CTA per graph, up to 8; more graphs share CTAs).
+ * A, W: M x M; U0, U: M x n_univ (n_univ == 32); ms_h: HOST int32[G].
  * mode: 0 = full solve; 1 = exactly one iteration with projector `step_projector` (0 sinkhorn, 1 hungarian)
  * at temperature init_tau (teacher-forced parity tests).
  * info (int32[8], device): {iterations, sinkhorn-stage iterations, hungarian-stage iterations, LAP calls,
- *                           sinkhorn stages, converged-flag of last stage, 0, 0}.
- * scratch: ttdg_gagm_scratch_bytes(M, G).  Scalars are doubles because the reference keeps tau etc. as
- * Python floats (mgm:307,379).
+ *                           sinkhorn stages, 0, 0, 0}.
+ * scratch: ttdg_gagm_scratch_bytes(M, G).
  * --------------------------------------------------------------------------------------------- */
 int64_t ttdg_gagm_scratch_bytes(int M, int G);
-int ttdg_gagm_solve(const float *A, const float *W, const float *U0, const int32_t *ms, int G, int M,
-                    double init_tau, double min_tau, double sk_gamma, int max_iter, int sk_iter,
+int ttdg_gagm_solve(const float *A, const float *W, const float *U0, const int32_t *ms_h, int G, int M,
+                    int n_univ, double init_tau, double min_tau, double sk_gamma, int max_iter, int sk_iter,
                     double converge_tol, double quad_weight, int mode, int step_projector, float *U,
                     int32_t *info, void *scratch, void *stream);
 
@@ -129,17 +146,46 @@ int ttdg_gagm_solve(const float *A, const float *W, const float *U0, const int32
  * Matching loss.  Replaces collect_intra_class_matching_wrapper + the 'perm' loss loop (mgm:543-564,
  * 594-633) -> PermutationLoss / BCEFocalLoss (utils/losses.py:83-103, 419-455):
  *     loss = mean over pairs i1<i2 of mean_ij focal_bce(clamp(S_ij), (U_i1 U_i2^T)_ij)
- * S is read from Wds (M x M) with the orientation rule of mgm:620-623.  loss: 1 float (device).
- * The backward writes grad_Wds (M x M, zero outside the touched blocks) scaled by *grad_loss.
+ * S_ij is read from Wds (M x M) at the block the pairwise Sinkhorn wrote (rows of graph i2, columns of graph
+ * i1 - mgm:507-525, :620-623).  loss: 1 float.  flags: int32[1], set non-zero if an S or target value left
+ * [0, 1] (the reference asserts, losses.py:437-442).  The backward writes grad_Wds (M x M, zero outside
+ * the touched blocks) scaled by *grad_loss.
  * --------------------------------------------------------------------------------------------- */
+int64_t ttdg_matching_loss_scratch_bytes(int G);
 int ttdg_matching_loss_fwd(const float *Wds, const float *U, const int32_t *node_off, int G, int M, int n_univ,
-                           float *loss, int32_t *flags, void *stream);
+                           float *loss, int32_t *flags, void *scratch, void *stream);
 int ttdg_matching_loss_bwd(const float *Wds, const float *U, const int32_t *node_off, int G, int M, int n_univ,
                            const float *grad_loss, float *grad_Wds, void *stream);
-/* generic focal BCE on one matrix (utils/losses.py:83-103): mean reduction. */
-int ttdg_focal_bce_fwd(const float *p, const float *y, int64_t n, float *loss, void *stream);
+/* generic focal BCE on one dense array (utils/losses.py:83-103): mean reduction. */
+int64_t ttdg_focal_bce_scratch_bytes(void);
+int ttdg_focal_bce_fwd(const float *p, const float *y, int64_t n, float *loss, void *scratch, void *stream);
 int ttdg_focal_bce_bwd(const float *p, const float *y, int64_t n, const float *grad_loss, float *grad_p,
                        void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Node sampler.  Replaces PrototypeComputation.__call__ (build_graph.py:160-250; targets :70-115,
+ * locations :133-157).  Levels l = 0..4 with strides 4, 8, 16, 32, 64; lvl_hw_h = HOST int32[5][2] (H_l, W_l).
+ * boxes: float[total_boxes][4] xyxy, classes int64[total_boxes], box_off int32[B+1] - one entry per LISTED
+ * image; images without boxes must already be dropped by the caller, and listed image b reads feature-map
+ * image b (the reference skips box-less images at :79 but indexes features by list position at :181).
+ * ttdg_sampler_select: label[b][loc] (int32, L = sum_l H_l W_l locations per image), counts[b][l] = number of
+ *   kept nodes, sel_idx[b][l][max_per_level] = flat location index (inside the image) of every kept node.
+ * ttdg_sampler_gather: nodes (n_total x C) and labels (int64) in the reference order (image, level, location);
+ *   node_off = device int32[B*5+1] prefix sums of counts.  Feature maps are read through strides
+ *   (feat_strides_h = HOST int64[5][3] = {image, channel, pixel} element strides) so NCHW and NHWC both work;
+ *   feat_ptrs_h = HOST array of 5 device pointers.
+ * ttdg_sampler_scatter_bwd: gfeat[l][b, :, pixel] += grad_nodes[k, :] (kept locations are unique).
+ * --------------------------------------------------------------------------------------------- */
+int ttdg_sampler_select(const float *boxes, const int64_t *classes, const int32_t *box_off, int B,
+                        const int32_t *lvl_hw_h, int sample_dist, int max_per_level, int32_t *label,
+                        int32_t *counts, int32_t *sel_idx, void *stream);
+int ttdg_sampler_gather(const float *const *feat_ptrs_h, const int64_t *feat_strides_h, const int32_t *lvl_hw_h,
+                        int B, int C, int n_total, const int32_t *label, const int32_t *sel_idx,
+                        int max_per_level, const int32_t *node_off, float *nodes, int64_t *labels_out,
+                        void *stream);
+int ttdg_sampler_scatter_bwd(const float *grad_nodes, float *const *gfeat_ptrs_h, const int64_t *feat_strides_h,
+                             const int32_t *lvl_hw_h, int B, int C, int n_total, const int32_t *sel_idx,
+                             int max_per_level, const int32_t *node_off, void *stream);
 
 #ifdef __cplusplus
 }

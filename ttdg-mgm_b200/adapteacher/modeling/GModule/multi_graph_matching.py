@@ -1,0 +1,107 @@
+"""Multi-graph-matching head; mirrors reference adapteacher/modeling/GModule/multi_graph_matching.py:
+``MGM3_unsup`` (:451-633, the test-time-adaptation loss), ``GA_GM`` (:191-389, graduated assignment solver)
+and ``U_sup`` (:119-168; at test time only its ``U`` parameter is read, rcnn.py:353).
+
+Same constructor signatures and state-dict keys; the forward is a short host script over libttdg_sm100.so:
+6 dense launches (attention q/k/logits, affinity projections/hidden), 1 affinity-pair kernel, 1 batched
+pairwise Sinkhorn, 1 persistent GA-GM cluster kernel (the reference: ~213 iterations x (4 GEMMs + Sinkhorn or
+G x SciPy round trips)), 1 loss kernel - and the mirrored backward.
+"""
+import torch
+import torch.nn as nn
+
+from ttdg_b200 import ops
+from .utils.affinity import Affinity
+from .utils.attentions import MultiHeadAttention
+from .utils.losses import PermutationLoss
+from .utils.sinkhorn import Sinkhorn
+
+
+class GA_GM(nn.Module):
+    """Graduated-assignment solver (mgm:191-389) for the multi-graph case the hot path uses (num_clusters == 1)."""
+
+    def __init__(self, mgm_iter=(200,), cluster_iter=10, sk_iter=20, sk_tau0=(0.5,), sk_gamma=0.5, cluster_beta=(1., 0.),
+                 converge_tol=1e-5, min_tau=(1e-2,), projector0=('sinkhorn',)):
+        super().__init__()
+        self.mgm_iter = mgm_iter
+        self.cluster_iter = cluster_iter
+        self.sk_iter = sk_iter
+        self.sk_tau0 = sk_tau0
+        self.sk_gamma = sk_gamma
+        self.cluster_beta = cluster_beta
+        self.converge_tol = converge_tol
+        self.min_tau = min_tau
+        self.projector0 = projector0
+        self.last_info = None
+
+    def forward(self, A, W, U0, ms, n_univ, quad_weight=1., cluster_quad_weight=1., num_clusters=1):
+        if num_clusters != 1:
+            raise NotImplementedError("clustered matching (num_clusters > 1) is unreachable from MGM3_unsup (mgm:533)")
+        if self.projector0[0] != 'sinkhorn':
+            raise NameError('Unknown projecter name: {}'.format(self.projector0[0]))
+        ms_l = [int(v) for v in (ms.tolist() if torch.is_tensor(ms) else ms)]
+        U, info = ops.gagm_solve(A, W.detach(), U0, ms_l, n_univ, init_tau=self.sk_tau0[0], min_tau=self.min_tau[0],
+                                 sk_gamma=self.sk_gamma, max_iter=self.mgm_iter[0], sk_iter=self.sk_iter,
+                                 converge_tol=self.converge_tol, quad_weight=quad_weight, return_info=True)
+        self.last_info = info
+        return U, torch.zeros(len(ms_l), dtype=torch.int)
+
+
+class U_sup(nn.Module):
+    """Holder of the learned universe embedding ``U`` (mgm:119-135).  The source-training forward (HiPPI,
+    mgm:137-168) is outside the test-time path."""
+
+    def __init__(self, num_cls, univ_size, dim=256):
+        super().__init__()
+        self.num_cls = num_cls
+        self.univ_size = univ_size
+        self.U = nn.Parameter(torch.randn(univ_size, dim) + 1 / univ_size)      # mgm:124
+
+    def forward(self, nodes, labels):
+        raise NotImplementedError("U_sup.forward (source-time universe learning) is not on the test-time path")
+
+
+class MGM3_unsup(nn.Module):
+    def __init__(self, num_cls, univ_size, dim=256):
+        super().__init__()
+        self.num_classes = num_cls
+        self.univ_size = univ_size
+        self.quad_weight = 0.5                     # mgm:457
+        self.cluster_quad_weight = 1.
+        self.perm_loss = 'perm'
+        self.criterion = PermutationLoss()
+        self.intra_domain_graph = MultiHeadAttention(dim, 1, dropout=0.1, version='v2')     # mgm:463
+        self.node_affinity = Affinity(d=dim)
+        self.sinkhorn = Sinkhorn(max_iter=20, tau=0.05, epsilon=1e-10)                     # mgm:467-468
+        self.ga_mgmc = GA_GM(mgm_iter=(200,), cluster_iter=10, sk_iter=20, sk_tau0=(0.1,), sk_gamma=0.5,
+                             cluster_beta=(1., 0.), converge_tol=1e-3, min_tau=(1e-2,), projector0=('sinkhorn',))   # mgm:469-474
+        # parity hooks (tests): explicit dropout keep-masks / a forced matching result
+        self.debug_keep_masks = None
+        self.debug_U_override = None
+        self.last_aux = None
+
+    def _cfg(self):
+        g = self.ga_mgmc
+        return dict(sk_iter=self.sinkhorn.max_iter, sk_tau=self.sinkhorn.tau, ga_iter=g.mgm_iter[0], ga_sk_iter=g.sk_iter,
+                    ga_tau0=g.sk_tau0[0], ga_gamma=g.sk_gamma, ga_tol=g.converge_tol, ga_min_tau=g.min_tau[0],
+                    quad_weight=self.quad_weight)
+
+    def forward(self, nodes, labels, U):
+        if nodes is None or len(nodes) == 1:
+            return None                                                           # mgm:489-490
+        sizes = [int(n.shape[0]) for n in nodes]
+        if max(sizes) > 96 or min(sizes) < 1:
+            raise ValueError("graphs must have 1..96 nodes (the sampler yields at most 95, build_graph.py:189-195)")
+        X = torch.cat(list(nodes), dim=0)                                        # M x 256, carries the gradient
+        with torch.no_grad():
+            A = self.intra_domain_graph.adjacency(X, sizes, self.debug_keep_masks)          # mgm:496-502
+            U0 = ops.linear(X, U)                                                # mgm:531-532 (detached)
+        aff = self.node_affinity.forward_pairs(X, sizes, ops.mgm_pairs(len(sizes)))          # mgm:504-525 (learned part)
+        loss, Wds, U_b, flags, info = ops.matching_loss(aff, A, U0, sizes, self._cfg(), self.debug_U_override)
+        self.last_aux = {"A": A, "Wds": Wds, "U0": U0, "U": U_b, "flags": flags, "info": info, "sizes": sizes}
+        return loss
+
+    def check_flags(self):
+        """Deferred form of the reference's range assertions (losses.py:437-442): one host sync, on demand."""
+        if self.last_aux is not None and int(self.last_aux["flags"].item()) != 0:
+            raise AssertionError("matching loss inputs left [0, 1]")

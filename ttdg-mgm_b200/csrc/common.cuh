@@ -33,6 +33,11 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(TTDG_FULL, v, o));
     return v;
 }
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(TTDG_FULL, v, o);
+    return v;
+}
 __device__ __forceinline__ int warp_min_i(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(TTDG_FULL, v, o));
@@ -52,3 +57,6 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace ttdg
+
+#define TTDG_STR2(x) #x
+#define TTDG_STR(x) TTDG_STR2(x)

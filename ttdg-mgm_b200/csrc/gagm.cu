@@ -1,0 +1,329 @@
+// gagm.cu - the graduated-assignment multi-graph-matching solver as ONE persistent thread-block cluster.
+//
+// Reference: GA_GM.forward + GA_GM.gagm (adapteacher/modeling/GModule/multi_graph_matching.py:223-244, 300-389)
+// with num_clusters = 1 (cluster weight == 1), projector0 = 'sinkhorn', hung_iter = True - the only
+// configuration MGM3_unsup uses (mgm:469-474, 533).  Per iteration the reference does
+//     UUt = U U^T;  V = chain_matmul(A, UUt, A, U) * quad_weight * 2 + W U;  V /= G          (mgm:317-321)
+//     U   = batched Sinkhorn(V / tau)   or   per-graph Hungarian(V)                             (mgm:324-353)
+//     G == 2: U[:ms0] = eye (mgm:358-359);  stop on ||U - lastU|| < tol or ||U - lastU2|| == 0   (mgm:361)
+// i.e. ~213 iterations of 4 small GEMMs + a projector + 2 norms, each norm a host sync, each Hungarian a
+// device->host->device round trip (~800 per step).  Here: zero host involvement.
+//
+// Mapping: cluster of C = min(G, 8) CTAs; CTA c owns graphs c, c + C, ...  A is block diagonal, so with
+// X_g = A_gg U_g the chain is  A (U (U^T (A U))) = A_gg (U_g T),  T = sum_g U_g^T X_g  (32 x 32):
+//   phase 1: X_g, partial T  -> global scratch  | cluster barrier
+//   phase 2: T, Q_g = U_g T, V_g = (2 qw A_gg Q_g + W[g,:] U) / G, projector, U_new_g, partial norms | cluster barrier
+// All arithmetic is fp64 (A, W, U0 are fp32 inputs widened exactly): the iteration is a discrete dynamical
+// system that amplifies rounding noise, fp64 makes it independent of summation order.
+#include "lap.cuh"
+#include "sinkhorn_small.cuh"
+#include <cooperative_groups.h>
+
+namespace ttdg {
+
+constexpr int GAGM_THREADS = 512;
+constexpr int GAGM_WARPS = GAGM_THREADS / 32;
+constexpr int GAGM_MAX_N = 96;            // nodes per graph
+constexpr int GAGM_MAX_G = 64;
+constexpr int GAGM_MAX_C = 8;             // portable cluster size
+constexpr int NU = 32;                    // universe size (rcnn.py:116)
+constexpr int RPW = GAGM_MAX_N / GAGM_WARPS;   // rows per warp = 6
+constexpr int ZP = NU + 1;                // pitch of the V / z tile
+
+struct GagmParams {
+    const float *A, *W, *U0;
+    float *U_out;
+    int32_t *info;
+    double *Ubuf;        // 3 x M x NU
+    double *Tpart;       // C x NU*NU
+    double *normpart;    // C x 2
+    int G, M, C;
+    double init_tau, min_tau, sk_gamma, tol, quad_weight;
+    int max_iter, sk_iter, mode, step_projector;
+    int node_off[GAGM_MAX_G + 1];
+};
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+// acc[r] += sum_j Mg[(warp + 16 r) * ld + j] * S[j * NU + lane],  r < R = ceil(nrows / 16); rows >= nrows are
+// computed on row 0 and ignored by the caller
+template <int R>
+__device__ __forceinline__ void rows_times_tile_r(const float *__restrict__ Mg, int ld, int nrows, int ncols,
+                                                  const double *__restrict__ S, double (&acc)[RPW], int warp, int lane) {
+    const float *rp[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = warp + GAGM_WARPS * r;
+        rp[r] = Mg + (size_t)(i < nrows ? i : 0) * ld;
+    }
+#pragma unroll 4
+    for (int j = 0; j < ncols; ++j) {
+        const double sv = S[j * NU + lane];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = fma((double)__ldg(rp[r] + j), sv, acc[r]);
+    }
+}
+__device__ __forceinline__ void rows_times_tile(const float *__restrict__ Mg, int ld, int nrows, int ncols,
+                                                const double *__restrict__ S, double (&acc)[RPW], int warp, int lane) {
+    switch ((nrows + GAGM_WARPS - 1) / GAGM_WARPS) {
+        case 1: rows_times_tile_r<1>(Mg, ld, nrows, ncols, S, acc, warp, lane); break;
+        case 2: rows_times_tile_r<2>(Mg, ld, nrows, ncols, S, acc, warp, lane); break;
+        case 3: rows_times_tile_r<3>(Mg, ld, nrows, ncols, S, acc, warp, lane); break;
+        case 4: rows_times_tile_r<4>(Mg, ld, nrows, ncols, S, acc, warp, lane); break;
+        case 5: rows_times_tile_r<5>(Mg, ld, nrows, ncols, S, acc, warp, lane); break;
+        default: rows_times_tile_r<6>(Mg, ld, nrows, ncols, S, acc, warp, lane); break;
+    }
+}
+
+__global__ void __launch_bounds__(GAGM_THREADS, 1)
+gagm_kernel(const __grid_constant__ GagmParams p) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    double *Ug = reinterpret_cast<double *>(gsm);          // n x NU   (U_g, later U_new_g)
+    double *X = Ug + GAGM_MAX_N * NU;                      // n x NU   (A U, then Q = U T)
+    double *Uo = X + GAGM_MAX_N * NU;                      // n x NU   (U_h tile for W U)
+    double *Z = Uo + GAGM_MAX_N * NU;                      // n x ZP   (V, then Sinkhorn log-matrix)
+    double *T = Z + GAGM_MAX_N * ZP;                       // NU x NU
+    double *padv = T + NU * NU;                            // GAGM_MAX_N
+    double *red = padv + GAGM_MAX_N;                       // 2 * GAGM_WARPS
+    LapWork *lapw = reinterpret_cast<LapWork *>(red + 2 * GAGM_WARPS);
+
+    const int c = blockIdx.x, C = p.C, G = p.G, M = p.M;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const size_t UB = (size_t)M * NU;
+
+    // ---- init: U buffers
+    for (int g = c; g < G; g += C) {
+        const int o = p.node_off[g], n = p.node_off[g + 1] - o;
+        for (int e = tid; e < n * NU; e += GAGM_THREADS) {
+            p.Ubuf[(size_t)o * NU + e] = (double)p.U0[(size_t)o * NU + e];
+            p.Ubuf[UB + (size_t)o * NU + e] = 0.0;           // lastU = zeros_like(U)  (mgm:305)
+            p.Ubuf[2 * UB + (size_t)o * NU + e] = 0.0;
+        }
+    }
+    __threadfence();
+    cluster_sync_all();
+
+    int cur = 0, last = 1, last2 = 2;
+    double tau = p.init_tau;
+    int projector = (p.mode == 1) ? p.step_projector : 0;   // 0 sinkhorn, 1 hungarian
+    int it_total = 0, it_sk = 0, it_hg = 0, n_lap = 0, n_stage = 0;
+
+    while (true) {
+        bool stop_all = false;
+        for (int i = 0; i < p.max_iter; ++i) {
+            { const int nxt = last2; last2 = last; last = cur; cur = nxt; }   // lastU2 = lastU; lastU = U (mgm:313-314)
+            const double *Ul = p.Ubuf + (size_t)last * UB;      // U_t
+            const double *Ul2 = p.Ubuf + (size_t)last2 * UB;    // U_{t-1}
+            double *Un = p.Ubuf + (size_t)cur * UB;             // U_{t+1}
+
+            // ================= phase 1: X_g = A_gg U_g, partial T = sum_g U_g^T X_g
+            double t0 = 0.0, t1 = 0.0;
+            const int e0 = 2 * tid, u1 = e0 / NU, u2 = e0 % NU;
+            for (int g = c; g < G; g += C) {
+                const int o = p.node_off[g], n = p.node_off[g + 1] - o;
+                for (int e = tid; e < n * NU; e += GAGM_THREADS) Ug[e] = __ldcg(Ul + (size_t)o * NU + e);
+                __syncthreads();
+                double acc[RPW];
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) acc[r] = 0.0;
+                rows_times_tile(p.A + (size_t)o * M + o, M, n, n, Ug, acc, warp, lane);
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) { const int row = warp + GAGM_WARPS * r; if (row < n) X[row * NU + lane] = acc[r]; }
+                __syncthreads();
+                for (int r = 0; r < n; ++r) {
+                    const double uv = Ug[r * NU + u1];
+                    t0 = fma(uv, X[r * NU + u2], t0);
+                    t1 = fma(uv, X[r * NU + u2 + 1], t1);
+                }
+                __syncthreads();
+            }
+            p.Tpart[(size_t)c * NU * NU + e0] = t0;
+            p.Tpart[(size_t)c * NU * NU + e0 + 1] = t1;
+            __threadfence();
+            cluster_sync_all();
+
+            // ================= phase 2
+            {
+                double s0 = 0.0, s1 = 0.0;
+                for (int cc = 0; cc < C; ++cc) {
+                    s0 += __ldcg(p.Tpart + (size_t)cc * NU * NU + e0);
+                    s1 += __ldcg(p.Tpart + (size_t)cc * NU * NU + e0 + 1);
+                }
+                T[e0] = s0; T[e0 + 1] = s1;
+            }
+            double d1 = 0.0, d2 = 0.0;
+            for (int g = c; g < G; g += C) {
+                const int o = p.node_off[g], n = p.node_off[g + 1] - o;
+                for (int e = tid; e < n * NU; e += GAGM_THREADS) Ug[e] = __ldcg(Ul + (size_t)o * NU + e);
+                __syncthreads();                                   // also publishes T
+                // Q = U_g T
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) {
+                    const int row = warp + GAGM_WARPS * r;
+                    if (row < n) {
+                        double q = 0.0;
+                        for (int v = 0; v < NU; ++v) q = fma(Ug[row * NU + v], T[v * NU + lane], q);
+                        X[row * NU + lane] = q;
+                    }
+                }
+                __syncthreads();
+                // V1 = A_gg Q
+                double v1[RPW], v2[RPW];
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) { v1[r] = 0.0; v2[r] = 0.0; }
+                rows_times_tile(p.A + (size_t)o * M + o, M, n, n, X, v1, warp, lane);
+                // V2 = W[g rows, :] U   (tile by graph h)
+                for (int h = 0; h < G; ++h) {
+                    const int oh = p.node_off[h], nh = p.node_off[h + 1] - oh;
+                    const double *Us;
+                    if (h == g) Us = Ug;
+                    else {
+                        __syncthreads();                           // previous tile fully consumed
+                        for (int e = tid; e < nh * NU; e += GAGM_THREADS) Uo[e] = __ldcg(Ul + (size_t)oh * NU + e);
+                        __syncthreads();
+                        Us = Uo;
+                    }
+                    rows_times_tile(p.W + (size_t)o * M + oh, M, n, nh, Us, v2, warp, lane);
+                }
+                // V = (V1 * qw * 2 + V2) / G
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) {
+                    const int row = warp + GAGM_WARPS * r;
+                    if (row < n) {
+                        const double v = (v1[r] * p.quad_weight * 2.0 + v2[r]) / (double)G;
+                        Z[row * ZP + lane] = projector == 0 ? v / tau : v;
+                    }
+                }
+                __syncthreads();
+                // ---- projector -> U_new_g in Ug
+                if (projector == 0) {
+                    const bool tr = n > NU;                        // working matrix = transpose (rows = universe)
+                    const int nr = tr ? NU : n, nq = tr ? n : NU;
+                    const int ldr = tr ? 1 : ZP, ldq = tr ? ZP : 1;
+                    const int mult = nq - nr;                      // dummy_row = True (mgm:333-349)
+                    for (int q = tid; q < nq; q += GAGM_THREADS) padv[q] = -100.0;
+                    __syncthreads();
+                    for (int k = 0; k < p.sk_iter; ++k) {
+                        sinkhorn_step(Z, ldr, ldq, nr, nq, padv, mult, k, nullptr, warp, GAGM_WARPS, lane);
+                        __syncthreads();
+                    }
+                    for (int e = tid; e < n * NU; e += GAGM_THREADS) Ug[e] = exp(Z[(e / NU) * ZP + (e % NU)]);
+                } else {
+                    for (int e = tid; e < n * NU; e += GAGM_THREADS) Ug[e] = 0.0;
+                    __syncthreads();
+                    if (warp == 0) {
+                        const double *Zc = Z;
+                        if (n <= NU) {
+                            lap_solve_warp(n, NU, [=](int i, int j) { return -Zc[i * ZP + j]; }, *lapw);
+                            for (int i = lane; i < n; i += 32) Ug[i * NU + lapw->col4row[i]] = 1.0;
+                        } else {
+                            lap_solve_warp(NU, n, [=](int i, int j) { return -Zc[j * ZP + i]; }, *lapw);
+                            for (int i = lane; i < NU; i += 32) Ug[lapw->col4row[i] * NU + i] = 1.0;
+                        }
+                    }
+                }
+                __syncthreads();
+                if (G == 2 && g == 0) {                            // mgm:358-359
+                    for (int e = tid; e < n * NU; e += GAGM_THREADS) Ug[e] = (e / NU == e % NU) ? 1.0 : 0.0;
+                    __syncthreads();
+                }
+                for (int e = tid; e < n * NU; e += GAGM_THREADS) {
+                    const double un = Ug[e];
+                    const double a = un - __ldcg(Ul + (size_t)o * NU + e);
+                    const double b = un - __ldcg(Ul2 + (size_t)o * NU + e);
+                    d1 = fma(a, a, d1);
+                    d2 = fma(b, b, d2);
+                    Un[(size_t)o * NU + e] = un;
+                }
+                __syncthreads();
+            }
+            d1 = warp_sum(d1); d2 = warp_sum(d2);
+            if (lane == 0) { red[warp] = d1; red[GAGM_WARPS + warp] = d2; }
+            __syncthreads();
+            if (tid == 0) {
+                double a = 0.0, b = 0.0;
+                for (int w = 0; w < GAGM_WARPS; ++w) { a += red[w]; b += red[GAGM_WARPS + w]; }
+                p.normpart[2 * c] = a; p.normpart[2 * c + 1] = b;
+            }
+            __threadfence();
+            cluster_sync_all();
+            double n1 = 0.0, n2 = 0.0;
+            for (int cc = 0; cc < C; ++cc) { n1 += __ldcg(p.normpart + 2 * cc); n2 += __ldcg(p.normpart + 2 * cc + 1); }
+            ++it_total;
+            if (projector == 0) ++it_sk; else { ++it_hg; n_lap += G; }
+            if (p.mode == 1) { stop_all = true; break; }
+            if (sqrt(n1) < p.tol || n2 == 0.0) break;              // mgm:361
+        }
+        if (stop_all) break;
+        // projection control (mgm:373-383); "not converged" with hung_iter is a no-op (mgm:364-366)
+        if (projector == 1) break;
+        ++n_stage;
+        if (tau > p.min_tau) tau *= p.sk_gamma;
+        else projector = 1;
+    }
+
+    const double *Uf = p.Ubuf + (size_t)cur * UB;
+    for (int g = c; g < G; g += C) {
+        const int o = p.node_off[g], n = p.node_off[g + 1] - o;
+        for (int e = tid; e < n * NU; e += GAGM_THREADS) p.U_out[(size_t)o * NU + e] = (float)Uf[(size_t)o * NU + e];
+    }
+    if (c == 0 && tid == 0 && p.info) {
+        p.info[0] = it_total; p.info[1] = it_sk; p.info[2] = it_hg; p.info[3] = n_lap; p.info[4] = n_stage;
+        p.info[5] = 0; p.info[6] = 0; p.info[7] = 0;
+    }
+}
+
+static size_t gagm_smem_bytes() {
+    return (size_t)(3 * GAGM_MAX_N * NU + GAGM_MAX_N * ZP + NU * NU + GAGM_MAX_N + 2 * GAGM_WARPS) * sizeof(double) +
+           sizeof(LapWork) + 16;
+}
+
+}  // namespace ttdg
+
+using namespace ttdg;
+
+extern "C" int64_t ttdg_gagm_scratch_bytes(int M, int G) {
+    (void)G;
+    return (int64_t)(3 * (int64_t)M * NU + GAGM_MAX_C * NU * NU + 2 * GAGM_MAX_C) * (int64_t)sizeof(double);
+}
+
+extern "C" int ttdg_gagm_solve(const float *A, const float *W, const float *U0, const int32_t *ms_h, int G, int M,
+                               int n_univ, double init_tau, double min_tau, double sk_gamma, int max_iter, int sk_iter,
+                               double converge_tol, double quad_weight, int mode, int step_projector, float *U,
+                               int32_t *info, void *scratch, void *stream) {
+    TTDG_CHECK_ARG(A && W && U0 && ms_h && U && scratch && G >= 1 && M >= 1 && max_iter >= 1 && sk_iter >= 0);
+    TTDG_CHECK_ARG(init_tau > 0 && (mode == 0 || mode == 1) && (step_projector == 0 || step_projector == 1));
+    if (n_univ != NU || G > GAGM_MAX_G) return TTDG_E_LIMIT;
+    GagmParams p;
+    p.A = A; p.W = W; p.U0 = U0; p.U_out = U; p.info = info;
+    p.G = G; p.M = M; p.C = G < GAGM_MAX_C ? G : GAGM_MAX_C;
+    p.node_off[0] = 0;
+    for (int g = 0; g < G; ++g) {
+        if (ms_h[g] < 1 || ms_h[g] > GAGM_MAX_N) return TTDG_E_LIMIT;
+        p.node_off[g + 1] = p.node_off[g] + ms_h[g];
+    }
+    if (p.node_off[G] != M) return TTDG_E_ARG;
+    p.Ubuf = reinterpret_cast<double *>(scratch);
+    p.Tpart = p.Ubuf + 3 * (size_t)M * NU;
+    p.normpart = p.Tpart + GAGM_MAX_C * NU * NU;
+    p.init_tau = init_tau; p.min_tau = min_tau; p.sk_gamma = sk_gamma; p.tol = converge_tol; p.quad_weight = quad_weight;
+    p.max_iter = max_iter; p.sk_iter = sk_iter; p.mode = mode; p.step_projector = step_projector;
+
+    const size_t smem = gagm_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(gagm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.C);
+    cfg.blockDim = dim3(GAGM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, gagm_kernel, p);
+    return (int)e;
+}
