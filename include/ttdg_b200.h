@@ -31,26 +31,30 @@ extern "C" {
 /* library / build info; never touches the GPU */
 int ttdg_version(void);            /* MAJOR*10000 + MINOR*100 + PATCH */
 const char *ttdg_build_info(void); /* "sm_100a nvcc 12.9 ..." */
-int ttdg_limit(const char *name);  /* "small_max_dim", "lap_max_dim", "gagm_max_graphs", "univ", "feat_dim"; -1 if unknown */
+int ttdg_limit(const char *name);
+long long ttdg_launch_count(void); /* kernels launched through this library since load (all entry points) */
+  /* "small_max_dim", "lap_max_dim", "gagm_max_graphs", "univ", "feat_dim"; -1 if unknown */
 
 /* ---------------------------------------------------------------------------------------------
  * Sinkhorn.  Replaces utils/sinkhorn.py:58-87 -> pygmtools.sinkhorn(backend='pytorch') (0.3.8).
  * Per-item semantics: the stored n1 x n2 matrix is worked on in the orientation
- * with rows <= cols (transposed when n2 < n1); divided by tau; if dummy_row the (cols-rows) missing rows
+ * with rows <= cols (transposed when n2 < n1; a SQUARE item is transposed iff flag bit 0 is set - pygmtools
+ * transposes a whole padded batch when its padded shape is tall, and only re-transposes the items that are
+ * strictly wide, so square items inherit the batch orientation); divided by tau; if dummy_row the (cols-rows) missing rows
  * are filled with -100; `max_iter` alternating normalisations (even = each row over its columns, odd =
  * each column over its rows); exp; written back in the stored orientation.
  * --------------------------------------------------------------------------------------------- */
 
 /* Small matrices (n1, n2 <= ttdg_limit("small_max_dim")): one CTA per item, matrix resident in shared
- * memory, fp64 internal.  items: int64[n_items][8] =
- *   { s_off, out_off, mirror_off, n1, n2, ld_s, ld_out, ld_mirror }   (element offsets / leading dims)
+ * memory, fp64 internal.  items: int64[n_items][9] =
+ *   { s_off, out_off, mirror_off, n1, n2, ld_s, ld_out, ld_mirror, flags }   (element offsets / leading dims)
  * out receives the n1 x n2 result at out_off; if mirror_off >= 0 its TRANSPOSE (n2 x n1) is also written
  * at mirror_off (MGM3_unsup stores both Wds[src,tgt] and Wds[tgt,src], mgm:523-525).
  * max_dim: host-known upper bound of every n1, n2 (sizes the shared memory; items above it are skipped). */
 int ttdg_sinkhorn_small_fwd(const float *s, float *out, const int64_t *items, int n_items, int max_dim,
                             double tau, int max_iter, int dummy_row, void *stream);
-/* Backward: grad_in = d(sum(out * grad_out)) / d s.  Recomputes the forward in-kernel.  items: int64[n][8] =
- *   { s_off, gout_off, gin_off, n1, n2, ld_s, ld_gout, ld_gin }. */
+/* Backward: grad_in = d(sum(out * grad_out)) / d s.  Recomputes the forward in-kernel.  items: int64[n][9] =
+ *   { s_off, gout_off, gin_off, n1, n2, ld_s, ld_gout, ld_gin, flags }. */
 int ttdg_sinkhorn_small_bwd(const float *s, const float *grad_out, float *grad_in, const int64_t *items,
                             int n_items, int max_dim, double tau, int max_iter, int dummy_row, void *stream);
 
@@ -135,12 +139,15 @@ int ttdg_gemm_f64acc(int transA, int transB, int m, int n, int k, const void *A,
  * info (int32[8], device): {iterations, sinkhorn-stage iterations, hungarian-stage iterations, LAP calls,
  *                           sinkhorn stages, 0, 0, 0}.
  * scratch: ttdg_gagm_scratch_bytes(M, G).
+ * trace (optional, may be NULL): fp64[(trace_cap + 1)][M][32] receives U_t of every iteration t <= trace_cap
+ * (U_0 = U0) and trace_meta fp64[trace_cap][2] = {projector, tau} - lets a test verify EVERY iteration of the
+ * trajectory against the oracle's single step (the trajectory as a whole is chaotic).
  * --------------------------------------------------------------------------------------------- */
 int64_t ttdg_gagm_scratch_bytes(int M, int G);
 int ttdg_gagm_solve(const float *A, const float *W, const float *U0, const int32_t *ms_h, int G, int M,
                     int n_univ, double init_tau, double min_tau, double sk_gamma, int max_iter, int sk_iter,
                     double converge_tol, double quad_weight, int mode, int step_projector, float *U,
-                    int32_t *info, void *scratch, void *stream);
+                    int32_t *info, void *scratch, double *trace, double *trace_meta, int trace_cap, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Matching loss.  Replaces collect_intra_class_matching_wrapper + the 'perm' loss loop (mgm:543-564,
@@ -186,6 +193,15 @@ int ttdg_sampler_gather(const float *const *feat_ptrs_h, const int64_t *feat_str
 int ttdg_sampler_scatter_bwd(const float *grad_nodes, float *const *gfeat_ptrs_h, const int64_t *feat_strides_h,
                              const int32_t *lvl_hw_h, int B, int C, int n_total, const int32_t *sel_idx,
                              int max_per_level, const int32_t *node_off, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused SGD step over one flat fp32 bucket.  Replaces the torch.optim.SGD the caller steps at
+ * engine/trainer.py:480-482 (Detectron2 build_optimizer: momentum 0.9, weight decay 1e-4, lr from
+ * configs/test_segment.yaml:28):  g = grad_scale * g + wd * p;  m = first_step ? g : momentum * m + g;
+ * p -= lr * m.  grad_scale carries the 1 / world_size of the gradient all-reduce.  p, g, m 16-byte aligned.
+ * --------------------------------------------------------------------------------------------- */
+int ttdg_sgd_step(float *p, const float *g, float *m, int64_t n, float lr, float momentum, float weight_decay,
+                  float grad_scale, int first_step, void *stream);
 
 #ifdef __cplusplus
 }

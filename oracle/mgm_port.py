@@ -141,7 +141,7 @@ def gagm(A, W, U0, ms, n_univ, init_tau=0.1, min_tau=1e-2, max_iter=200, sk_iter
 
 # ---------------------------------------------------------------- MGM3_unsup.forward
 def mgm3_unsup_forward(sd, nodes, labels, U_univ, keep_masks=None, univ_size=32, quad_weight=0.5,
-                       return_aux=False, precise=False):
+                       return_aux=False, precise=False, U_override=None):
     """multi_graph_matching.py:487-569.  ``nodes``: list of n_i x 256 (may require grad);
     ``labels`` unused by the loss; ``U_univ``: 32 x 256."""
     if nodes is None or len(nodes) == 1:
@@ -150,13 +150,14 @@ def mgm3_unsup_forward(sd, nodes, labels, U_univ, keep_masks=None, univ_size=32,
     G, M = len(ms), sum(ms)
     offs = np.concatenate([[0], np.cumsum(ms)]).tolist()
 
-    A = torch.zeros(M, M)
+    dt = nodes[0].dtype          # float64 inputs run the whole pipeline in float64 (noise-free gradients)
+    A = torch.zeros(M, M, dtype=dt)
     for g, x in enumerate(nodes):
         adj = attention_adjacency(sd, x, None if keep_masks is None else keep_masks[g])
         A[offs[g]:offs[g + 1], offs[g]:offs[g + 1]] += adj.reshape(ms[g], ms[g]).detach()
     A.fill_diagonal_(0)
 
-    Wds = torch.zeros(M, M)
+    Wds = torch.zeros(M, M, dtype=dt)
     for si, ti in itertools.product(range(G), repeat=2):
         if si < ti:
             continue
@@ -170,7 +171,10 @@ def mgm3_unsup_forward(sd, nodes, labels, U_univ, keep_masks=None, univ_size=32,
             Wds[offs[ti]:offs[ti + 1], offs[si]:offs[si + 1]] += ds.t()
 
     U0 = torch.cat([torch.mm(x, U_univ.t()) for x in nodes], dim=0).detach()
-    Ub = gagm(A, Wds.detach(), U0, ms, univ_size, quad_weight=quad_weight, precise=precise)
+    if U_override is not None:
+        Ub = U_override.to(dt)
+    else:
+        Ub = gagm(A, Wds.detach(), U0, ms, univ_size, quad_weight=quad_weight, precise=precise)
     Us = [Ub[offs[g]:offs[g + 1]] for g in range(G)]
 
     loss = 0
@@ -182,7 +186,7 @@ def mgm3_unsup_forward(sd, nodes, labels, U_univ, keep_masks=None, univ_size=32,
             s = Wds[offs[i2]:offs[i2 + 1], offs[i1]:offs[i1 + 1]].t()
         x_gt = torch.mm(Us[i1], Us[i2].t())
         assert torch.all((s >= 0) & (s <= 1)) and torch.all((x_gt >= 0) & (x_gt <= 1))
-        loss = loss + (torch.tensor(0.) + focal_bce(s, x_gt))
+        loss = loss + (torch.tensor(0., dtype=dt) + focal_bce(s, x_gt))
         npairs += 1
     loss = loss / npairs
     if return_aux:

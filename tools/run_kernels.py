@@ -1,0 +1,34 @@
+"""Launches individual hot kernels a few times - the target command for `ncu` captures (see profiles/README.md).
+    python tools/run_kernels.py sinkhorn_stream | gagm | mgm_step"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "ttdg-mgm_b200")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+from ttdg_b200 import ops, synth  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "sinkhorn_stream"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+dev = torch.device("cuda", 0)
+if what == "sinkhorn_stream":
+    n = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+    batch = (512 << 20) // (n * n * 4)
+    s = torch.randn(batch, n, n, device=dev)
+    out = torch.empty_like(s)
+    for _ in range(reps):
+        ops.sinkhorn_stream(s, tau=0.05, max_iter=50, out=out)
+elif what in ("gagm", "mgm_step"):
+    from adapteacher.modeling.GModule.multi_graph_matching import MGM3_unsup
+    m = MGM3_unsup(2, 32).to(dev)
+    m.load_state_dict(synth.perturb_affinity_state(synth.mgm_unsup_state(0), 0))
+    m.train()
+    sizes = (33, 34, 33, 33, 34, 33, 34, 33)
+    nodes, labels, _ = synth.mgm_inputs(sizes, 77)
+    U = synth.universe(0).to(dev)
+    for _ in range(reps):
+        loss = m([n.to(dev).requires_grad_(True) for n in nodes], [l.to(dev) for l in labels], U)
+        loss.backward()
+    print("gagm info", m.last_aux["info"].tolist())
+torch.cuda.synchronize()

@@ -36,7 +36,7 @@ class MultiHeadAttention(nn.Module):
         """Block-diagonal, zero-diagonal attention adjacency of all graphs stacked in X (mgm:496-502)."""
         p = self.dot_product_attention.dropout.p if self.training else 0.0
         A = ops.attention_adjacency(X, sizes, self.linear_q.weight, self.linear_q.bias, self.linear_k.weight,
-                                    self.linear_k.bias, keep_masks=keep_masks, p_drop=0.0 if keep_masks is not None else p,
+                                    self.linear_k.bias, keep_masks=keep_masks, p_drop=p,
                                     seed=self.philox_seed, offset=self.philox_offset)
         if keep_masks is None and p > 0:
             self.philox_offset += int(X.shape[0]) ** 2

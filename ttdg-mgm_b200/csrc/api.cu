@@ -1,6 +1,14 @@
 // api.cu - version / limits of libttdg_sm100.so (host only).
 #include "common.cuh"
 #include <string.h>
+#include <atomic>
+
+namespace ttdg {
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace ttdg
+
+extern "C" long long ttdg_launch_count(void) { return ttdg::g_launches.load(); }
 
 extern "C" int ttdg_version(void) { return 100; }   // 0.1.0
 

@@ -53,6 +53,7 @@ __device__ __forceinline__ void group_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+void count_launches(int n);      // api.cu: kernels launched through the C ABI (bench.py reports it)
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 

@@ -89,6 +89,7 @@ extern "C" int ttdg_gemm_f64acc(int transA, int transB, int m, int n, int k, con
     TTDG_CHECK_ARG(A && B && C && m >= 0 && n >= 0 && k >= 0);
     if (m == 0 || n == 0) return 0;
     dim3 grid(ceil_div(n, GT), ceil_div(m, GT));
+    ttdg::count_launches(1);
     gemm_f64acc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(transA, transB, m, n, k, A, a_is_f64, lda, B, b_is_f64, ldb,
                                                               C, c_is_f64, ldc, nullptr, accumulate);
     TTDG_LAUNCH_RET();
@@ -99,6 +100,7 @@ extern "C" int ttdg_linear_f64acc(const float *X, int ldx, const float *W, int l
     TTDG_CHECK_ARG(X && W && Y && m >= 0 && n >= 0 && k >= 0);
     if (m == 0 || n == 0) return 0;
     dim3 grid(ceil_div(n, GT), ceil_div(m, GT));
+    ttdg::count_launches(1);
     gemm_f64acc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(0, 1, m, n, k, X, 0, ldx, W, 0, ldw, Y, 0, ldy, b, 0);
     TTDG_LAUNCH_RET();
 }

@@ -37,9 +37,12 @@ struct GagmParams {
     double *Ubuf;        // 3 x M x NU
     double *Tpart;       // C x NU*NU
     double *normpart;    // C x 2
+    double *trace;       // optional: (trace_cap + 1) x M x NU, U_t of every iteration (tests)
+    double *trace_meta;  // optional: trace_cap x 2 = {projector, tau}
+    int trace_cap;
     int G, M, C;
     double init_tau, min_tau, sk_gamma, tol, quad_weight;
-    int max_iter, sk_iter, mode, step_projector;
+    int max_iter, sk_iter, mode, step_projector, sq_transposed;
     int node_off[GAGM_MAX_G + 1];
 };
 
@@ -200,7 +203,9 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                 __syncthreads();
                 // ---- projector -> U_new_g in Ug
                 if (projector == 0) {
-                    const bool tr = n > NU;                        // working matrix = transpose (rows = universe)
+                    // working matrix = transpose (rows = universe) for n > 32, and for n == 32 inside a ragged batch
+                    // whose padded shape is tall (pygmtools transposes the whole batch)
+                    const bool tr = n > NU || (n == NU && p.sq_transposed);
                     const int nr = tr ? NU : n, nq = tr ? n : NU;
                     const int ldr = tr ? 1 : ZP, ldq = tr ? ZP : 1;
                     const int mult = nq - nr;                      // dummy_row = True (mgm:333-349)
@@ -237,6 +242,10 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                     d1 = fma(a, a, d1);
                     d2 = fma(b, b, d2);
                     Un[(size_t)o * NU + e] = un;
+                    if (p.trace && it_total < p.trace_cap) {
+                        if (it_total == 0) p.trace[(size_t)o * NU + e] = __ldcg(Ul + (size_t)o * NU + e);
+                        p.trace[(size_t)(it_total + 1) * UB + (size_t)o * NU + e] = un;
+                    }
                 }
                 __syncthreads();
             }
@@ -252,6 +261,9 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
             cluster_sync_all();
             double n1 = 0.0, n2 = 0.0;
             for (int cc = 0; cc < C; ++cc) { n1 += __ldcg(p.normpart + 2 * cc); n2 += __ldcg(p.normpart + 2 * cc + 1); }
+            if (p.trace_meta && c == 0 && tid == 0 && it_total < p.trace_cap) {
+                p.trace_meta[2 * it_total] = (double)projector; p.trace_meta[2 * it_total + 1] = tau;
+            }
             ++it_total;
             if (projector == 0) ++it_sk; else { ++it_hg; n_lap += G; }
             if (p.mode == 1) { stop_all = true; break; }
@@ -293,7 +305,8 @@ extern "C" int64_t ttdg_gagm_scratch_bytes(int M, int G) {
 extern "C" int ttdg_gagm_solve(const float *A, const float *W, const float *U0, const int32_t *ms_h, int G, int M,
                                int n_univ, double init_tau, double min_tau, double sk_gamma, int max_iter, int sk_iter,
                                double converge_tol, double quad_weight, int mode, int step_projector, float *U,
-                               int32_t *info, void *scratch, void *stream) {
+                               int32_t *info, void *scratch, double *trace, double *trace_meta, int trace_cap,
+                               void *stream) {
     TTDG_CHECK_ARG(A && W && U0 && ms_h && U && scratch && G >= 1 && M >= 1 && max_iter >= 1 && sk_iter >= 0);
     TTDG_CHECK_ARG(init_tau > 0 && (mode == 0 || mode == 1) && (step_projector == 0 || step_projector == 1));
     if (n_univ != NU || G > GAGM_MAX_G) return TTDG_E_LIMIT;
@@ -306,11 +319,17 @@ extern "C" int ttdg_gagm_solve(const float *A, const float *W, const float *U0, 
         p.node_off[g + 1] = p.node_off[g] + ms_h[g];
     }
     if (p.node_off[G] != M) return TTDG_E_ARG;
+    {   // mgm:330-353: equal sizes -> plain reshape (never square-transposed); ragged -> padded batch G x max_n x 32
+        bool equal = true; int mx = 0;
+        for (int g = 0; g < G; ++g) { equal = equal && ms_h[g] == ms_h[0]; mx = ms_h[g] > mx ? ms_h[g] : mx; }
+        p.sq_transposed = (!equal && mx > NU) ? 1 : 0;
+    }
     p.Ubuf = reinterpret_cast<double *>(scratch);
     p.Tpart = p.Ubuf + 3 * (size_t)M * NU;
     p.normpart = p.Tpart + GAGM_MAX_C * NU * NU;
     p.init_tau = init_tau; p.min_tau = min_tau; p.sk_gamma = sk_gamma; p.tol = converge_tol; p.quad_weight = quad_weight;
     p.max_iter = max_iter; p.sk_iter = sk_iter; p.mode = mode; p.step_projector = step_projector;
+    p.trace = trace; p.trace_meta = trace_meta; p.trace_cap = trace ? trace_cap : 0;
 
     const size_t smem = gagm_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(gagm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -324,6 +343,7 @@ extern "C" int ttdg_gagm_solve(const float *A, const float *W, const float *U0, 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = p.C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    ttdg::count_launches(1);
     e = cudaLaunchKernelEx(&cfg, gagm_kernel, p);
     return (int)e;
 }

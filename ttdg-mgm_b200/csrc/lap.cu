@@ -28,6 +28,7 @@ extern "C" int ttdg_lap_solve(const float *s, float *perm, const int64_t *items,
     const size_t smem = sizeof(LapWork) * LAP_WARPS;
     cudaError_t e = cudaFuncSetAttribute(lap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    ttdg::count_launches(1);
     lap_kernel<<<ceil_div(n_items, LAP_WARPS), LAP_WARPS * 32, smem, (cudaStream_t)stream>>>(s, perm, items, n_items);
     TTDG_LAUNCH_RET();
 }

@@ -283,6 +283,7 @@ extern "C" int ttdg_attn_adjacency(const float *S, const int32_t *node_off, int 
     TTDG_CHECK_ARG(S && node_off && A && G >= 1 && M >= 0 && p_drop >= 0.0f && p_drop < 1.0f);
     TTDG_CHECK_ARG(!keep_mask || mask_off);
     if (M == 0) return 0;
+    ttdg::count_launches(1);
     attn_adjacency_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(S, node_off, G, M, scale, keep_mask, mask_off,
                                                                            p_drop, seed, offset, A);
     TTDG_LAUNCH_RET();
@@ -298,6 +299,7 @@ extern "C" int ttdg_affinity_hidden(const float *Xp, const float *Yp, const floa
     rc = ttdg_gemm_f64acc(0, 1, M, hidden, dim, Yp, 0, dim, w0 + dim, 0, 2 * dim, ac + hidden, 1, 2 * hidden, 0, stream);
     if (rc) return rc;
     const size_t n = (size_t)M * hidden;
+    ttdg::count_launches(1);
     affinity_bias_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ac, b0, M, hidden);
     TTDG_LAUNCH_RET();
 }
@@ -311,6 +313,7 @@ extern "C" int ttdg_affinity_pairs_fwd(const double *ac, const float *w1, const 
     cudaError_t e = cudaFuncSetAttribute(affinity_pairs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     dim3 grid(ceil_div(max_n_src, AFF_TI), n_pairs);
+    ttdg::count_launches(1);
     affinity_pairs_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(ac, w1, b1, pairs, out_off, hidden, out);
     TTDG_LAUNCH_RET();
 }
@@ -327,6 +330,7 @@ extern "C" int ttdg_affinity_pairs_bwd(const double *ac, const float *w1, const 
     TTDG_CHECK_ARG(hidden % 256 == 0 && hidden / 256 <= 4 && M >= 0 && max_n >= 0);
     if (M == 0) return 0;
     dim3 grid(M, 2);
+    ttdg::count_launches(2);
     affinity_pairs_bwd_kernel<<<grid, 256, (size_t)max_n * sizeof(float), (cudaStream_t)stream>>>(
         ac, w1, pairs, out_off, n_pairs, hidden, grad_out, g_ac, reinterpret_cast<double *>(scratch));
     cudaError_t e = cudaGetLastError();
@@ -342,6 +346,7 @@ extern "C" int ttdg_matching_loss_fwd(const float *Wds, const float *U, const in
                                       float *loss, int32_t *flags, void *scratch, void *stream) {
     TTDG_CHECK_ARG(Wds && U && node_off && loss && flags && scratch && G >= 2 && M >= 0 && n_univ > 0);
     const int npairs = G * (G - 1) / 2;
+    ttdg::count_launches(2);
     matching_loss_kernel<false><<<npairs, 256, 0, (cudaStream_t)stream>>>(Wds, U, node_off, G, M, n_univ,
                                                                          reinterpret_cast<double *>(scratch), flags, nullptr, nullptr);
     cudaError_t e = cudaGetLastError();
@@ -355,6 +360,7 @@ extern "C" int ttdg_matching_loss_bwd(const float *Wds, const float *U, const in
     TTDG_CHECK_ARG(Wds && U && node_off && grad_loss && grad_Wds && G >= 2 && M >= 0 && n_univ > 0);
     cudaError_t e = cudaMemsetAsync(grad_Wds, 0, (size_t)M * M * sizeof(float), (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
+    ttdg::count_launches(1);
     matching_loss_kernel<true><<<G * (G - 1) / 2, 256, 0, (cudaStream_t)stream>>>(Wds, U, node_off, G, M, n_univ, nullptr,
                                                                                  nullptr, grad_loss, grad_Wds);
     TTDG_LAUNCH_RET();
@@ -365,6 +371,7 @@ extern "C" int64_t ttdg_focal_bce_scratch_bytes(void) { return 1024 * 8; }
 extern "C" int ttdg_focal_bce_fwd(const float *p, const float *y, int64_t n, float *loss, void *scratch, void *stream) {
     TTDG_CHECK_ARG(p && y && loss && scratch && n > 0);
     const int nb = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);      // 4 CTAs per SM x 148
+    ttdg::count_launches(2);
     focal_bce_fwd_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(p, y, n, reinterpret_cast<double *>(scratch));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
@@ -376,6 +383,7 @@ extern "C" int ttdg_focal_bce_bwd(const float *p, const float *y, int64_t n, con
                                   void *stream) {
     TTDG_CHECK_ARG(p && y && grad_loss && grad_p && n > 0);
     const int nb = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
+    ttdg::count_launches(1);
     focal_bce_bwd_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(p, y, n, grad_loss, grad_p);
     TTDG_LAUNCH_RET();
 }

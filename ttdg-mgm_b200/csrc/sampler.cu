@@ -143,6 +143,7 @@ extern "C" int ttdg_sampler_select(const float *boxes, const int64_t *classes, c
     Pyramid pyr;
     if (make_pyramid(lvl_hw_h, pyr)) return TTDG_E_ARG;
     dim3 g1(ceil_div(pyr.base[5], 256), B);
+    ttdg::count_launches(2);
     sampler_label_kernel<<<g1, 256, 0, (cudaStream_t)stream>>>(boxes, classes, box_off, pyr, label);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
@@ -169,6 +170,7 @@ extern "C" int ttdg_sampler_gather(const float *const *feat_ptrs_h, const int64_
     Pyramid pyr;
     FeatPtrsW f;
     if (make_pyramid(lvl_hw_h, pyr) || fill_feat((const void *const *)feat_ptrs_h, feat_strides_h, f)) return TTDG_E_ARG;
+    ttdg::count_launches(1);
     sampler_gather_kernel<false><<<n_total, 256, 0, (cudaStream_t)stream>>>(f, pyr, B, C, label, sel_idx, max_per_level,
                                                                            node_off, nodes, labels_out);
     TTDG_LAUNCH_RET();
@@ -182,6 +184,7 @@ extern "C" int ttdg_sampler_scatter_bwd(const float *grad_nodes, float *const *g
     Pyramid pyr;
     FeatPtrsW f;
     if (make_pyramid(lvl_hw_h, pyr) || fill_feat((const void *const *)gfeat_ptrs_h, feat_strides_h, f)) return TTDG_E_ARG;
+    ttdg::count_launches(1);
     sampler_gather_kernel<true><<<n_total, 256, 0, (cudaStream_t)stream>>>(f, pyr, B, C, nullptr, sel_idx, max_per_level,
                                                                           node_off, const_cast<float *>(grad_nodes), nullptr);
     TTDG_LAUNCH_RET();

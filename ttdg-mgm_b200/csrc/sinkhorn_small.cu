@@ -9,13 +9,14 @@ namespace ttdg {
 constexpr int SK_SMALL_MAX = 96;        // graphs have <= 95 nodes (19 per level x 5 levels, build_graph.py:189-195)
 constexpr int SK_THREADS = 256;
 
-struct SkItem { long long a_off, b_off, c_off; int n1, n2, lda, ldb, ldc; };
+struct SkItem { long long a_off, b_off, c_off; int n1, n2, lda, ldb, ldc, flags; };
+constexpr int SK_ITEM_FIELDS = 9;
 
 __device__ __forceinline__ SkItem load_item(const int64_t *items, int b) {
-    const int64_t *d = items + (size_t)b * 8;
+    const int64_t *d = items + (size_t)b * SK_ITEM_FIELDS;
     SkItem it;
     it.a_off = d[0]; it.b_off = d[1]; it.c_off = d[2];
-    it.n1 = (int)d[3]; it.n2 = (int)d[4]; it.lda = (int)d[5]; it.ldb = (int)d[6]; it.ldc = (int)d[7];
+    it.n1 = (int)d[3]; it.n2 = (int)d[4]; it.lda = (int)d[5]; it.ldb = (int)d[6]; it.ldc = (int)d[7]; it.flags = (int)d[8];
     return it;
 }
 
@@ -26,7 +27,7 @@ sinkhorn_small_fwd_kernel(const float *__restrict__ s, float *__restrict__ out, 
     const SkItem it = load_item(items, blockIdx.x);
     const int n1 = it.n1, n2 = it.n2;
     if (n1 <= 0 || n2 <= 0 || n1 > max_dim || n2 > max_dim) return;
-    const bool tr = n2 < n1;
+    const bool tr = n2 < n1 || (n1 == n2 && (it.flags & 1));
     const int nr = tr ? n2 : n1, nq = tr ? n1 : n2;
     const int pitch = nq | 1;
     double *z = smem;
@@ -67,7 +68,7 @@ sinkhorn_small_bwd_kernel(const float *__restrict__ s, const float *__restrict__
     const SkItem it = load_item(items, blockIdx.x);
     const int n1 = it.n1, n2 = it.n2;
     if (n1 <= 0 || n2 <= 0 || n1 > max_dim || n2 > max_dim) return;
-    const bool tr = n2 < n1;
+    const bool tr = n2 < n1 || (n1 == n2 && (it.flags & 1));
     const int nr = tr ? n2 : n1, nq = tr ? n1 : n2;
     const int pitch = nq | 1;
     double *z = smem;
@@ -125,6 +126,7 @@ extern "C" int ttdg_sinkhorn_small_fwd(const float *s, float *out, const int64_t
     const size_t smem = fwd_smem(max_dim);
     cudaError_t e = cudaFuncSetAttribute(sinkhorn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(SK_SMALL_MAX));
     if (e != cudaSuccess) return (int)e;
+    ttdg::count_launches(1);
     sinkhorn_small_fwd_kernel<<<n_items, SK_THREADS, smem, (cudaStream_t)stream>>>(s, out, items, tau, max_iter, dummy_row, max_dim);
     TTDG_LAUNCH_RET();
 }
@@ -138,6 +140,7 @@ extern "C" int ttdg_sinkhorn_small_bwd(const float *s, const float *grad_out, fl
     if (smem > 227 * 1024) return TTDG_E_LIMIT;
     cudaError_t e = cudaFuncSetAttribute(sinkhorn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    ttdg::count_launches(1);
     sinkhorn_small_bwd_kernel<<<n_items, SK_THREADS, smem, (cudaStream_t)stream>>>(s, grad_out, grad_in, items, tau,
                                                                                   max_iter, dummy_row, max_dim);
     TTDG_LAUNCH_RET();

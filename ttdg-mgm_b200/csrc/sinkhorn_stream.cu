@@ -17,9 +17,8 @@ namespace cg = cooperative_groups;
 
 namespace ttdg {
 
-constexpr int SKS_THREADS = 1024;
+constexpr int SKS_THREADS = 512;        // 16 warps: 128 registers per thread for the register-resident row
 constexpr int SKS_WARPS = SKS_THREADS / 32;
-constexpr int SKS_SLAB_BYTES = 192 * 1024;
 
 struct SksParams {
     const float *s;
@@ -29,7 +28,12 @@ struct SksParams {
 };
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float max4(const float4 &v) { return fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)); }
 
+// Everything lives in the log2 domain: slab = x * log2(e) / tau, potentials f, g in log2 units, exp = ex2.approx
+// (one MUFU op, no multiply), out = 2^(t - f - g).
 __global__ void __launch_bounds__(SKS_THREADS, 1)
 sinkhorn_stream_kernel(const SksParams p) {
     cg::cluster_group cluster = cg::this_cluster();
@@ -37,27 +41,28 @@ sinkhorn_stream_kernel(const SksParams p) {
     const int cid = blockIdx.x / p.R, ncl = gridDim.x / p.R;
     extern __shared__ __align__(16) unsigned char sks_smem[];
     const int n2 = p.n2;
-    float *slab = reinterpret_cast<float *>(sks_smem);            // res_rows x n2 (already scaled by 1/tau)
+    float *slab = reinterpret_cast<float *>(sks_smem);            // res_rows x n2 (scaled)
     float *g = slab + (size_t)p.res_rows * n2;                    // n2      column potentials (replicated per CTA)
-    float *f = g + n2;                                            // rows_per_cta
-    float *cm = f + p.rows_per_cta;                               // n2      this CTA's partial column max
+    float *f = g + n2;                                            // rows_per_cta (padded to a multiple of 4)
+    float *cm = f + ((p.rows_per_cta + 3) & ~3);                  // n2      this CTA's partial column max
     float *cs = cm + n2;                                          // n2      this CTA's partial column sum
     float *pm = cs + n2;                                          // RG x n2 per-row-group partials
-    const int CW = n2 < SKS_THREADS ? n2 : SKS_THREADS;           // threads across columns in the column step
+    const int n2q = n2 >> 2;                                      // float4 columns
+    const int CW = n2q < SKS_THREADS ? n2q : SKS_THREADS;         // threads across float4 columns in the column step
     const int RG = SKS_THREADS / CW;                              // row groups
     float *ps = pm + (size_t)RG * n2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = r * p.rows_per_cta;
     const int nrows = max(0, min(p.rows_per_cta, p.n1 - row0));
     const int cols_per_cta = (n2 + p.R - 1) / p.R;
+    const float sc = p.inv_tau;                                   // log2(e) / tau
 
     for (int b = cid; b < p.batch; b += ncl) {
         const float *x = p.s + (size_t)b * p.n1 * n2 + (size_t)row0 * n2;
-        // ---- load the resident slab (scaled)
         const int nres = min(nrows, p.res_rows);
         for (int e = tid * 4; e < nres * n2; e += SKS_THREADS * 4) {
             float4 v = ld4(x + e);
-            v.x *= p.inv_tau; v.y *= p.inv_tau; v.z *= p.inv_tau; v.w *= p.inv_tau;
+            v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
             *reinterpret_cast<float4 *>(slab + e) = v;
         }
         for (int j = tid; j < n2; j += SKS_THREADS) g[j] = 0.f;
@@ -66,43 +71,70 @@ sinkhorn_stream_kernel(const SksParams p) {
 
         for (int it = 0; it < p.max_iter; ++it) {
             if ((it & 1) == 0) {
-                // ---------------- row step: f_i = lse_j (t_ij - g_j), warp per row
+                // ---------------- row step: f_i = lse_j (t_ij - g_j); warp per row, the row is held in registers
                 for (int i = warp; i < nrows; i += SKS_WARPS) {
                     const bool res = i < p.res_rows;
                     const float *row = res ? slab + (size_t)i * n2 : x + (size_t)i * n2;
-                    const float sc = res ? 1.f : p.inv_tau;
-                    float m = -INFINITY;
-                    for (int j = lane * 4; j < n2; j += 128) {
-                        const float4 v = ld4(row + j), gv = ld4(g + j);
-                        m = fmaxf(m, fmaxf(fmaxf(v.x * sc - gv.x, v.y * sc - gv.y), fmaxf(v.z * sc - gv.z, v.w * sc - gv.w)));
-                    }
-                    m = warp_max(m);
-                    float sum = 0.f;
-                    for (int j = lane * 4; j < n2; j += 128) {
-                        const float4 v = ld4(row + j), gv = ld4(g + j);
-                        sum += __expf(v.x * sc - gv.x - m) + __expf(v.y * sc - gv.y - m) + __expf(v.z * sc - gv.z - m) +
-                               __expf(v.w * sc - gv.w - m);
+                    const float rs = res ? 1.f : sc;
+                    float m = -INFINITY, sum = 0.f;
+                    if (n2 <= 1024) {
+                        float4 v[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const int j = c * 128 + lane * 4;
+                            if (j < n2) {
+                                const float4 t = ld4(row + j), gv = ld4(g + j);
+                                v[c] = make_float4(fmaf(t.x, rs, -gv.x), fmaf(t.y, rs, -gv.y), fmaf(t.z, rs, -gv.z), fmaf(t.w, rs, -gv.w));
+                                m = fmaxf(m, max4(v[c]));
+                            }
+                        }
+                        m = warp_max(m);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (c * 128 + lane * 4 < n2) sum += ex2(v[c].x - m) + ex2(v[c].y - m) + ex2(v[c].z - m) + ex2(v[c].w - m);
+                    } else {
+                        for (int j = lane * 4; j < n2; j += 128) {
+                            const float4 t = ld4(row + j), gv = ld4(g + j);
+                            m = fmaxf(m, fmaxf(fmaxf(fmaf(t.x, rs, -gv.x), fmaf(t.y, rs, -gv.y)), fmaxf(fmaf(t.z, rs, -gv.z), fmaf(t.w, rs, -gv.w))));
+                        }
+                        m = warp_max(m);
+                        for (int j = lane * 4; j < n2; j += 128) {
+                            const float4 t = ld4(row + j), gv = ld4(g + j);
+                            sum += ex2(fmaf(t.x, rs, -gv.x) - m) + ex2(fmaf(t.y, rs, -gv.y) - m) + ex2(fmaf(t.z, rs, -gv.z) - m) +
+                                   ex2(fmaf(t.w, rs, -gv.w) - m);
+                        }
                     }
                     sum = warp_sum(sum);
-                    if (lane == 0) f[i] = m + __logf(sum);
+                    if (lane == 0) f[i] = m + lg2(sum);
                 }
                 __syncthreads();
             } else {
-                // ---------------- column step: partial (max, sum) over this CTA's rows
+                // ---------------- column step: partial (max, sum) over this CTA's rows; a thread owns 4 columns
                 const int cx = tid % CW, ry = tid / CW;
-                for (int j = cx; j < n2; j += CW) {
-                    float m = -INFINITY;
+                if (ry < RG) for (int jq = cx; jq < n2q; jq += CW) {
+                    const int j = jq * 4;
+                    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll 4
                     for (int i = ry; i < nrows; i += RG) {
-                        const float t = i < p.res_rows ? slab[(size_t)i * n2 + j] : __ldg(x + (size_t)i * n2 + j) * p.inv_tau;
-                        m = fmaxf(m, t - f[i]);
+                        const bool res = i < p.res_rows;
+                        const float4 t = ld4((res ? slab : x) + (size_t)i * n2 + j);
+                        const float rs = res ? 1.f : sc, fi = f[i];
+                        m.x = fmaxf(m.x, fmaf(t.x, rs, -fi)); m.y = fmaxf(m.y, fmaf(t.y, rs, -fi));
+                        m.z = fmaxf(m.z, fmaf(t.z, rs, -fi)); m.w = fmaxf(m.w, fmaf(t.w, rs, -fi));
                     }
-                    float sum = 0.f;
-                    if (m > -INFINITY)
+                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (nrows > ry) {
+#pragma unroll 4
                         for (int i = ry; i < nrows; i += RG) {
-                            const float t = i < p.res_rows ? slab[(size_t)i * n2 + j] : __ldg(x + (size_t)i * n2 + j) * p.inv_tau;
-                            sum += __expf(t - f[i] - m);
+                            const bool res = i < p.res_rows;
+                            const float4 t = ld4((res ? slab : x) + (size_t)i * n2 + j);
+                            const float rs = res ? 1.f : sc, fi = f[i];
+                            sum.x += ex2(fmaf(t.x, rs, -fi) - m.x); sum.y += ex2(fmaf(t.y, rs, -fi) - m.y);
+                            sum.z += ex2(fmaf(t.z, rs, -fi) - m.z); sum.w += ex2(fmaf(t.w, rs, -fi) - m.w);
                         }
-                    pm[(size_t)ry * n2 + j] = m; ps[(size_t)ry * n2 + j] = sum;
+                    }
+                    *reinterpret_cast<float4 *>(pm + (size_t)ry * n2 + j) = m;
+                    *reinterpret_cast<float4 *>(ps + (size_t)ry * n2 + j) = sum;
                 }
                 __syncthreads();
                 for (int j = tid; j < n2; j += SKS_THREADS) {
@@ -110,7 +142,7 @@ sinkhorn_stream_kernel(const SksParams p) {
                     for (int q = 1; q < RG; ++q) m = fmaxf(m, pm[(size_t)q * n2 + j]);
                     float sum = 0.f;
                     if (m > -INFINITY)
-                        for (int q = 0; q < RG; ++q) sum += ps[(size_t)q * n2 + j] * __expf(pm[(size_t)q * n2 + j] - m);
+                        for (int q = 0; q < RG; ++q) sum += ps[(size_t)q * n2 + j] * ex2(pm[(size_t)q * n2 + j] - m);
                     cm[j] = m; cs[j] = sum;
                 }
                 cluster.sync();                                    // partials of every CTA are published
@@ -119,32 +151,38 @@ sinkhorn_stream_kernel(const SksParams p) {
                     const int j = r * cols_per_cta + jj;
                     if (j < n2) {
                         float m = -INFINITY;
-                        float mq[16], sq[16];
-                        for (int q = 0; q < p.R; ++q) {
-                            mq[q] = *cluster.map_shared_rank(cm + j, q);
-                            sq[q] = *cluster.map_shared_rank(cs + j, q);
-                            m = fmaxf(m, mq[q]);
-                        }
+                        float mq[8], sq[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (q < p.R) {
+                                mq[q] = *cluster.map_shared_rank(cm + j, q);
+                                sq[q] = *cluster.map_shared_rank(cs + j, q);
+                                m = fmaxf(m, mq[q]);
+                            }
                         float sum = 0.f;
-                        for (int q = 0; q < p.R; ++q) sum += sq[q] * __expf(mq[q] - m);
-                        const float gj = m + __logf(sum);
-                        for (int q = 0; q < p.R; ++q) *cluster.map_shared_rank(g + j, q) = gj;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (q < p.R && mq[q] > -INFINITY) sum += sq[q] * ex2(mq[q] - m);
+                        const float gj = m + lg2(sum);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (q < p.R) *cluster.map_shared_rank(g + j, q) = gj;
                     }
                 }
                 cluster.sync();                                    // new g visible everywhere
             }
         }
-        // ---- out = exp(t - f - g)
+        // ---- out = 2^(t - f - g)
         float *o = p.out + (size_t)b * p.n1 * n2 + (size_t)row0 * n2;
         for (int e = tid * 4; e < nrows * n2; e += SKS_THREADS * 4) {
             const int i = e / n2, j = e - i * n2;
             float4 v;
             if (i < p.res_rows) v = *reinterpret_cast<const float4 *>(slab + e);
-            else { v = ld4(x + e); v.x *= p.inv_tau; v.y *= p.inv_tau; v.z *= p.inv_tau; v.w *= p.inv_tau; }
+            else { v = ld4(x + e); v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
             const float4 gv = ld4(g + j);
             const float fi = f[i];
-            v.x = __expf(v.x - fi - gv.x); v.y = __expf(v.y - fi - gv.y); v.z = __expf(v.z - fi - gv.z); v.w = __expf(v.w - fi - gv.w);
-            *reinterpret_cast<float4 *>(o + e) = v;
+            v.x = ex2(v.x - fi - gv.x); v.y = ex2(v.y - fi - gv.y); v.z = ex2(v.z - fi - gv.z); v.w = ex2(v.w - fi - gv.w);
+            __stcs(reinterpret_cast<float4 *>(o + e), v);
         }
         __syncthreads();
     }
@@ -152,15 +190,20 @@ sinkhorn_stream_kernel(const SksParams p) {
 }
 
 static void sks_plan(int n1, int n2, SksParams &p, size_t &smem) {
-    int R = 8;
+    int R = 8;                       // portable cluster size; 148 SMs hold up to 18 clusters of 8
     while (R > 1 && n1 / R < 32) R >>= 1;
     p.R = R;
     p.rows_per_cta = (n1 + R - 1) / R;
-    int res = SKS_SLAB_BYTES / (n2 * (int)sizeof(float));
+    int res = 226 * 1024 / (n2 * (int)sizeof(float));
     p.res_rows = res < p.rows_per_cta ? res : p.rows_per_cta;
-    const int CW = n2 < SKS_THREADS ? n2 : SKS_THREADS;
+    const int n2q = n2 / 4;
+    const int CW = n2q < SKS_THREADS ? n2q : SKS_THREADS;
     const int RG = SKS_THREADS / CW;
-    smem = ((size_t)p.res_rows * n2 + n2 + p.rows_per_cta + 2 * (size_t)n2 + 2 * (size_t)RG * n2) * sizeof(float);
+    auto need = [&](int res_rows) {
+        return ((size_t)res_rows * n2 + n2 + ((p.rows_per_cta + 3) & ~3) + 2 * (size_t)n2 + 2 * (size_t)RG * n2) * sizeof(float);
+    };
+    while (p.res_rows > 0 && need(p.res_rows) > 226 * 1024) --p.res_rows;      // bookkeeping arrays share the 227 KB
+    smem = need(p.res_rows);
 }
 
 }  // namespace ttdg
@@ -182,7 +225,7 @@ extern "C" int ttdg_sinkhorn_stream_fwd(const float *s, float *out, int batch, i
     size_t smem;
     sks_plan(n1, n2, p, smem);
     if (smem > 227 * 1024) return TTDG_E_LIMIT;
-    p.s = s; p.out = out; p.batch = batch; p.n1 = n1; p.n2 = n2; p.max_iter = max_iter; p.inv_tau = 1.0f / tau;
+    p.s = s; p.out = out; p.batch = batch; p.n1 = n1; p.n2 = n2; p.max_iter = max_iter; p.inv_tau = 1.4426950408889634f / tau;     // log2(e) / tau
     cudaError_t e = cudaFuncSetAttribute(sinkhorn_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     cudaLaunchConfig_t cfg = {};
@@ -199,6 +242,7 @@ extern "C" int ttdg_sinkhorn_stream_fwd(const float *s, float *out, int batch, i
     if (e != cudaSuccess || max_clusters < 1) { cudaGetLastError(); max_clusters = 148 / p.R; }
     const int ncl = batch < max_clusters ? batch : max_clusters;
     cfg.gridDim = dim3(ncl * p.R);
+    ttdg::count_launches(1);
     e = cudaLaunchKernelEx(&cfg, sinkhorn_stream_kernel, p);
     return (int)e;
 }

@@ -17,6 +17,8 @@ SIGNATURES = {
     "ttdg_version": (c_int, []),
     "ttdg_build_info": (c_char_p, []),
     "ttdg_limit": (c_int, [c_char_p]),
+    "ttdg_launch_count": (ctypes.c_longlong, []),
+    "ttdg_sgd_step": (c_int, [P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, P]),
     "ttdg_sinkhorn_small_fwd": (c_int, [P, P, P, c_int, c_int, c_double, c_int, c_int, P]),
     "ttdg_sinkhorn_small_bwd": (c_int, [P, P, P, P, c_int, c_int, c_double, c_int, c_int, P]),
     "ttdg_sinkhorn_stream_scratch_bytes": (c_int64, [c_int, c_int, c_int]),
@@ -32,7 +34,7 @@ SIGNATURES = {
     "ttdg_affinity_pairs_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, c_int64, P, P, P, P, P]),
     "ttdg_gagm_scratch_bytes": (c_int64, [c_int, c_int]),
     "ttdg_gagm_solve": (c_int, [P, P, P, P, c_int, c_int, c_int, c_double, c_double, c_double, c_int, c_int, c_double,
-                                c_double, c_int, c_int, P, P, P, P]),
+                                c_double, c_int, c_int, P, P, P, P, P, c_int, P]),
     "ttdg_matching_loss_scratch_bytes": (c_int64, [c_int]),
     "ttdg_matching_loss_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P]),
     "ttdg_matching_loss_bwd": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P]),

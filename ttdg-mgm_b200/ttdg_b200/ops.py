@@ -77,7 +77,8 @@ def _items_dense(batch, n1s, n2s, N1, N2, with_third=True):
     rows = []
     for b in range(batch):
         off = b * N1 * N2
-        rows.append([off, off, -1 if with_third else off, int(n1s[b]), int(n2s[b]), N2, N2, N2])
+        # a square item inherits the orientation of the padded batch (pygmtools transposes a tall batch globally)
+        rows.append([off, off, -1 if with_third else off, int(n1s[b]), int(n2s[b]), N2, N2, N2, 1 if N1 > N2 else 0])
     return rows
 
 
@@ -300,7 +301,7 @@ def affinity_pairs(X, w_sr, w_tg, w0, b0, w1, b1, sizes, pairs):
 
 # ------------------------------------------------------------------------------------------------ GA-GM
 def gagm_solve(A, W, U0, ms, n_univ=NU, init_tau=0.1, min_tau=1e-2, sk_gamma=0.5, max_iter=200, sk_iter=20,
-               converge_tol=1e-3, quad_weight=0.5, mode=0, step_projector=0, return_info=False):
+               converge_tol=1e-3, quad_weight=0.5, mode=0, step_projector=0, return_info=False, trace_cap=0):
     """GA_GM.gagm (mgm:300-389) on the device: one persistent cluster, no host round trips."""
     _need_cuda(A, W, U0)
     L = _C.lib()
@@ -312,10 +313,16 @@ def gagm_solve(A, W, U0, ms, n_univ=NU, init_tau=0.1, min_tau=1e-2, sk_gamma=0.5
     U = torch.empty(M, n_univ, dtype=torch.float32, device=A.device)
     info = torch.zeros(8, dtype=torch.int32, device=A.device)
     scratch = torch.empty(L.ttdg_gagm_scratch_bytes(M, G), dtype=torch.uint8, device=A.device)
+    trace = meta = None
+    if trace_cap > 0:                   # test hook: the whole trajectory, fp64
+        trace = torch.zeros(trace_cap + 1, M, n_univ, dtype=torch.float64, device=A.device)
+        meta = torch.zeros(trace_cap, 2, dtype=torch.float64, device=A.device)
     check(L.ttdg_gagm_solve(_p(A_c), _p(W_c), _p(U0_c), ctypes.cast(ms_h, ctypes.c_void_p), G, M, n_univ, float(init_tau),
                             float(min_tau), float(sk_gamma), int(max_iter), int(sk_iter), float(converge_tol),
-                            float(quad_weight), int(mode), int(step_projector), _p(U), _p(info), _p(scratch), _stream()),
-          "gagm_solve")
+                            float(quad_weight), int(mode), int(step_projector), _p(U), _p(info), _p(scratch), _p(trace),
+                            _p(meta), int(trace_cap), _stream()), "gagm_solve")
+    if trace_cap > 0:
+        return U, info, trace, meta
     return (U, info) if return_info else U
 
 
@@ -344,7 +351,7 @@ class _MatchingLoss(torch.autograd.Function):
         for (s, t) in pairs:
             main = offs[s] * M + offs[t]
             mirror = offs[t] * M + offs[s] if s != t else -1
-            rows.append([tot, main, mirror, sizes[s], sizes[t], sizes[t], M, M])
+            rows.append([tot, main, mirror, sizes[s], sizes[t], sizes[t], M, M, 0])
             tot += sizes[s] * sizes[t]
         items = _i64(rows, dev)
         # utils/sinkhorn.py via mgm:467-468, 519-522: max_iter 20, tau 0.05, dummy_row
@@ -379,7 +386,7 @@ class _MatchingLoss(torch.autograd.Function):
         check(L.ttdg_matching_loss_bwd(_p(Wds), _p(U), _p(node_off), G, M, NU, _p(gl), _p(gW), _stream()), "matching_loss_bwd")
         g_aff = torch.zeros(tot, dtype=torch.float32, device=dev)
         # only the off-diagonal pairs feed the loss; {s_off, gout_off, gin_off, n1, n2, ld_s, ld_gout, ld_gin}
-        brow = [[r[0], r[1], r[0], r[3], r[4], r[5], M, r[5]] for r in rows if r[2] >= 0]
+        brow = [[r[0], r[1], r[0], r[3], r[4], r[5], M, r[5], 0] for r in rows if r[2] >= 0]
         if brow:
             items = _i64(brow, dev)
             check(L.ttdg_sinkhorn_small_bwd(_p(aff_c), _p(gW), _p(g_aff), _p(items), len(brow), max(sizes), cfg["sk_tau"],

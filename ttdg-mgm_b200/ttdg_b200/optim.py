@@ -1,0 +1,52 @@
+"""Flat-bucket SGD for the test-time-adaptation step (reference: the ``optimizer`` the caller steps at
+adapteacher/engine/trainer.py:480-482, built by Detectron2's ``build_optimizer`` - SGD, momentum 0.9, weight
+decay 1e-4, lr ``SOLVER.BASE_LR`` = 0.005 from configs/test_segment.yaml:28, no scheduler during TTT).
+
+All adapted parameters live in ONE flat fp32 buffer (parameters become views of it), their gradients in a second
+one (``p.grad`` are views, autograd accumulates in place), so a step is: [one NCCL all-reduce of the gradient
+bucket when world_size > 1] + one fused kernel (``ttdg_sgd_step``, 20 bytes per parameter of HBM traffic).  The
+1 / world_size of the all-reduce average is folded into the kernel."""
+import ctypes
+
+import torch
+
+from . import _C
+from ._C import check
+
+
+class FlatSGD:
+    def __init__(self, params, lr=0.005, momentum=0.9, weight_decay=1e-4):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatSGD: no trainable parameters")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise _C.TTDGError("FlatSGD needs CUDA parameters (there is no CPU fallback)")
+        self.lr, self.momentum, self.weight_decay = float(lr), float(momentum), float(weight_decay)
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]          # keep every view 16-byte aligned
+        self.numel = sum(sizes)
+        self.flat_p = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p, n in zip(self.params, sizes):
+                view = self.flat_p[off:off + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view
+                p.grad = self.flat_g[off:off + p.numel()].view_as(p)
+                off += n
+        self.steps = 0
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_g.zero_()
+
+    def step(self, world_size=1, process_group=None):
+        """All-reduce (sum) the gradient bucket when world_size > 1, then one fused update."""
+        if world_size > 1:
+            torch.distributed.all_reduce(self.flat_g, group=process_group)
+        s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(_C.lib().ttdg_sgd_step(ctypes.c_void_p(self.flat_p.data_ptr()), ctypes.c_void_p(self.flat_g.data_ptr()),
+                                     ctypes.c_void_p(self.flat_m.data_ptr()), self.numel, self.lr, self.momentum,
+                                     self.weight_decay, 1.0 / world_size, int(self.steps == 0), s), "sgd_step")
+        self.steps += 1
