@@ -60,9 +60,9 @@ int ttdg_sinkhorn_small_bwd(const float *s, const float *grad_out, float *grad_i
 
 /* Large matrices: fp32 path for the N = 256/512/1024 micro-benchmark of BASELINE.json.  Uniform batch of
  * dense n1 x n2 matrices (n1 <= n2; n1 < n2 needs dummy_row = 0 or 1 as in the reference; n2 % 4 == 0).
- * One thread-block cluster per matrix keeps the matrix in distributed shared memory for all iterations
- * (row/column potentials, one read pass per half-iteration, no intermediate HBM traffic) when it fits,
- * otherwise re-reads the part that does not fit through L2.  scratch: ttdg_sinkhorn_stream_scratch_bytes. */
+ * One thread-block cluster (1..8 CTAs) per matrix keeps the matrix in distributed shared memory for all
+ * iterations (row/column potentials: the matrix is never rewritten, no intermediate HBM traffic); rows that do
+ * not fit (N = 1024) are re-read through L2.  scratch: ttdg_sinkhorn_stream_scratch_bytes. */
 int64_t ttdg_sinkhorn_stream_scratch_bytes(int batch, int n1, int n2);
 int ttdg_sinkhorn_stream_fwd(const float *s, float *out, int batch, int n1, int n2, float tau, int max_iter,
                              int dummy_row, void *scratch, void *stream);

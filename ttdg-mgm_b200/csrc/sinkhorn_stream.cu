@@ -151,9 +151,9 @@ sinkhorn_stream_kernel(const SksParams p) {
                     const int j = r * cols_per_cta + jj;
                     if (j < n2) {
                         float m = -INFINITY;
-                        float mq[8], sq[8];
+                        float mq[16], sq[16];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
+                        for (int q = 0; q < 16; ++q)
                             if (q < p.R) {
                                 mq[q] = *cluster.map_shared_rank(cm + j, q);
                                 sq[q] = *cluster.map_shared_rank(cs + j, q);
@@ -161,11 +161,11 @@ sinkhorn_stream_kernel(const SksParams p) {
                             }
                         float sum = 0.f;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
+                        for (int q = 0; q < 16; ++q)
                             if (q < p.R && mq[q] > -INFINITY) sum += sq[q] * ex2(mq[q] - m);
                         const float gj = m + lg2(sum);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
+                        for (int q = 0; q < 16; ++q)
                             if (q < p.R) *cluster.map_shared_rank(g + j, q) = gj;
                     }
                 }
@@ -189,21 +189,27 @@ sinkhorn_stream_kernel(const SksParams p) {
     cluster.sync();                                                // no CTA exits while peers may still touch its smem
 }
 
-static void sks_plan(int n1, int n2, SksParams &p, size_t &smem) {
-    int R = 8;                       // portable cluster size; 148 SMs hold up to 18 clusters of 8
-    while (R > 1 && n1 / R < 32) R >>= 1;
-    p.R = R;
-    p.rows_per_cta = (n1 + R - 1) / R;
-    int res = 226 * 1024 / (n2 * (int)sizeof(float));
-    p.res_rows = res < p.rows_per_cta ? res : p.rows_per_cta;
+static size_t sks_need(int n2, int rows_per_cta, int res_rows) {
     const int n2q = n2 / 4;
     const int CW = n2q < SKS_THREADS ? n2q : SKS_THREADS;
     const int RG = SKS_THREADS / CW;
-    auto need = [&](int res_rows) {
-        return ((size_t)res_rows * n2 + n2 + ((p.rows_per_cta + 3) & ~3) + 2 * (size_t)n2 + 2 * (size_t)RG * n2) * sizeof(float);
-    };
-    while (p.res_rows > 0 && need(p.res_rows) > 226 * 1024) --p.res_rows;      // bookkeeping arrays share the 227 KB
-    smem = need(p.res_rows);
+    return ((size_t)res_rows * n2 + n2 + ((rows_per_cta + 3) & ~3) + 2 * (size_t)n2 + 2 * (size_t)RG * n2) * sizeof(float);
+}
+
+// Smallest cluster whose slabs hold the whole matrix (fewer CTAs per matrix = cheaper cluster barriers and more
+// matrices in flight: N = 256 -> 2 CTAs, N = 512 -> 8); if even 8 slabs are too small (N = 1024) use 8 and re-read
+// the rows that do not fit through L2.
+static void sks_plan(int n1, int n2, SksParams &p, size_t &smem) {
+    const size_t budget = 226 * 1024;
+    for (int R = 1; R <= 8; R <<= 1) {
+        const int rows = (n1 + R - 1) / R;
+        if (sks_need(n2, rows, rows) <= budget || R == 8) {
+            p.R = R; p.rows_per_cta = rows; p.res_rows = rows;
+            while (p.res_rows > 0 && sks_need(n2, rows, p.res_rows) > budget) --p.res_rows;
+            smem = sks_need(n2, rows, p.res_rows);
+            return;
+        }
+    }
 }
 
 }  // namespace ttdg
@@ -223,23 +229,25 @@ extern "C" int ttdg_sinkhorn_stream_fwd(const float *s, float *out, int batch, i
     if (batch == 0) return 0;
     SksParams p;
     size_t smem;
+    cudaError_t e;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    int max_clusters = 0;
     sks_plan(n1, n2, p, smem);
     if (smem > 227 * 1024) return TTDG_E_LIMIT;
-    p.s = s; p.out = out; p.batch = batch; p.n1 = n1; p.n2 = n2; p.max_iter = max_iter; p.inv_tau = 1.4426950408889634f / tau;     // log2(e) / tau
-    cudaError_t e = cudaFuncSetAttribute(sinkhorn_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(sinkhorn_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(SKS_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = p.R; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cfg.gridDim = dim3(p.R);
-    int max_clusters = 0;
     e = cudaOccupancyMaxActiveClusters(&max_clusters, sinkhorn_stream_kernel, &cfg);
     if (e != cudaSuccess || max_clusters < 1) { cudaGetLastError(); max_clusters = 148 / p.R; }
+    p.s = s; p.out = out; p.batch = batch; p.n1 = n1; p.n2 = n2; p.max_iter = max_iter;
+    p.inv_tau = 1.4426950408889634f / tau;     // log2(e) / tau
     const int ncl = batch < max_clusters ? batch : max_clusters;
     cfg.gridDim = dim3(ncl * p.R);
     ttdg::count_launches(1);
