@@ -203,6 +203,66 @@ int ttdg_sampler_scatter_bwd(const float *grad_nodes, float *const *gfeat_ptrs_h
 int ttdg_sgd_step(float *p, const float *g, float *m, int64_t n, float lr, float momentum, float weight_decay,
                   float grad_scale, int first_step, void *stream);
 
+/* =============================================================================================
+ * Detector (Detectron2 0.5 Mask R-CNN R50-FPN as configured by configs/Base-RCNN-FPN.yaml + test_segment.yaml;
+ * driven by meta_arch/rcnn.py:219-226,331-357 and :181-182).  Activations are NHWC fp32; convolution weights are
+ * [R][S][Cin][Cout] (the host wrapper permutes torch's [Cout][Cin][R][S]); channel counts are multiples of 4.
+ * ============================================================================================= */
+
+/* Convolution forward with fused epilogue  y = relu?( conv(x) * scale[c] + bias[c] + residual )  - FrozenBN folded
+ * into (scale, bias) (d2 FrozenBatchNorm2d), conv bias, the bottleneck shortcut add (res_mode 1: residual has y's
+ * shape) or the FPN top-down add (res_mode 2: residual is the half-resolution map, nearest-upsampled on the fly).
+ * Replaces the cuDNN calls behind d2 ResNet/FPN/RPN-head/mask-head convs and the box-head FCs (as 1x1 convs on
+ * N = rows, H = W = 1). */
+int ttdg_conv_fwd(const float *x, const float *w, const float *scale, const float *bias, const float *residual,
+                  int res_mode, int relu, int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad,
+                  float *y, void *stream);
+/* Data gradient (autograd of the above for the layers the TTT loss reaches: res3-res5 and FPN).
+ * (N, H, W, Cin) is the forward input geometry; stride 1 any R x S, or 1x1 stride 2 (dx must be zero-filled). */
+int ttdg_conv_dgrad(const float *dy, const float *w, int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
+                    int pad, float *dx, void *stream);
+/* Weight gradient, ACCUMULATED into dw [R][S][Cin][Cout] (split over pixels, fp32 atomics). Cin % 128 == 0. */
+int ttdg_conv_wgrad(const float *x, const float *dy, int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
+                    int pad, float *dw, void *stream);
+/* out = (y > 0 ? g : 0) * scale[c]: backward through ReLU (mask from the stored output y, may be NULL) and the
+ * FrozenBN scale (may be NULL). */
+int ttdg_relu_bn_bwd(const float *g, const float *y, const float *scale, int C, int64_t numel, float *out, void *stream);
+/* out[c] += sum over pixels of g[pixel][c]  (conv bias gradient) */
+int ttdg_bias_grad(const float *g, int64_t pixels, int C, float *out, void *stream);
+int ttdg_maxpool3x3s2(const float *x, int N, int H, int W, int C, float *y, void *stream);           /* ResNet stem pool */
+/* mode 0: y[small] = x[big at even pixels] (p6 = max_pool2d(p5, 1, 2)); 1: y[big even] += x[small] (its backward);
+ * 2: y[small] += sum of 2x2 children of x[big] (backward of the FPN nearest upsample).  Hs x Ws = small grid. */
+int ttdg_resample2(const float *x, float *y, int N, int Hs, int Ws, int C, int mode, void *stream);
+/* uint8 N x 3 x H x W planar -> fp32 NHWC with 4 channels (4th = 0), minus PIXEL_MEAN (d2 preprocess_image). */
+int ttdg_preprocess(const unsigned char *img_u8, int N, int H, int W, float mean0, float mean1, float mean2, float *out,
+                    void *stream);
+
+/* RPN: decode + clip the anchors selected per level (d2 find_top_rpn_proposals / Box2BoxTransform.apply_deltas).
+ * idx [n_img][k] indexes (pixel * A + a); deltas = NHWC head output, channel a * 4 + c, row pitch ld_deltas;
+ * cell_anchors_h = HOST float[A][4].  valid = finite and non-empty after clipping. */
+int ttdg_rpn_decode(const float *deltas, int ld_deltas, const int64_t *idx, int n_img, int k, int Hl, int Wl, int A,
+                    int stride, const float *cell_anchors_h, float img_h, float img_w, float *boxes,
+                    unsigned char *valid, void *stream);
+/* Box head output (FastRCNNOutputLayers.inference up to the score filter): softmax over K+1 class scores,
+ * class-specific deltas with weights (10, 10, 5, 5), clip; cand_scores = -1 where score <= thresh. */
+int ttdg_box_predict(const float *cls, int ld_cls, const float *reg, int ld_reg, const float *proposals, int R, int K,
+                     float img_h, float img_w, float score_thresh, float *cand_boxes, float *cand_scores, void *stream);
+/* Per-category NMS (torchvision batched_nms semantics) over boxes already sorted by descending score.
+ * keep [max_keep] receives indices in order, *n_keep their number.  scratch: ttdg_nms_scratch_bytes(n). */
+int64_t ttdg_nms_scratch_bytes(int n);
+int ttdg_nms(const float *boxes_sorted, const int32_t *category, int n, float iou_thresh, int max_keep, int32_t *keep,
+             int32_t *n_keep, void *scratch, void *stream);
+/* ROIPooler + ROIAlignV2 (aligned, sampling_ratio 0) over p2..p5: rois [n][5] = {image, x0, y0, x1, y1};
+ * out [n][pooled][pooled][C].  feat_ptrs_h = HOST array of 4 device pointers, lvl_hw_h = HOST int32[4][2]. */
+int ttdg_roi_align(const float *const *feat_ptrs_h, const int32_t *lvl_hw_h, const float *rois, int n_rois, int C,
+                   int pooled, float *out, void *stream);
+/* x [R][H][W][(a, b, c)] -> y [R][2H][2W][c]  (the 2x2 stride-2 deconv of the mask head, computed as a 1x1 conv) */
+int ttdg_pixel_shuffle2(const float *x, int R, int H, int W, int C, float *y, void *stream);
+/* detector_postprocess / paste_masks_in_image: out[r] = bilinear(sigmoid(logits[r, :, :, class[r]])) >= threshold
+ * over the H x W image (grid_sample semantics, align_corners = False). */
+int ttdg_mask_paste(const float *logits, int ld_logits, int M, const float *boxes, const int64_t *classes, int R, int H,
+                    int W, float threshold, unsigned char *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,21 @@ SIGNATURES = {
     "ttdg_focal_bce_scratch_bytes": (c_int64, []),
     "ttdg_focal_bce_fwd": (c_int, [P, P, c_int64, P, P, P]),
     "ttdg_focal_bce_bwd": (c_int, [P, P, c_int64, P, P, P]),
+    "ttdg_conv_fwd": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "ttdg_conv_dgrad": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "ttdg_conv_wgrad": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "ttdg_relu_bn_bwd": (c_int, [P, P, P, c_int, c_int64, P, P]),
+    "ttdg_bias_grad": (c_int, [P, c_int64, c_int, P, P]),
+    "ttdg_maxpool3x3s2": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
+    "ttdg_resample2": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "ttdg_preprocess": (c_int, [P, c_int, c_int, c_int, c_float, c_float, c_float, P, P]),
+    "ttdg_rpn_decode": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_float, c_float, P, P, P]),
+    "ttdg_box_predict": (c_int, [P, c_int, P, c_int, P, c_int, c_int, c_float, c_float, c_float, P, P, P]),
+    "ttdg_nms_scratch_bytes": (c_int64, [c_int]),
+    "ttdg_nms": (c_int, [P, P, c_int, c_float, c_int, P, P, P, P]),
+    "ttdg_roi_align": (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
+    "ttdg_pixel_shuffle2": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
+    "ttdg_mask_paste": (c_int, [P, c_int, c_int, P, P, c_int, c_int, c_int, c_float, P, P]),
     "ttdg_sampler_select": (c_int, [P, P, P, c_int, P, c_int, c_int, P, P, P, P]),
     "ttdg_sampler_gather": (c_int, [P, P, P, c_int, c_int, c_int, P, P, c_int, P, P, P, P]),
     "ttdg_sampler_scatter_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, P, c_int, P, P]),

@@ -1,0 +1,565 @@
+"""Detector half of the hot path: Detectron2 0.5 Mask R-CNN R50-FPN (configs/Base-RCNN-FPN.yaml +
+configs/test_segment.yaml) as driven by adapteacher/modeling/meta_arch/rcnn.py:154-357, on the sm_100a kernels of
+libttdg_sm100.so (csrc/conv.cu, csrc/detect.cu).
+
+Activations are NHWC fp32 on the device.  Parameters keep Detectron2's state-dict names and shapes on load / save
+(``backbone.bottom_up.res3.0.conv1.weight`` ...), but live in the kernels' layout ([R][S][Cin][Cout], channels padded
+to a multiple of 4) so that the fused SGD step and the weight-gradient kernel work on them in place.  FrozenBN is
+folded into a per-channel (scale, bias) epilogue.  torch ops appear only as plumbing (allocation, slicing, sort /
+top-k for ordering); there is no eager or CPU fallback.
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _C
+from ._C import check
+from .ops import _p, _stream, _need_cuda
+
+PIXEL_MEAN = (103.530, 116.280, 123.675)
+STRIDES = (4, 8, 16, 32, 64)
+ANCHOR_SIZES = (32, 64, 128, 256, 512)
+ANCHOR_RATIOS = (0.5, 1.0, 2.0)
+RES_STAGES = (("res2", 3, 64, 256, 1), ("res3", 4, 128, 512, 2), ("res4", 6, 256, 1024, 2), ("res5", 3, 512, 2048, 2))
+
+
+def _pad4(c):
+    return (c + 3) // 4 * 4
+
+
+# ---------------------------------------------------------------------------------------------- raw op wrappers
+def conv_forward(x, w, scale, bias, residual, res_mode, relu, R, S, stride, pad, out=None):
+    """x: N x H x W x Cin (NHWC contiguous) -> N x Ho x Wo x Cout."""
+    N, H, W, Cin = x.shape
+    Cout = w.shape[-1]
+    Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+    y = torch.empty(N, Ho, Wo, Cout, dtype=torch.float32, device=x.device) if out is None else out
+    check(_C.lib().ttdg_conv_fwd(_p(x), _p(w), _p(scale), _p(bias), _p(residual), int(res_mode), int(relu), N, H, W, Cin, Cout, R, S,
+                                 stride, pad, _p(y), _stream()), "conv_fwd")
+    return y
+
+
+class _ConvFn(torch.autograd.Function):
+    """y = relu?(conv(x, w) * scale + bias + residual) with the gradients the TTT loss needs."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias_param, residual, scale, bias_const, res_mode, relu, R, S, stride, pad):
+        bias = bias_param if bias_param is not None else bias_const
+        y = conv_forward(x, w, scale, bias, residual, res_mode, relu, R, S, stride, pad)
+        ctx.save_for_backward(x, w, y if relu else None, scale)
+        ctx.meta = (res_mode, relu, R, S, stride, pad, bias_param is not None, residual is not None and residual.requires_grad)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _C.lib()
+        x, w, y, scale = ctx.saved_tensors
+        res_mode, relu, R, S, stride, pad, has_bias, res_grad = ctx.meta
+        N, H, W, Cin = x.shape
+        Cout = w.shape[-1]
+        g = g.contiguous()
+        s = _stream()
+        if relu:                                           # dPre = g * [y > 0]
+            d_pre = torch.empty_like(g)
+            check(L.ttdg_relu_bn_bwd(_p(g), _p(y), None, Cout, g.numel(), _p(d_pre), s), "relu_bwd")
+        else:
+            d_pre = g
+        g_res = None
+        if res_grad:
+            if res_mode == 1:
+                g_res = d_pre
+            else:                                          # FPN top-down: sum over the 2x2 children
+                Ho, Wo = g.shape[1], g.shape[2]
+                g_res = torch.zeros(N, Ho // 2, Wo // 2, Cout, dtype=torch.float32, device=g.device)
+                check(L.ttdg_resample2(_p(d_pre), _p(g_res), N, Ho // 2, Wo // 2, Cout, 2, s), "upsample_bwd")
+        g_bias = None
+        if has_bias and ctx.needs_input_grad[2]:
+            g_bias = torch.zeros(Cout, dtype=torch.float32, device=g.device)
+            check(L.ttdg_bias_grad(_p(d_pre), d_pre.numel() // Cout, Cout, _p(g_bias), s), "bias_grad")
+        if scale is not None:                              # through the FrozenBN scale
+            d_conv = torch.empty_like(d_pre)
+            check(L.ttdg_relu_bn_bwd(_p(d_pre), None, _p(scale), Cout, d_pre.numel(), _p(d_conv), s), "bn_bwd")
+        else:
+            d_conv = d_pre
+        g_x = g_w = None
+        if ctx.needs_input_grad[0]:
+            g_x = (torch.zeros if stride == 2 else torch.empty)(N, H, W, Cin, dtype=torch.float32, device=g.device)
+            check(L.ttdg_conv_dgrad(_p(d_conv), _p(w), N, H, W, Cin, Cout, R, S, stride, pad, _p(g_x), s), "conv_dgrad")
+        if ctx.needs_input_grad[1]:
+            g_w = torch.zeros_like(w)
+            check(L.ttdg_conv_wgrad(_p(x), _p(d_conv), N, H, W, Cin, Cout, R, S, stride, pad, _p(g_w), s), "conv_wgrad")
+        return g_x, g_w, g_bias, g_res, None, None, None, None, None, None, None, None
+
+
+class FrozenBN(nn.Module):
+    """State holder of d2's FrozenBatchNorm2d (buffers only); folded into (scale, bias) by the owning Conv2d."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.register_buffer("weight", torch.ones(c))
+        self.register_buffer("bias", torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.eps = 1e-5
+
+
+class Conv2d(nn.Module):
+    """Convolution / linear layer in the kernels' layout with d2-compatible state-dict I/O.
+
+    kind: 'conv' (torch weight Cout x Cin x R x S), 'linear' (Cout x Cin), 'linear_chw' (Cout x C*H*W flattened in
+    (C, H, W) order - the box head's fc1; our activations are (H, W, C)), 'deconv' (ConvTranspose2d Cin x Cout x 2 x 2,
+    stored as a 1x1 conv with 4 Cout outputs ordered (a, b, c))."""
+
+    def __init__(self, cin, cout, k=1, stride=1, pad=0, bias=True, norm=False, kind="conv", chw=None):
+        super().__init__()
+        self.cin, self.cout, self.k, self.stride, self.pad, self.kind, self.chw = cin, cout, k, stride, pad, kind, chw
+        self.cin_p, self.cout_p = _pad4(cin), _pad4(cout)
+        if kind == "deconv":
+            self.weight = nn.Parameter(torch.zeros(1, 1, self.cin_p, 4 * self.cout_p))
+            self.bias = nn.Parameter(torch.zeros(4 * self.cout_p))
+        else:
+            self.weight = nn.Parameter(torch.zeros(k, k, self.cin_p, self.cout_p))
+            self.bias = nn.Parameter(torch.zeros(self.cout_p)) if bias else None
+        self.norm = FrozenBN(cout) if norm else None
+        self.register_buffer("fold_scale", None, persistent=False)
+        self.register_buffer("fold_bias", None, persistent=False)
+
+    # ---- state dict in Detectron2's names / shapes
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        w = self.weight.detach()
+        if self.kind == "conv":
+            t = w[:, :, :self.cin, :self.cout].permute(3, 2, 0, 1).contiguous()
+        elif self.kind == "linear":
+            t = w[0, 0, :self.cin, :self.cout].t().contiguous()
+        elif self.kind == "linear_chw":
+            C, H, W = self.chw
+            t = w[0, 0, :, :self.cout].reshape(H, W, C, self.cout).permute(3, 2, 0, 1).reshape(self.cout, C * H * W).contiguous()
+        else:   # deconv: stored [ci][(a, b, co)] -> torch [ci][co][a][b]
+            t = w[0, 0, :self.cin].reshape(self.cin, 2, 2, self.cout_p)[..., :self.cout].permute(0, 3, 1, 2).contiguous()
+        destination[prefix + "weight"] = t
+        if self.bias is not None:
+            b = self.bias.detach()
+            destination[prefix + "bias"] = (b.reshape(4, self.cout_p)[0, :self.cout] if self.kind == "deconv" else b[:self.cout]).clone()
+        if self.norm is not None:
+            for k in ("weight", "bias", "running_mean", "running_var"):
+                destination[prefix + "norm." + k] = getattr(self.norm, k).clone()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        key = prefix + "weight"
+        if key not in state_dict:
+            missing_keys.append(key)
+            return
+        t = state_dict[key].to(torch.float32)
+        with torch.no_grad():
+            w = torch.zeros_like(self.weight)
+            if self.kind == "conv":
+                w[:, :, :self.cin, :self.cout] = t.permute(2, 3, 1, 0)
+            elif self.kind == "linear":
+                w[0, 0, :self.cin, :self.cout] = t.t()
+            elif self.kind == "linear_chw":
+                C, H, W = self.chw
+                w[0, 0, :, :self.cout] = t.reshape(self.cout, C, H, W).permute(2, 3, 1, 0).reshape(H * W * C, self.cout)
+            else:
+                w[0, 0, :self.cin] = torch.nn.functional.pad(t.permute(0, 2, 3, 1), (0, self.cout_p - self.cout)).reshape(self.cin, 4 * self.cout_p)
+            self.weight.copy_(w)
+            if self.bias is not None:
+                if prefix + "bias" not in state_dict:
+                    missing_keys.append(prefix + "bias")
+                else:
+                    b = torch.zeros_like(self.bias)
+                    src = state_dict[prefix + "bias"].to(torch.float32)
+                    if self.kind == "deconv":
+                        b.view(4, self.cout_p)[:, :self.cout] = src
+                    else:
+                        b[:self.cout] = src
+                    self.bias.copy_(b)
+            if self.norm is not None:
+                for k in ("weight", "bias", "running_mean", "running_var"):
+                    if prefix + "norm." + k not in state_dict:
+                        missing_keys.append(prefix + "norm." + k)
+                    else:
+                        getattr(self.norm, k).copy_(state_dict[prefix + "norm." + k])
+                self.fold()
+
+    def fold(self):
+        """FrozenBatchNorm2d: scale = w * rsqrt(var + eps), bias = b - mean * scale."""
+        n = self.norm
+        scale = n.weight * (n.running_var + n.eps).rsqrt()
+        bias = n.bias - n.running_mean * scale
+        self.fold_scale = torch.nn.functional.pad(scale, (0, self.cout_p - self.cout)).contiguous()
+        self.fold_bias = torch.nn.functional.pad(bias, (0, self.cout_p - self.cout)).contiguous()
+
+    def forward(self, x, relu=False, residual=None, res_mode=0):
+        if self.norm is not None and self.fold_scale is None:
+            self.fold()
+        scale = self.fold_scale if self.norm is not None else None
+        bias_const = self.fold_bias if self.norm is not None else None
+        k = 1 if self.kind != "conv" else self.k
+        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
+            return _ConvFn.apply(x, self.weight, self.bias, residual, scale, bias_const, res_mode, relu, k, k, self.stride, self.pad)
+        bias = self.bias if self.bias is not None else bias_const
+        return conv_forward(x, self.weight.detach(), scale, None if bias is None else bias.detach(), residual, res_mode, relu, k, k,
+                            self.stride, self.pad)
+
+
+class Bottleneck(nn.Module):
+    def __init__(self, cin, mid, cout, stride, shortcut):
+        super().__init__()
+        self.shortcut = Conv2d(cin, cout, 1, stride, 0, bias=False, norm=True) if shortcut else None
+        self.conv1 = Conv2d(cin, mid, 1, stride, 0, bias=False, norm=True)          # STRIDE_IN_1X1
+        self.conv2 = Conv2d(mid, mid, 3, 1, 1, bias=False, norm=True)
+        self.conv3 = Conv2d(mid, cout, 1, 1, 0, bias=False, norm=True)
+
+    def forward(self, x):
+        out = self.conv1(x, relu=True)
+        out = self.conv2(out, relu=True)
+        sc = self.shortcut(x) if self.shortcut is not None else x
+        return self.conv3(out, relu=True, residual=sc, res_mode=1)                   # relu(bn(conv3) + shortcut)
+
+
+class Stem(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv1 = Conv2d(3, 64, 7, 2, 3, bias=False, norm=True)
+
+
+class ResNet50(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.stem = Stem()
+        cin = 64
+        for name, blocks, mid, cout, stride in RES_STAGES:
+            layers = []
+            for b in range(blocks):
+                layers.append(Bottleneck(cin, mid, cout, stride if b == 0 else 1, b == 0))
+                cin = cout
+            setattr(self, name, nn.Sequential(*layers))
+
+    def forward(self, x):
+        L = _C.lib()
+        with torch.no_grad():                                   # FREEZE_AT = 2: stem + res2
+            y = self.stem.conv1(x, relu=True)
+            N, H, W, C = y.shape
+            p = torch.empty(N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C, dtype=torch.float32, device=y.device)
+            check(L.ttdg_maxpool3x3s2(_p(y), N, H, W, C, _p(p), _stream()), "maxpool")
+            y = self.res2(p)
+        out = {"res2": y}
+        for name in ("res3", "res4", "res5"):
+            y = getattr(self, name)(y)
+            out[name] = y
+        return out
+
+
+class _Subsample2(torch.autograd.Function):
+    """p6 = max_pool2d(p5, kernel_size=1, stride=2) (d2 LastLevelMaxPool)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        N, H, W, C = x.shape
+        y = torch.empty(N, H // 2, W // 2, C, dtype=torch.float32, device=x.device)
+        check(_C.lib().ttdg_resample2(_p(x), _p(y), N, H // 2, W // 2, C, 0, _stream()), "subsample")
+        ctx.shape = (N, H, W, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        N, H, W, C = ctx.shape
+        gx = torch.zeros(N, H, W, C, dtype=torch.float32, device=g.device)
+        check(_C.lib().ttdg_resample2(_p(g.contiguous()), _p(gx), N, H // 2, W // 2, C, 1, _stream()), "subsample_bwd")
+        return gx
+
+
+class Backbone(nn.Module):
+    """build_resnet_fpn_backbone: ResNet-50 bottom-up + FPN (sum fusion, no norm) + LastLevelMaxPool."""
+
+    def __init__(self):
+        super().__init__()
+        self.bottom_up = ResNet50()
+        for lvl, c in zip((2, 3, 4, 5), (256, 512, 1024, 2048)):
+            setattr(self, f"fpn_lateral{lvl}", Conv2d(c, 256, 1, 1, 0, bias=True))
+            setattr(self, f"fpn_output{lvl}", Conv2d(256, 256, 3, 1, 1, bias=True))
+
+    def forward(self, x):
+        res = self.bottom_up(x)
+        outs, prev = {}, None
+        for lvl in (5, 4, 3, 2):
+            lat = getattr(self, f"fpn_lateral{lvl}")
+            prev = lat(res[f"res{lvl}"]) if prev is None else lat(res[f"res{lvl}"], residual=prev, res_mode=2)
+            outs[lvl] = getattr(self, f"fpn_output{lvl}")(prev)
+        return [outs[2], outs[3], outs[4], outs[5], _Subsample2.apply(outs[5])]
+
+
+class RPNHead(nn.Module):
+    def __init__(self, num_anchors=15):
+        super().__init__()
+        self.conv = Conv2d(256, 256, 3, 1, 1, bias=True)
+        self.objectness_logits = Conv2d(256, num_anchors, 1, 1, 0, bias=True)
+        self.anchor_deltas = Conv2d(256, num_anchors * 4, 1, 1, 0, bias=True)
+
+
+def cell_anchors():
+    a = []
+    for s in ANCHOR_SIZES:
+        area = float(s) ** 2
+        for r in ANCHOR_RATIOS:
+            w = math.sqrt(area / r)
+            h = r * w
+            a.append([-w / 2.0, -h / 2.0, w / 2.0, h / 2.0])
+    return torch.tensor(a, dtype=torch.float32)
+
+
+def nms_sorted(boxes, cats, thresh, max_keep):
+    """Per-category NMS over boxes sorted by descending score: returns (keep int32[max_keep], n_keep int32[1])."""
+    n = boxes.shape[0]
+    L = _C.lib()
+    keep = torch.zeros(max_keep, dtype=torch.int32, device=boxes.device)
+    n_keep = torch.zeros(1, dtype=torch.int32, device=boxes.device)
+    scratch = torch.empty(max(L.ttdg_nms_scratch_bytes(n), 8), dtype=torch.uint8, device=boxes.device)
+    check(L.ttdg_nms(_p(boxes), _p(cats), n, float(thresh), int(max_keep), _p(keep), _p(n_keep), _p(scratch), _stream()), "nms")
+    return keep, n_keep
+
+
+class RPN(nn.Module):
+    """PseudoLabRPN (proposal_generator/rpn.py:16-55) with compute_loss=False: StandardRPNHead + d2
+    find_top_rpn_proposals.  pre-NMS top-k per level is 2000 in train mode (the TTT pass) / 1000 in eval mode."""
+
+    def __init__(self):
+        super().__init__()
+        self.rpn_head = RPNHead(len(ANCHOR_SIZES) * len(ANCHOR_RATIOS))
+        self.nms_thresh, self.post_topk = 0.7, 1000
+        self._cell = cell_anchors()
+
+    @torch.no_grad()
+    def forward(self, feats, image_size, training):
+        L = _C.lib()
+        A = self._cell.shape[0]
+        pre_topk = 2000 if training else 1000
+        N = feats[0].shape[0]
+        dev = feats[0].device
+        cell_h = (ctypes.c_float * (A * 4))(*self._cell.reshape(-1).tolist())
+        boxes_l, scores_l, valid_l, lvl_l = [], [], [], []
+        for l, f in enumerate(feats):
+            f = f.detach()
+            _, H, W, _ = f.shape
+            t = self.rpn_head.conv(f, relu=True)
+            logits = self.rpn_head.objectness_logits(t)                 # N x H x W x 16 (15 used)
+            deltas = self.rpn_head.anchor_deltas(t)                     # N x H x W x 60
+            flat = logits[..., :A].reshape(N, H * W * A)
+            k = min(flat.shape[1], pre_topk)
+            sc, idx = torch.topk(flat, k, dim=1, sorted=True)           # ordering only (plumbing)
+            boxes = torch.empty(N, k, 4, dtype=torch.float32, device=dev)
+            valid = torch.empty(N, k, dtype=torch.uint8, device=dev)
+            check(L.ttdg_rpn_decode(_p(deltas), deltas.shape[-1], _p(idx.contiguous()), N, k, H, W, A, STRIDES[l],
+                                    ctypes.cast(cell_h, ctypes.c_void_p), float(image_size[0]), float(image_size[1]), _p(boxes),
+                                    _p(valid), _stream()), "rpn_decode")
+            boxes_l.append(boxes); scores_l.append(sc); valid_l.append(valid)
+            lvl_l.append(torch.full((k,), l, dtype=torch.int32, device=dev))
+        boxes, scores, valid, lvl = torch.cat(boxes_l, 1), torch.cat(scores_l, 1), torch.cat(valid_l, 1).bool(), torch.cat(lvl_l)
+        # invalid (non-finite / empty) boxes sort last and never interact (unique negative category)
+        key = torch.where(valid & torch.isfinite(scores), scores, torch.full_like(scores, -float("inf")))
+        order = torch.argsort(key, dim=1, descending=True, stable=True)
+        n_valid = (key > -float("inf")).sum(1).to(torch.int32)
+        res, meta = [], []
+        Kt = boxes.shape[1]
+        neg = -1 - torch.arange(Kt, dtype=torch.int32, device=dev)
+        for n in range(N):
+            b = boxes[n][order[n]].contiguous()
+            s = scores[n][order[n]]
+            c = torch.where(torch.arange(Kt, device=dev) < n_valid[n], lvl[order[n]], neg).contiguous()
+            keep, n_keep = nms_sorted(b, c, self.nms_thresh, self.post_topk)
+            res.append((b, s, keep))
+            meta.append(n_keep)
+        counts = torch.stack([torch.minimum(m[0], ((r[2][:self.post_topk] < nv) & (torch.arange(self.post_topk, device=dev) < m[0])).sum().to(torch.int32))
+                              for m, r, nv in zip(meta, res, n_valid)]).cpu().tolist()      # one host sync per batch
+        out = []
+        for (b, s, keep), cnt in zip(res, counts):
+            kk = keep[:cnt].long()
+            out.append((b[kk], s[kk]))
+        return out
+
+
+class BoxHead(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.fc1 = Conv2d(256 * 7 * 7, 1024, kind="linear_chw", chw=(256, 7, 7))
+        self.fc2 = Conv2d(1024, 1024, kind="linear")
+
+
+class BoxPredictor(nn.Module):
+    def __init__(self, num_classes):
+        super().__init__()
+        self.cls_score = Conv2d(1024, num_classes + 1, kind="linear")
+        self.bbox_pred = Conv2d(1024, num_classes * 4, kind="linear")
+
+
+class MaskHead(nn.Module):
+    def __init__(self, num_classes):
+        super().__init__()
+        for i in range(1, 5):
+            setattr(self, f"mask_fcn{i}", Conv2d(256, 256, 3, 1, 1, bias=True))
+        self.deconv = Conv2d(256, 256, kind="deconv")
+        self.predictor = Conv2d(256, num_classes, 1, 1, 0, bias=True)
+
+
+def roi_align(feats4, rois, pooled):
+    L = _C.lib()
+    n = rois.shape[0]
+    C = feats4[0].shape[-1]
+    out = torch.empty(n, pooled, pooled, C, dtype=torch.float32, device=rois.device)
+    ptrs = (ctypes.c_void_p * 4)(*[f.data_ptr() for f in feats4])
+    hw = (ctypes.c_int32 * 8)(*[v for f in feats4 for v in (f.shape[1], f.shape[2])])
+    check(L.ttdg_roi_align(ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(hw, ctypes.c_void_p), _p(rois), n, C, pooled, _p(out),
+                           _stream()), "roi_align")
+    return out
+
+
+def _rois(boxes_per_image):
+    dev = boxes_per_image[0].device
+    idx = torch.cat([torch.full((len(b), 1), float(i), device=dev) for i, b in enumerate(boxes_per_image)])
+    return torch.cat([idx, torch.cat(boxes_per_image)], dim=1).contiguous()
+
+
+class ROIHeads(nn.Module):
+    """StandardROIHeadsPseudoLab (roi_heads/roi_heads.py:65-114, 173-205) in inference form: box branch, and for
+    every branch except 'TTT' the mask branch (forward_with_given_boxes)."""
+
+    def __init__(self, num_classes=2):
+        super().__init__()
+        self.num_classes = num_classes
+        self.box_head = BoxHead()
+        self.box_predictor = BoxPredictor(num_classes)
+        self.mask_head = MaskHead(num_classes)
+        self.score_thresh, self.nms_thresh, self.topk = 0.05, 0.5, 100
+
+    @torch.no_grad()
+    def forward_box(self, feats, proposals, image_size):
+        L = _C.lib()
+        K = self.num_classes
+        feats4 = [f.detach() for f in feats[:4]]
+        dev = feats4[0].device
+        props = [p[0] for p in proposals]
+        rois = _rois(props)
+        R = rois.shape[0]
+        x = roi_align(feats4, rois, 7).reshape(R, 1, 1, 7 * 7 * 256)
+        x = self.box_head.fc1(x, relu=True)
+        x = self.box_head.fc2(x, relu=True)
+        cls = self.box_predictor.cls_score(x).reshape(R, -1)
+        reg = self.box_predictor.bbox_pred(x).reshape(R, -1)
+        pb = torch.cat(props).contiguous()
+        cand_b = torch.empty(R * K, 4, dtype=torch.float32, device=dev)
+        cand_s = torch.empty(R * K, dtype=torch.float32, device=dev)
+        check(L.ttdg_box_predict(_p(cls), cls.shape[1], _p(reg), reg.shape[1], _p(pb), R, K, float(image_size[0]), float(image_size[1]),
+                                 self.score_thresh, _p(cand_b), _p(cand_s), _stream()), "box_predict")
+        res, metas, o = [], [], 0
+        cls_id = torch.arange(K, dtype=torch.int32, device=dev)
+        for p in props:
+            n = len(p) * K
+            s, b = cand_s[o:o + n], cand_b[o:o + n]
+            o += n
+            order = torch.argsort(s, descending=True, stable=True)
+            ss, bb = s[order], b[order].contiguous()
+            cc = cls_id.repeat(len(p))[order]
+            n_valid = (ss > 0).sum().to(torch.int32)
+            cats = torch.where(torch.arange(n, device=dev) < n_valid, cc, -1 - torch.arange(n, dtype=torch.int32, device=dev)).contiguous()
+            keep, n_keep = nms_sorted(bb, cats, self.nms_thresh, self.topk)
+            res.append((bb, ss, cc, keep))
+            metas.append(torch.minimum(n_keep[0], ((keep < n_valid) & (torch.arange(self.topk, device=dev) < n_keep[0])).sum().to(torch.int32)))
+        counts = torch.stack(metas).cpu().tolist()                       # one host sync per batch
+        out = []
+        for (bb, ss, cc, keep), cnt in zip(res, counts):
+            kk = keep[:cnt].long()
+            out.append((bb[kk], ss[kk], cc[kk].long()))
+        return out
+
+    @torch.no_grad()
+    def forward_mask(self, feats, dets, out_size, image_size):
+        """Mask branch + detector_postprocess: returns per image a dict with pred_boxes / scores / pred_classes /
+        pred_masks (bool R x H x W)."""
+        L = _C.lib()
+        feats4 = [f.detach() for f in feats[:4]]
+        dev = feats4[0].device
+        boxes = [d[0] for d in dets]
+        results = []
+        R = sum(len(b) for b in boxes)
+        H, W = out_size
+        sx, sy = out_size[1] / image_size[1], out_size[0] / image_size[0]
+        if R > 0:
+            x = roi_align(feats4, _rois(boxes), 14)
+            for i in range(1, 5):
+                x = getattr(self.mask_head, f"mask_fcn{i}")(x, relu=True)
+            y4 = self.mask_head.deconv(x, relu=True)                     # R x 14 x 14 x (4 * 256)
+            y = torch.empty(R, 28, 28, 256, dtype=torch.float32, device=dev)
+            check(L.ttdg_pixel_shuffle2(_p(y4), R, 14, 14, 256, _p(y), _stream()), "pixel_shuffle")
+            logits = self.mask_head.predictor(y)                         # R x 28 x 28 x 4 (K used)
+        o = 0
+        for b, s, c in dets:
+            n = len(b)
+            bs = b * torch.tensor([sx, sy, sx, sy], device=dev)
+            bs = torch.stack((bs[:, 0].clamp(0, W), bs[:, 1].clamp(0, H), bs[:, 2].clamp(0, W), bs[:, 3].clamp(0, H)), dim=1).contiguous()
+            masks = torch.zeros(n, H, W, dtype=torch.uint8, device=dev)
+            if n:
+                lg = logits[o:o + n]
+                check(L.ttdg_mask_paste(_p(lg), lg.shape[-1], 28, _p(bs), _p(c.contiguous()), n, H, W, 0.5, _p(masks), _stream()), "mask_paste")
+            o += n
+            keep = ((bs[:, 2] - bs[:, 0]) > 0) & ((bs[:, 3] - bs[:, 1]) > 0)        # Boxes.nonempty()
+            results.append({"pred_boxes": bs[keep], "scores": s[keep], "pred_classes": c[keep], "pred_masks": masks[keep].bool()})
+        return results
+
+
+def preprocess(images_u8, device):
+    """d2 preprocess_image: list of uint8 3 x H x W (same size) -> N x H x W x 4 fp32 NHWC, mean-subtracted, padded to
+    a multiple of 32 (size_divisibility)."""
+    x = torch.stack(list(images_u8)).to(device, non_blocking=True).contiguous()
+    N, C, H, W = x.shape
+    assert C == 3 and x.dtype == torch.uint8
+    out = torch.empty(N, H, W, 4, dtype=torch.float32, device=device)
+    check(_C.lib().ttdg_preprocess(_p(x), N, H, W, *PIXEL_MEAN, _p(out), _stream()), "preprocess")
+    ph, pw = (32 - H % 32) % 32, (32 - W % 32) % 32
+    if ph or pw:
+        out = torch.nn.functional.pad(out, (0, 0, 0, pw, 0, ph)).contiguous()
+    return out
+
+
+class MaskRCNN(nn.Module):
+    """Backbone + PseudoLabRPN + StandardROIHeadsPseudoLab with d2's module / parameter names."""
+
+    def __init__(self, num_classes=2):
+        super().__init__()
+        self.backbone = Backbone()
+        self.proposal_generator = RPN()
+        self.roi_heads = ROIHeads(num_classes)
+
+    def adapted_parameters(self):
+        """Parameters the test-time loss reaches: res3-res5 and FPN (stem + res2 are frozen, FREEZE_AT = 2; RPN / ROI
+        heads are not in the TTT loss graph)."""
+        ps = []
+        for name in ("res3", "res4", "res5"):
+            ps += list(getattr(self.backbone.bottom_up, name).parameters())
+        for lvl in (2, 3, 4, 5):
+            ps += list(getattr(self.backbone, f"fpn_lateral{lvl}").parameters())
+            ps += list(getattr(self.backbone, f"fpn_output{lvl}").parameters())
+        return ps
+
+    def features(self, images_u8):
+        _need_cuda(*[p for p in [self.backbone.fpn_output2.weight]])
+        x = preprocess(images_u8, self.backbone.fpn_output2.weight.device)
+        return self.backbone(x)
+
+    def detect_ttt(self, images_u8):
+        """rcnn.py:331-345: features (NHWC, grad-carrying), RPN proposals and box-head detections in TRAIN mode."""
+        size = tuple(images_u8[0].shape[-2:])
+        feats = self.features(images_u8)
+        props = self.proposal_generator(feats, size, training=True)
+        dets = self.roi_heads.forward_box(feats, props, size)
+        return feats, props, dets
+
+    @torch.no_grad()
+    def inference(self, images_u8, out_sizes=None):
+        """GeneralizedRCNN.inference (rcnn.py:181-182): eval-mode detections with pasted masks."""
+        size = tuple(images_u8[0].shape[-2:])
+        feats = self.features(images_u8)
+        props = self.proposal_generator(feats, size, training=False)
+        dets = self.roi_heads.forward_box(feats, props, size)
+        return self.roi_heads.forward_mask(feats, dets, out_sizes or size, size), feats, props, dets

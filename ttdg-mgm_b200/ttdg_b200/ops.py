@@ -436,7 +436,8 @@ class _SamplerGather(torch.autograd.Function):
         plan = ctx.plan
         g = _f32c(gnodes)
         dev = g.device
-        grads = [torch.zeros(shape, dtype=torch.float32, device=dev) for shape, _ in ctx.shapes]
+        # same memory layout as the feature maps (NHWC pyramids stay NHWC: no transposes on the way back)
+        grads = [torch.empty_strided(shape, stride, dtype=torch.float32, device=dev).zero_() for shape, stride in ctx.shapes]
         ptrs = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in grads])
         strides = (ctypes.c_int64 * 15)(*[v for t in grads for v in (t.stride(0), t.stride(1), t.stride(3))])
         check(L.ttdg_sampler_scatter_bwd(_p(g), ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(strides, ctypes.c_void_p),

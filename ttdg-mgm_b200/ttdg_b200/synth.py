@@ -127,3 +127,117 @@ def sampler_feats(name):
     g = torch.Generator().manual_seed(c["seed"])
     B = len(c["boxes"])
     return [torch.randn(B, c["C"], c["S"] // s, c["S"] // s, generator=g) for s in (4, 8, 16, 32, 64)]
+
+
+# ---------------------------------------------------------------------------------------------- detector weights
+RES_STAGES = (("res2", 3, 64, 256, 1), ("res3", 4, 128, 512, 2), ("res4", 6, 256, 1024, 2), ("res5", 3, 512, 2048, 2))
+
+
+def detector_state(seed=0, num_classes=2, num_anchors=15):
+    """Random-init state dict of the Mask R-CNN R50-FPN detector with Detectron2 0.5 parameter names and
+    init distributions ([recalled]): c2_msra_fill (kaiming normal, fan_out) for ResNet / mask-head
+    convs, c2_xavier_fill (kaiming uniform, a=1) for FPN and box FCs, N(0, .01) for RPN and cls_score, N(0, .001) for
+    bbox_pred and the mask predictor, zero biases.  FrozenBN: gamma 1, beta 0, and - unlike a fresh d2 model - mildly
+    randomised running statistics so the fold scale/bias path is exercised (mean N(0, .1), var U(.5, 1.5)); no trained
+    checkpoint is available offline (README.md:96)."""
+    g = torch.Generator().manual_seed(5_000_003 + seed)
+    sd = {}
+
+    def msra(name, cout, cin, k):
+        std = math.sqrt(2.0 / (cout * k * k))
+        sd[name + ".weight"] = torch.randn(cout, cin, k, k, generator=g) * std
+
+    def xavier(name, shape, fan_in):
+        bound = math.sqrt(3.0 / fan_in)               # kaiming_uniform_(a=1)
+        sd[name + ".weight"] = _uniform(g, shape, bound)
+        sd[name + ".bias"] = torch.zeros(shape[0])
+
+    def normal(name, shape, std):
+        sd[name + ".weight"] = torch.randn(*shape, generator=g) * std
+        sd[name + ".bias"] = torch.zeros(shape[0])
+
+    def bn(name, c):
+        sd[name + ".weight"] = torch.ones(c)
+        sd[name + ".bias"] = torch.zeros(c)
+        sd[name + ".running_mean"] = torch.randn(c, generator=g) * 0.1
+        sd[name + ".running_var"] = torch.rand(c, generator=g) + 0.5
+
+    p = "backbone.bottom_up."
+    msra(p + "stem.conv1", 64, 3, 7)
+    bn(p + "stem.conv1.norm", 64)
+    cin = 64
+    for stage, blocks, mid, cout, _ in RES_STAGES:
+        for b in range(blocks):
+            q = f"{p}{stage}.{b}."
+            if b == 0:
+                msra(q + "shortcut", cout, cin, 1)
+                bn(q + "shortcut.norm", cout)
+            msra(q + "conv1", mid, cin, 1)
+            bn(q + "conv1.norm", mid)
+            msra(q + "conv2", mid, mid, 3)
+            bn(q + "conv2.norm", mid)
+            msra(q + "conv3", cout, mid, 1)
+            bn(q + "conv3.norm", cout)
+            cin = cout
+    for lvl, c in zip((2, 3, 4, 5), (256, 512, 1024, 2048)):
+        xavier(f"backbone.fpn_lateral{lvl}", (256, c, 1, 1), c)
+        xavier(f"backbone.fpn_output{lvl}", (256, 256, 3, 3), 256 * 9)
+    r = "proposal_generator.rpn_head."
+    normal(r + "conv", (256, 256, 3, 3), 0.01)
+    normal(r + "objectness_logits", (num_anchors, 256, 1, 1), 0.01)
+    normal(r + "anchor_deltas", (num_anchors * 4, 256, 1, 1), 0.01)
+    h = "roi_heads."
+    xavier(h + "box_head.fc1", (1024, 256 * 7 * 7), 256 * 7 * 7)
+    xavier(h + "box_head.fc2", (1024, 1024), 1024)
+    normal(h + "box_predictor.cls_score", (num_classes + 1, 1024), 0.01)
+    normal(h + "box_predictor.bbox_pred", (num_classes * 4, 1024), 0.001)
+    for i in range(1, 5):
+        msra(h + f"mask_head.mask_fcn{i}", 256, 256, 3)
+        sd[h + f"mask_head.mask_fcn{i}.bias"] = torch.zeros(256)
+    std = math.sqrt(2.0 / (256 * 2 * 2))
+    sd[h + "mask_head.deconv.weight"] = torch.randn(256, 256, 2, 2, generator=g) * std      # ConvTranspose2d: (in, out, kh, kw)
+    sd[h + "mask_head.deconv.bias"] = torch.zeros(256)
+    normal(h + "mask_head.predictor", (num_classes, 256, 1, 1), 0.001)
+    return sd
+
+
+def calibrate_frozen_bn(sd, size=128, n_images=2, seed=0):
+    """Sets every FrozenBN's running statistics to the statistics its input actually has on a few synthetic images
+    (what training would have left in a real checkpoint), so activations stay O(1) through the 16 residual blocks
+    and the detector produces a realistic workload (about a thousand proposals per image after NMS).  Plain torch on
+    the CPU, deterministic for a given machine; both the oracle and the CUDA path load the resulting dict."""
+    import torch.nn.functional as F
+    x = torch.stack([fundus_like_image(9000 + seed + i, size)["image"].float() for i in range(n_images)])
+    x = x - torch.tensor([103.530, 116.280, 123.675]).reshape(1, 3, 1, 1)
+
+    def conv_bn(x, name, stride=1, pad=0, relu=True):
+        y = F.conv2d(x, sd[name + ".weight"], None, stride, pad)
+        sd[name + ".norm.running_mean"] = y.mean(dim=(0, 2, 3))
+        sd[name + ".norm.running_var"] = y.var(dim=(0, 2, 3), unbiased=False) + 1e-3
+        scale = sd[name + ".norm.weight"] * (sd[name + ".norm.running_var"] + 1e-5).rsqrt()
+        y = (y - sd[name + ".norm.running_mean"].reshape(1, -1, 1, 1)) * scale.reshape(1, -1, 1, 1) + sd[name + ".norm.bias"].reshape(1, -1, 1, 1)
+        return F.relu(y) if relu else y
+
+    p = "backbone.bottom_up."
+    y = F.max_pool2d(conv_bn(x, p + "stem.conv1", 2, 3), 3, 2, 1)
+    for stage, blocks, _, _, stride in RES_STAGES:
+        for b in range(blocks):
+            q = f"{p}{stage}.{b}."
+            s = stride if b == 0 else 1
+            out = conv_bn(y, q + "conv1", s)
+            out = conv_bn(out, q + "conv2", 1, 1)
+            out = conv_bn(out, q + "conv3", relu=False)
+            sc = conv_bn(y, q + "shortcut", s, relu=False) if b == 0 else y
+            y = F.relu(out + sc)
+    return sd
+
+
+_DET_CACHE = {}
+
+
+def detector_state_calibrated(seed=0, num_classes=2):
+    key = (seed, num_classes)
+    if key not in _DET_CACHE:
+        with torch.no_grad():
+            _DET_CACHE[key] = calibrate_frozen_bn(detector_state(seed, num_classes), seed=seed)
+    return {k: v.clone() for k, v in _DET_CACHE[key].items()}
