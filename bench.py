@@ -4,14 +4,16 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Round-1 scope: one step = the MATCHING STAGE of one test-time-adaptation step on one batch
-of 8 synthetic 512x512 images per GPU (BASELINE.json configs[1]): node sampling from the FPN pyramid
-(PrototypeComputation) -> MGM3_unsup forward (attention adjacency, learned affinity, pairwise Sinkhorn, GA-GM
-solver with on-device Hungarian, matching loss) -> backward to the pyramid and the affinity parameters ->
-[NCCL all-reduce of the gradient bucket when N > 1] -> fused SGD step.  The detector's convolution stack is not
-built yet, so the pyramid is synthetic and resident in HBM; the JSON line says so in config.workload.
-
-The `roofline` object is the Sinkhorn kernel of BASELINE.json configs[4] (N = 1024, 50 iterations), timed live.
+One step = one batch of 8 synthetic 512x512 2-class images per GPU (BASELINE.json configs[1]) through BOTH passes of
+adapteacher/engine/trainer.py:469-485:
+  (1) test-time adaptation: detector forward in train mode (ResNet-50-FPN, RPN, box head) -> node sampler ->
+      MGM3_unsup (attention adjacency, affinity, Sinkhorn 20 iters, GA-GM with on-device Hungarian, matching loss)
+      -> backward through FPN + res3-res5 -> [NCCL all-reduce of the 26.97 M-element gradient bucket when N > 1]
+      -> fused SGD step;
+  (2) eval-mode inference with the adapted weights: detector forward, mask head, masks pasted to 512x512.
+`value` = adapted images / s with the uint8 images resident in HBM; `e2e` = the same from pinned HOST images through
+the plugin call (model(batched_inputs, branch='TTT') ... model(batched_inputs)) with the loss and a mask checksum read
+back.  `roofline` = the Sinkhorn kernel of BASELINE.json configs[4] (N = 1024, 50 iterations), timed live.
 """
 import argparse
 import json
@@ -43,40 +45,35 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def make_workload(rank, device):
-    """Per-rank batch: 8 seeded synthetic images' worth of FPN pyramid (resident in HBM) + the predicted boxes
-    the node sampler consumes (the synthetic images' disc / cup boxes)."""
+def make_inputs(rank):
+    """Per-rank batch of seeded synthetic fundus-like images (uint8 3 x 512 x 512), as the dataset mapper
+    would deliver them: list of dicts with 'image', 'height', 'width', 'image_id'."""
     from ttdg_b200 import synth
-    g = torch.Generator().manual_seed(4000 + rank)
-    feats = [torch.randn(IMAGES_PER_GPU, 256, IMG // s, IMG // s, generator=g).to(device) for s in (4, 8, 16, 32, 64)]
-    boxes, classes = [], []
+    out = []
     for i in range(IMAGES_PER_GPU):
         im = synth.fundus_like_image(rank * IMAGES_PER_GPU + i, IMG)
-        boxes.append(im["gt_boxes"].to(device))
-        classes.append(im["gt_classes"].to(device))
-    return feats, boxes, classes
+        out.append({"image": im["image"], "height": IMG, "width": IMG, "image_id": rank * IMAGES_PER_GPU + i})
+    return out
 
 
-class Inst:
-    def __init__(self, b, c):
-        self.pred_boxes = type("B", (), {"tensor": b})()
-        self.pred_classes = c
-        self._fields = {"pred_boxes": self.pred_boxes, "pred_classes": c}
-
-    def __len__(self):
-        return self.pred_boxes.tensor.shape[0]
+def full_state():
+    from ttdg_b200 import synth
+    sd = dict(synth.detector_state_calibrated(0, 2))
+    # matching head: the reference constructors' own init (affinity.py:33-42, mgm:124).  With it the adaptation is gentle
+    # and the workload stays stationary over the run (100 detections / image, 30-45 nodes / graph); the "perturbed"
+    # affinity used by some parity tests makes a RANDOM-init detector diverge within ~10 steps at lr 0.005.
+    sd.update({"multi_matching_unsup." + k: v for k, v in synth.mgm_unsup_state(0).items()})
+    sd["multi_matching_sup.U"] = synth.universe(0)
+    return sd
 
 
 def build_ours(device):
-    from adapteacher.modeling.GModule.build_graph import PrototypeComputation
-    from adapteacher.modeling.GModule.multi_graph_matching import MGM3_unsup
-    from ttdg_b200 import synth
+    from adapteacher.modeling.meta_arch.rcnn import DAobjTwoStagePseudoLabGeneralizedRCNN
     from ttdg_b200.optim import FlatSGD
-    m = MGM3_unsup(2, 32).to(device)
-    m.load_state_dict(synth.perturb_affinity_state(synth.mgm_unsup_state(0), 0))
-    m.train()                                        # TTT runs in train mode: Philox dropout on the adjacency
-    opt = FlatSGD(m.node_affinity.parameters(), lr=0.005, momentum=0.9, weight_decay=1e-4)
-    return m, opt, PrototypeComputation(2, 10), synth.universe(0).to(device)
+    m = DAobjTwoStagePseudoLabGeneralizedRCNN(2).to(device)
+    m.load_state_dict(full_state(), strict=False)
+    opt = FlatSGD(m.adapted_parameters(), lr=0.005, momentum=0.9, weight_decay=1e-4)
+    return m, opt
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -148,62 +145,56 @@ def sinkhorn_roofline(device, n=1024, batch=128, iters=50, launches=5, warm=3):
 
 
 # ------------------------------------------------------------------------------------------------ CPU leg (oracle port)
-def cpu_port_step(nodes_cpu, labels_cpu, sd, U):
-    from oracle import mgm_port                         # the one place bench.py executes oracle/: as the timed baseline
-    nodes = [n.clone().requires_grad_(True) for n in nodes_cpu]
-    sdg = {k: v.clone().requires_grad_(k.startswith("node_affinity.")) for k, v in sd.items()}
-    loss = mgm_port.mgm3_unsup_forward(sdg, nodes, labels_cpu, U)
-    loss.backward()
-    return float(loss)
-
-
-def cpu_baseline(nodes_cpu, labels_cpu, steps):
+def cpu_baseline(images_u8, steps):
+    """The reference's algorithm on the host cores: oracle/ttt_port.Trainer (TTT step + eval pass) on `images_u8`."""
+    from oracle import ttt_port                          # the one place bench.py executes oracle/: as the timed baseline
     from ttdg_b200 import synth
-    sd = synth.perturb_affinity_state(synth.mgm_unsup_state(0), 0)
-    U = synth.universe(0)
     torch.set_num_threads(os.cpu_count() or 1)
-    cpu_port_step(nodes_cpu, labels_cpu, sd, U)            # warm-up
+    tr = ttt_port.Trainer(synth.detector_state_calibrated(0, 2), synth.mgm_unsup_state(0), synth.universe(0))
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_port_step(nodes_cpu, labels_cpu, sd, U)
+        tr.ttt_step(images_u8)
+        tr.eval_pass(images_u8)
     dt = (time.perf_counter() - t0) / steps
-    return IMAGES_PER_GPU / dt, dt
+    return len(images_u8) / dt, dt
 
 
 # ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    workload = ("configs[1] MATCHING STAGE ONLY: 8 images/GPU at 512x512, 2 classes - node sampler over a synthetic "
-                "resident FPN pyramid + MGM3_unsup fwd/bwd (Sinkhorn 20 iters, GA-GM) + SGD; detector conv stack not "
-                "built yet (round 1)")
-    config = {"workload": workload, "images_per_gpu": IMAGES_PER_GPU, "image_size": IMG, "universe": 32,
-              "sinkhorn_iters": 20, "parallelism": f"image-sharded x{world}",
+    workload = ("configs[1]: batch of 8 synthetic 512x512 2-class fundus-like images per GPU; per image one share of a "
+                "test-time-adaptation step (Mask R-CNN R50-FPN fwd in train mode, node sampler, MGM3_unsup with Sinkhorn 20 "
+                "iters + GA-GM, backward through FPN+res3-5, SGD) plus one eval forward with masks pasted at 512x512")
+    config = {"workload": workload, "images_per_gpu": IMAGES_PER_GPU, "image_size": IMG, "num_classes": 2, "universe": 32,
+              "sinkhorn_iters": 20, "conv_math": "fp32 CUDA-core FMA (parity config; tcgen05 path is next)",
+              "weights": "random init, FrozenBN statistics calibrated on synthetic images (no checkpoint offline)",
+              "parallelism": f"image-sharded x{world}, NCCL all-reduce of the gradient bucket",
               "l2": "flushed between timed steps (256 MiB memset outside the per-step event pairs)"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        # the reference's own CPU implementation of the path: its Python cannot travel (/root/reference is absent on
-        # the GPU box and pure Python cannot be compiled into oracle/_ref), so the oracle port stands in (kind "port")
-        from ttdg_b200 import synth
-        sizes = (33, 34, 33, 33, 34, 33, 34, 33)
-        nodes, labels, _ = synth.mgm_inputs(sizes, 77)
-        steps = max(1, min(args.steps, 3))
-        val, dt = cpu_baseline(nodes, labels, steps)
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus,
-                          "steps": steps, "warmup": 1, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True,
+        # The reference's own Python cannot travel to the GPU box (/root/reference is absent there, Detectron2 0.5 is not
+        # installable, and pure Python cannot be compiled into oracle/_ref): the oracle port stands in (kind "port").
+        n_img = 2                                            # bounded sample: 2 of the 8 images per step
+        images = [d["image"] for d in make_inputs(0)[:n_img]]
+        steps = max(1, min(args.steps, 2))
+        cpu_baseline(images, 1)                              # warm-up
+        val, dt = cpu_baseline(images, steps)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": steps, "warmup": 1, "ms_per_step": round(dt * 1e3, 1), "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                           "sample": f"{steps} matching-stage steps of 8 graphs x ~33 nodes (fwd+bwd), torch CPU"},
-                          "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                           "sample": f"{steps} steps of {n_img} images (TTT step + eval pass), torch CPU, all cores"},
+                          "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (the product path has no CPU fallback)"
@@ -213,21 +204,29 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=device)
     from ttdg_b200 import _C
     lib = _C.lib()
-    m, opt, sampler, U = build_ours(device)
-    feats, boxes, classes = make_workload(rank, device)
-    feats = [f.requires_grad_(True) for f in feats]
-    targets = [Inst(b, c) for b, c in zip(boxes, classes)]
+    m, opt = build_ours(device)
+    inputs_host = make_inputs(rank)
+    for d in inputs_host:
+        d["image"] = d["image"].pin_memory()
+    inputs_dev = [dict(d, image=d["image"].to(device)) for d in inputs_host]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    stats = {"skipped": 0}
 
-    def step():
-        for f in feats:
-            f.grad = None
-        nodes, labels = sampler(feats, targets)
-        loss = m(nodes, labels, U)
-        opt.zero_grad()
-        loss.backward()
-        opt.step(world)
-        return loss
+    def step(inputs, readback):
+        m.train()                                            # pass 1: adaptation (trainer.py:469-482)
+        loss, _, _, _ = m(inputs, branch="TTT")
+        if loss is None:
+            stats["skipped"] += 1
+        else:
+            opt.zero_grad()
+            loss.backward()
+            opt.step(world)
+        m.eval()                                             # pass 2: inference with the adapted weights (trainer.py:484-485)
+        out = m(inputs)
+        if readback:
+            chk = sum(int(o["instances"].pred_masks.sum().item()) for o in out)
+            return (float(loss.item()) if loss is not None else None), chk
+        return None
 
     def barrier():
         torch.cuda.synchronize()
@@ -235,7 +234,7 @@ def main():
             torch.distributed.barrier()
 
     for _ in range(max(args.warmup, 3)):
-        step()
+        step(inputs_dev, False)
     barrier()
     clocks = ClockSampler(local_rank)
     l0 = lib.ttdg_launch_count()
@@ -243,7 +242,7 @@ def main():
     for a, b in evs:
         flush.zero_()
         a.record()
-        step()
+        step(inputs_dev, False)
         b.record()
     barrier()
     launches = lib.ttdg_launch_count() - l0
@@ -254,29 +253,15 @@ def main():
     ms_total = float(t.item())
     value = IMAGES_PER_GPU * world * args.steps / (ms_total * 1e-3)
 
-    # ---- end to end through the plugin call with HOST buffers: MGM3_unsup(nodes, labels, U) from pinned host memory
-    with torch.no_grad():
-        nodes_d, labels_d = sampler([f.detach() for f in feats], targets)
-    nodes_h = [n.cpu().pin_memory() for n in nodes_d]
-    labels_h = [l.cpu().pin_memory() for l in labels_d]
-    h2d = sum(n.numel() * 4 for n in nodes_h) + sum(l.numel() * 8 for l in labels_h)
-
-    def e2e_step():
-        nodes = [n.to(device, non_blocking=True).requires_grad_(True) for n in nodes_h]
-        labels = [l.to(device, non_blocking=True) for l in labels_h]
-        loss = m(nodes, labels, U)
-        opt.zero_grad()
-        loss.backward()
-        opt.step(world)
-        return float(loss.item())                     # device -> host read of the step's result
-
-    for _ in range(3):
-        e2e_step()
+    # ---- end to end through the plugin call with pinned HOST images; loss + mask checksum read back every step
+    h2d = sum(d["image"].numel() for d in inputs_host)
+    for _ in range(2):
+        step(inputs_host, True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        e2e_step()
+        last = step(inputs_host, True)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
@@ -287,21 +272,22 @@ def main():
 
     if rank == 0:
         roof = sinkhorn_roofline(device)
-        steps_cpu = 2
-        cpu_val, cpu_dt = cpu_baseline([n.float() for n in nodes_h], [l for l in labels_h], steps_cpu)
-        info = m.last_aux["info"].cpu().tolist()
+        n_cpu = 2
+        cpu_val, cpu_dt = cpu_baseline([d["image"] for d in make_inputs(0)[:n_cpu]], 1)
+        aux = m.multi_matching_unsup.last_aux
+        info = aux["info"].cpu().tolist()
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64-internal/f32-io", "data": "synthetic", "config": config,
-                "scope": "matching stage only - NOT yet the full adapted-images/s of BASELINE.json (no detector)",
-                "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                        "call": "MGM3_unsup(nodes, labels, U) from pinned host node features + backward + fused SGD"},
-                "gpu_launches": int(launches), "gagm": {"iterations": info[0], "lap_calls": info[3], "graphs": IMAGES_PER_GPU,
-                                                        "nodes": int(sum(n.shape[0] for n in nodes_h))},
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 + 8 * IMAGES_PER_GPU,
+                        "call": "model(batched_inputs, branch='TTT') + backward + FlatSGD.step + model(batched_inputs) from pinned host images",
+                        "last_loss": last[0], "mask_pixels": last[1]},
+                "gpu_launches": int(launches), "skipped_steps": stats["skipped"],
+                "gagm": {"iterations": info[0], "lap_calls": info[3], "graphs": len(aux["sizes"]), "nodes": int(sum(aux["sizes"]))},
                 "clocks": clk, "roofline": roof,
-                "cpu_baseline": {"value": round(cpu_val, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                 "sample": f"{steps_cpu} matching-stage steps (same 8 graphs, fwd+bwd) with the oracle port on "
-                                           f"torch CPU, {cpu_dt:.2f} s/step"}}
+                "cpu_baseline": {"value": round(cpu_val, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                 "sample": f"1 step of {n_cpu} of the 8 images (TTT step + eval pass) with the oracle port on torch "
+                                           f"CPU, {cpu_dt:.1f} s"}}
         print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()

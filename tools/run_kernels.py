@@ -31,4 +31,16 @@ elif what in ("gagm", "mgm_step"):
         loss = m([n.to(dev).requires_grad_(True) for n in nodes], [l.to(dev) for l in labels], U)
         loss.backward()
     print("gagm info", m.last_aux["info"].tolist())
+elif what == "full_step":
+    sys.path.insert(0, ROOT)
+    import bench
+    m, opt = bench.build_ours(dev)
+    inputs = [dict(d, image=d["image"].to(dev)) for d in bench.make_inputs(0)]
+    for _ in range(reps):
+        m.train()
+        loss, _, _, _ = m(inputs, branch="TTT")
+        opt.zero_grad(); loss.backward(); opt.step(1)
+        m.eval()
+        out = m(inputs)
+    print("loss", float(loss), "dets", [len(o["instances"]) for o in out])
 torch.cuda.synchronize()

@@ -89,9 +89,14 @@ class MGM3_unsup(nn.Module):
     def forward(self, nodes, labels, U):
         if nodes is None or len(nodes) == 1:
             return None                                                           # mgm:489-490
+        # an image whose boxes contain no in-range FPN location yields a 0-node graph; the reference's Sinkhorn /
+        # Hungarian calls are undefined on empty matrices, so such graphs are dropped here (documented deviation)
+        nodes = [n for n in nodes if n.shape[0] > 0]
+        if len(nodes) < 2:
+            return None
         sizes = [int(n.shape[0]) for n in nodes]
-        if max(sizes) > 96 or min(sizes) < 1:
-            raise ValueError("graphs must have 1..96 nodes (the sampler yields at most 95, build_graph.py:189-195)")
+        if max(sizes) > 96:
+            raise ValueError("graphs must have at most 96 nodes (the sampler yields at most 95, build_graph.py:189-195)")
         X = torch.cat(list(nodes), dim=0)                                        # M x 256, carries the gradient
         with torch.no_grad():
             A = self.intra_domain_graph.adjacency(X, sizes, self.debug_keep_masks)          # mgm:496-502

@@ -251,13 +251,15 @@ relu_bn_bwd_kernel(const float *__restrict__ g, const float *__restrict__ y, con
     }
 }
 
-// out[c] = sum over pixels of g[pixel][c]   (bias gradient); one CTA per 32 channels
+// out[c] += sum over pixels of g[pixel][c]   (bias gradient); grid (C / 32, pixel chunks), one atomic per (CTA, channel)
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(const float *__restrict__ g, int64_t P, int C, float *__restrict__ out) {
     __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), pr = threadIdx.x >> 5;
+    const int64_t per = (P + gridDim.y - 1) / gridDim.y;
+    const int64_t p0 = (int64_t)blockIdx.y * per, p1 = min(P, p0 + per);
     float s = 0.f;
-    if (c < C) for (int64_t p = pr; p < P; p += 8) s += g[p * C + c];
+    if (c < C) for (int64_t p = p0 + pr; p < p1; p += 8) s += g[p * C + c];
     red[pr][threadIdx.x & 31] = s;
     __syncthreads();
     if (pr == 0 && c < C) {
@@ -426,7 +428,9 @@ extern "C" int ttdg_bias_grad(const float *g, int64_t pixels, int C, float *out,
     TTDG_CHECK_ARG(g && out && pixels >= 0 && C > 0);
     if (pixels == 0) return 0;
     count_launches(1);
-    bias_grad_kernel<<<ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(g, pixels, C, out);
+    int chunks = (int)((pixels + 1023) / 1024);
+    if (chunks > 148) chunks = 148;
+    bias_grad_kernel<<<dim3(ceil_div(C, 32), chunks), 256, 0, (cudaStream_t)stream>>>(g, pixels, C, out);
     TTDG_LAUNCH_RET();
 }
 

@@ -108,26 +108,43 @@ nms_mask_kernel(const float *__restrict__ boxes, const int32_t *__restrict__ cat
     mask[(size_t)i * words + cb] = bits;
 }
 
-// sequential sweep of the suppression mask; one CTA.  keep[] receives the kept indices in order, *n_keep their number.
+// Sweep of the suppression mask, one CTA, 64 boxes per round: thread 0 resolves the round's diagonal word serially in
+// registers (64 bit-steps, no barriers), then all threads OR the mask rows of the survivors into `removed`.
+// keep[] receives the kept indices in order, *n_keep their number (capped at max_keep).
 __global__ void __launch_bounds__(256)
 nms_sweep_kernel(const unsigned long long *__restrict__ mask, int n, int words, int max_keep, int32_t *__restrict__ keep,
                  int32_t *__restrict__ n_keep) {
     extern __shared__ unsigned long long removed[];
-    for (int w = threadIdx.x; w < words; w += 256) removed[w] = 0ull;
+    __shared__ unsigned long long diag[64];
+    __shared__ unsigned long long kept_bits;
     __shared__ int cnt;
+    for (int w = threadIdx.x; w < words; w += 256) removed[w] = 0ull;
     if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
-    for (int i = 0; i < n; ++i) {
-        const bool dead = (removed[i >> 6] >> (i & 63)) & 1ull;          // uniform
-        if (!dead) {
-            if (threadIdx.x == 0) { if (cnt < max_keep) keep[cnt] = i; ++cnt; }
-            __syncthreads();
-            if (cnt >= max_keep) break;
-            for (int w = (i >> 6) + threadIdx.x; w < words; w += 256) removed[w] |= mask[(size_t)i * words + w];
-            __syncthreads();
+    for (int wb = 0; wb < words; ++wb) {
+        const int base = wb * 64, nb = min(64, n - base);
+        if (threadIdx.x < nb) diag[threadIdx.x] = mask[(size_t)(base + threadIdx.x) * words + wb];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long dead = removed[wb], kb = 0ull;
+            int c = cnt;
+            for (int j = 0; j < nb && c < max_keep; ++j) {
+                if (!((dead >> j) & 1ull)) { kb |= 1ull << j; keep[c++] = base + j; dead |= diag[j]; }
+            }
+            kept_bits = kb;
+            cnt = c;
         }
+        __syncthreads();
+        if (cnt >= max_keep) break;
+        unsigned long long kb = kept_bits;
+        while (kb) {
+            const int j = __ffsll((long long)kb) - 1;
+            kb &= kb - 1;
+            const unsigned long long *row = mask + (size_t)(base + j) * words;
+            for (int w = wb + 1 + threadIdx.x; w < words; w += 256) removed[w] |= row[w];
+        }
+        __syncthreads();
     }
-    __syncthreads();
     if (threadIdx.x == 0) *n_keep = cnt < max_keep ? cnt : max_keep;
 }
 
