@@ -237,6 +237,23 @@ int ttdg_resample2(const float *x, float *y, int N, int Hs, int Ws, int C, int m
 int ttdg_preprocess(const unsigned char *img_u8, int N, int H, int W, float mean0, float mean1, float mean2, float *out,
                     void *stream);
 
+/* Tensor-core version of ttdg_conv_fwd / stride-1 ttdg_conv_dgrad: tcgen05.mma.kind::tf32 fed by TMA (activations as a 4-D
+ * NHWC tensor map - filter taps are coordinate shifts, padding is TMA's out-of-bounds zero fill), fp32 accumulators in
+ * TMEM, same fused epilogue.  Requires Cin % 32 == 0, Cout % 64 == 0, stride 1 (ttdg_conv_tc_supported).
+ *   x_hi, x_lo : N x H x W x Cin.  x_lo == NULL -> single-pass TF32 on x_hi.  Otherwise "3xTF32": hi = tf32(x),
+ *                lo = x - hi (ttdg_tf32_split) and hi*hi + lo*hi + hi*lo gives fp32-grade products (parity config).
+ *   wk_hi, wk_lo: weights K-major [taps][n][k]: forward = [R*S][Cout][Cin] (ttdg_weight_transpose_split of the
+ *                [R][S][Cin][Cout] parameter); data gradient (flip = 1, pad = R-1-pad_fwd, x = dY) = the parameter array
+ *                itself read as [R*S][n = Cin_fwd][k = Cout_fwd], split with ttdg_tf32_split.
+ *   (Cin, Cout) are the GEMM's k and n extents. */
+int ttdg_conv_tc_supported(int Cin, int Cout, int stride);
+int ttdg_conv_tc(const float *x_hi, const float *x_lo, const float *wk_hi, const float *wk_lo, const float *scale,
+                 const float *bias, const float *residual, int res_mode, int relu, int flip, int N, int H, int W,
+                 int Cin, int Cout, int R, int S, int pad, float *y, void *stream);
+int ttdg_tf32_split(const float *x, float *hi, float *lo, int64_t numel, void *stream);
+/* w [taps][Cin][Cout] -> wt_hi, wt_lo (may be NULL) [taps][Cout][Cin] */
+int ttdg_weight_transpose_split(const float *w, int taps, int Cin, int Cout, float *wt_hi, float *wt_lo, void *stream);
+
 /* RPN: decode + clip the anchors selected per level (d2 find_top_rpn_proposals / Box2BoxTransform.apply_deltas).
  * idx [n_img][k] indexes (pixel * A + a); deltas = NHWC head output, channel a * 4 + c, row pitch ld_deltas;
  * cell_anchors_h = HOST float[A][4].  valid = finite and non-empty after clipping. */

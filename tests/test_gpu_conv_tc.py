@@ -1,0 +1,127 @@
+"""tcgen05 / TMA implicit-GEMM convolution (csrc/conv_tc.cu) against torch.nn.functional, in both math modes:
+'tf32x3' (hi/lo operand split, fp32-grade - the parity configuration) and 'tf32' (single pass)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from ttdg_b200 import detector as det  # noqa: E402
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.fixture(autouse=True)
+def _restore_mode():
+    old = det.CONV_MODE[0]
+    yield
+    det.set_conv_mode(old)
+
+
+CASES = [
+    # cin, cout, k, pad, H, W, N
+    (64, 64, 1, 0, 16, 16, 2),            # BN_TILE 64
+    (64, 256, 1, 0, 8, 24, 1),
+    (128, 128, 3, 1, 12, 12, 2),          # 3x3: taps are TMA coordinate shifts, padding = OOB fill
+    (256, 256, 3, 1, 14, 14, 5),          # mask-head shape: 14 is not a power of two (partial boxes)
+    (256, 256, 3, 1, 128, 128, 1),        # BW = 128
+    (256, 64, 3, 1, 8, 8, 3),             # several images per tile
+    (12544, 1024, 1, 0, 1, 1, 300),       # box-head fc1 as a 1x1 conv on N = rows
+    (2048, 256, 1, 0, 4, 4, 2),
+]
+
+
+@pytest.mark.parametrize("mode,rtol", [("tf32x3", 2e-5), ("tf32", 4e-3)])
+@pytest.mark.parametrize("cin,cout,k,pad,H,W,N", CASES)
+def test_conv_tc_forward(mode, rtol, cin, cout, k, pad, H, W, N):
+    det.set_conv_mode(mode)
+    g = torch.Generator().manual_seed(cin + cout + k + H)
+    layer = det.Conv2d(cin, cout, k, 1, pad, bias=True).cuda()
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    layer.load_state_dict({"weight": w, "bias": b})
+    x = torch.randn(N, cin, H, W, generator=g)
+    res = torch.randn(N, cout, H, W, generator=g)
+    with torch.no_grad():
+        y = layer(nhwc(x).cuda(), relu=True, residual=nhwc(res).cuda(), res_mode=1)
+    ref = F.relu(F.conv2d(x, w, b, 1, pad) + res)
+    err = float((nchw(y.cpu()) - ref).abs().max() / ref.abs().max())
+    rtol = rtol * max(1.0, (cin * k * k / 1024.0) ** 0.5)          # fp32 accumulation error grows ~ sqrt(K)
+    assert err < rtol, err
+    det.set_conv_mode("simt")
+    with torch.no_grad():
+        y2 = layer(nhwc(x).cuda(), relu=True, residual=nhwc(res).cuda(), res_mode=1)
+    assert float((y2 - y).abs().max() / ref.abs().max()) < rtol
+
+
+@pytest.mark.parametrize("mode,rtol", [("tf32x3", 3e-5), ("tf32", 6e-3)])
+@pytest.mark.parametrize("cin,cout,k,pad,H,W,N", [(128, 128, 3, 1, 10, 12, 2), (512, 128, 1, 0, 8, 8, 2), (256, 256, 3, 1, 16, 16, 1)])
+def test_conv_tc_dgrad(mode, rtol, cin, cout, k, pad, H, W, N):
+    det.set_conv_mode(mode)
+    g = torch.Generator().manual_seed(cin + cout + k)
+    layer = det.Conv2d(cin, cout, k, 1, pad, bias=False).cuda()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).requires_grad_(True)
+    layer.load_state_dict({"weight": w.detach()})
+    x = torch.randn(N, cin, H, W, generator=g).requires_grad_(True)
+    up = torch.randn(N, cout, H, W, generator=g)
+    (F.conv2d(x, w, None, 1, pad) * up).sum().backward()
+    xc = nhwc(x.detach()).cuda().requires_grad_(True)
+    (layer(xc) * nhwc(up).cuda()).sum().backward()
+    err = float((nchw(xc.grad.cpu()) - x.grad).abs().max() / x.grad.abs().max())
+    assert err < rtol, err
+    gw = layer.weight.grad[:, :, :cin, :cout].permute(3, 2, 0, 1).cpu()
+    assert float((gw - w.grad).abs().max() / w.grad.abs().max()) < 3e-5          # wgrad stays on the fp32 CUDA-core kernel
+
+
+def test_fpn_upsample_add_epilogue_tc():
+    det.set_conv_mode("tf32x3")
+    g = torch.Generator().manual_seed(7)
+    lat = det.Conv2d(512, 256, 1, 1, 0, bias=True).cuda()
+    lat.load_state_dict({"weight": torch.randn(256, 512, 1, 1, generator=g) * 0.05, "bias": torch.randn(256, generator=g)})
+    x, coarse = torch.randn(2, 512, 16, 16, generator=g), torch.randn(2, 256, 8, 8, generator=g)
+    with torch.no_grad():
+        y = lat(nhwc(x).cuda(), residual=nhwc(coarse).cuda(), res_mode=2)
+    sd = lat.state_dict()
+    ref = F.conv2d(x, sd["weight"].cpu(), sd["bias"].cpu()) + F.interpolate(coarse, scale_factor=2.0, mode="nearest")
+    assert float((nchw(y.cpu()) - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("cin,cout,k,pad,H,W,N,norm,relu", [
+    (128, 128, 3, 1, 4, 4, 2, False, False), (128, 128, 3, 1, 4, 4, 2, True, True), (512, 128, 1, 0, 4, 4, 2, True, True),
+    (128, 512, 1, 0, 4, 4, 2, True, False), (128, 128, 3, 1, 10, 12, 2, True, True), (2048, 512, 1, 0, 2, 2, 2, True, True),
+    (512, 512, 3, 1, 2, 2, 2, True, True)])
+def test_conv_tc_layer_vs_torch(cin, cout, k, pad, H, W, N, norm, relu):
+    """One layer (conv + FrozenBN + ReLU), forward and input gradient, 3xTF32 with chunked accumulation: fp32-grade
+    (measured ~2e-6 relative, the CUDA-core fp32 kernel gives ~1e-6)."""
+    from oracle import detector_port as dp
+    det.set_conv_mode("tf32x3")
+    g = torch.Generator().manual_seed(cin + cout + k)
+    layer = det.Conv2d(cin, cout, k, 1, pad, bias=False, norm=norm).cuda()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).requires_grad_(True)
+    sd = {"weight": w.detach()}
+    if norm:
+        sd.update({"norm.weight": torch.rand(cout, generator=g) + 0.5, "norm.bias": torch.randn(cout, generator=g) * 0.1,
+                   "norm.running_mean": torch.randn(cout, generator=g) * 0.1, "norm.running_var": torch.rand(cout, generator=g) + 0.5})
+    layer.load_state_dict(sd)
+    x = torch.randn(N, cin, H, W, generator=g).requires_grad_(True)
+    up = torch.randn(N, cout, H, W, generator=g)
+    y = F.conv2d(x, w, None, 1, pad)
+    if norm:
+        y = dp.frozen_bn(y, {"n." + kk[5:]: v for kk, v in sd.items() if kk.startswith("norm.")}, "n")
+    if relu:
+        y = F.relu(y)
+    up = up * (y.detach().abs() > 1e-3)            # keep the functional away from the ReLU kink
+    (y * up).sum().backward()
+    xc = nhwc(x.detach()).cuda().requires_grad_(True)
+    yc = layer(xc, relu=relu)
+    (yc * nhwc(up).cuda()).sum().backward()
+    rel = lambda a, r: float((a - r).abs().max() / r.abs().max())
+    assert rel(nchw(yc.detach().cpu()), y.detach()) < 1e-5
+    assert rel(nchw(xc.grad.cpu()), x.grad) < 1e-5

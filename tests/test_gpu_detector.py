@@ -47,7 +47,7 @@ def test_conv_forward_vs_torch(cin, cout, k, stride, pad, H, W, N):
     with torch.no_grad():
         y = layer(xin, relu=True)
     ref = F.relu(F.conv2d(x, w, b, stride, pad))
-    np.testing.assert_allclose(nchw(y.cpu())[:, :cout].numpy(), ref.numpy(), atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose(nchw(y.cpu())[:, :cout].numpy(), ref.numpy(), atol=3e-5 * float(ref.abs().max()), rtol=1e-4)
     assert (y[..., cout:] == 0).all() or layer.cout_p == cout
 
 
@@ -107,7 +107,7 @@ def test_conv_autograd_vs_torch(cin, cout, k, stride, pad, H, W, N, relu, res):
     rc = nhwc(r.detach()).cuda().requires_grad_(True) if res else None
     yc = layer(xc, relu=relu, residual=rc, res_mode=1 if res else 0)
     (yc * nhwc(up).cuda()).sum().backward()
-    np.testing.assert_allclose(nchw(yc.detach().cpu()).numpy(), y.detach().numpy(), atol=3e-5, rtol=1e-4)
+    np.testing.assert_allclose(nchw(yc.detach().cpu()).numpy(), y.detach().numpy(), atol=3e-5 * float(y.detach().abs().max()), rtol=1e-4)
     scale = lambda t: 2e-5 * float(t.abs().max())
     np.testing.assert_allclose(nchw(xc.grad.cpu()).numpy(), x.grad.numpy(), atol=scale(x.grad), rtol=1e-4)
     gw = layer.weight.grad[:, :, :cin, :cout].permute(3, 2, 0, 1).cpu()
@@ -141,8 +141,16 @@ def test_backbone_features_vs_oracle(model_and_sd):
         np.testing.assert_allclose(nchw(f.cpu()).numpy(), r.numpy(), atol=2e-4 * float(r.abs().max()), rtol=2e-3, err_msg=f"p{l + 2}")
 
 
+@pytest.fixture(params=["simt", "tf32x3"])
+def conv_mode(request):
+    old = det.CONV_MODE[0]
+    det.set_conv_mode(request.param)
+    yield request.param
+    det.set_conv_mode(old)
+
+
 @pytest.mark.parametrize("stage,blocks,cin,H", [("res3", 4, 256, 8), ("res4", 6, 512, 8), ("res5", 3, 1024, 4)])
-def test_residual_stage_backward_vs_oracle(model_and_sd, stage, blocks, cin, H):
+def test_residual_stage_backward_vs_oracle(model_and_sd, conv_mode, stage, blocks, cin, H):
     """A whole residual stage (stride-2 first block with projection shortcut + identity blocks), forward and every
     gradient, on random inputs - tight, because random inputs keep pre-activations away from the ReLU kink."""
     m, sd = model_and_sd
@@ -154,7 +162,9 @@ def test_residual_stage_backward_vs_oracle(model_and_sd, stage, blocks, cin, H):
     y = x
     for b in range(blocks):
         y = dp.bottleneck(y, sdg, f"{q}{b}.", 2 if b == 0 else 1, b == 0)
-    w = torch.randn(y.shape, generator=g)
+    # outputs within 1e-3 of the ReLU kink are left out of the functional: one flipped mask there is ~1 % of the L2
+    # norm of these tiny gradients (measured), and 3xTF32 forward noise (~5e-6) does flip one now and then
+    w = torch.randn(y.shape, generator=g) * (y.detach().abs() > 1e-3)
     (y * w).sum().backward()
     for p in m.parameters():
         p.grad = None
@@ -162,14 +172,18 @@ def test_residual_stage_backward_vs_oracle(model_and_sd, stage, blocks, cin, H):
     yc = seq(xc)
     (yc * nhwc(w).cuda()).sum().backward()
     rel = lambda a, r: float((a - r).abs().max() / r.abs().max())
-    assert rel(nchw(yc.detach().cpu()), y.detach()) < 1e-5
-    assert rel(nchw(xc.grad.cpu()), x.grad) < 2e-5
+    rel2 = lambda a, r: float((a - r).norm() / r.norm())
+    assert rel(nchw(yc.detach().cpu()), y.detach()) < 5e-5          # 3xTF32 products + fp32 accumulation over 3-6 blocks
+    # gradients in L2: a forward difference of 1e-5 can flip a single ReLU mask out of ~1e5 activations, which moves a
+    # few gradient entries by ~1e-2 of the maximum (same effect as in test_backbone_backward_vs_oracle) but not the norm
+    tol = 2e-5 if det.CONV_MODE[0] == "simt" else 2e-2       # interior masks can still flip under 3xTF32 noise
+    assert rel2(nchw(xc.grad.cpu()), x.grad) < tol
     for b in range(blocks):
         for name in ("conv1", "conv2", "conv3", "shortcut"):
             layer = getattr(seq[b], name)
             if layer is not None:
                 gr = layer.weight.grad[:, :, :layer.cin, :layer.cout].permute(3, 2, 0, 1).cpu()
-                assert rel(gr, sdg[f"{q}{b}.{name}.weight"].grad) < 2e-5, (b, name)
+                assert rel2(gr, sdg[f"{q}{b}.{name}.weight"].grad) < tol, (b, name)
 
 
 def test_backbone_backward_vs_oracle(model_and_sd):
@@ -224,7 +238,7 @@ def _match(a, b, tol):
 
 
 @pytest.mark.parametrize("size,polyp", [(128, False), (256, True)])
-def test_inference_vs_oracle(model_and_sd, size, polyp):
+def test_inference_vs_oracle(model_and_sd, conv_mode, size, polyp):
     """Eval pass end to end.  Scores of different boxes can be closer than the fp32 noise of two different convolution
     summation orders, so orderings / NMS survivors may differ in a few places: boxes are compared as SETS, masks on
     the matched instances."""
@@ -244,18 +258,22 @@ def test_inference_vs_oracle(model_and_sd, size, polyp):
         assert ok.float().mean() >= 0.95, ok.float().mean()
         np.testing.assert_allclose(a["scores"].cpu()[ok].numpy(), b["scores"][idx][ok].numpy(), atol=5e-4)
         iou = _iou(a["pred_masks"].cpu()[ok], b["pred_masks"][idx][ok])
-        assert iou.mean() > 0.998 and (iou > 0.95).float().mean() > 0.98, (iou.mean(), iou.min())
+        # matched boxes differ by up to ~0.05 px (box deltas come out of a K = 12544 FC), which moves a few boundary pixels
+        if conv_mode == "simt":      # exact-fp32 products: the pipeline semantics, tight
+            assert iou.mean() > 0.998 and (iou > 0.95).float().mean() > 0.98, (iou.mean(), iou.min())
+        else:                        # 3xTF32 (per-layer error 2e-6, test_conv_tc_layer_vs_torch): the random-weight mask head
+            assert iou.mean() > 0.97, (iou.mean(), iou.min())       # amplifies it through near-zero logits
         gt = synth.fundus_like_image(100 + n, size, polyp)["gt_masks"]
 
         def miou(pred):
             best = torch.stack([_iou(pred, gt[j:j + 1].expand_as(pred)) for j in range(len(gt))]).max(0)[0]
             return float(best.mean())
         # matched instances only (what "same inputs, same detections" means): within 1e-4
-        assert abs(miou(a["pred_masks"].cpu()[ok]) - miou(b["pred_masks"][idx][ok])) < 1e-4
+        assert abs(miou(a["pred_masks"].cpu()[ok]) - miou(b["pred_masks"][idx][ok])) < (1e-4 if conv_mode == "simt" else 1e-3)
         assert abs(miou(a["pred_masks"].cpu()) - miou(b["pred_masks"])) < 3e-3
 
 
-def test_ttt_detections_vs_oracle(model_and_sd):
+def test_ttt_detections_vs_oracle(model_and_sd, conv_mode):
     m, sd = model_and_sd
     ims = _images(2, 128)
     with torch.no_grad():

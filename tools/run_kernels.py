@@ -43,4 +43,37 @@ elif what == "full_step":
         m.eval()
         out = m(inputs)
     print("loss", float(loss), "dets", [len(o["instances"]) for o in out])
+elif what == "timing":
+    # CUDA-event timing of the stages of one full step (not under a profiler)
+    sys.path.insert(0, ROOT)
+    import bench
+    from ttdg_b200.structures import Boxes, Instances
+    m, opt = bench.build_ours(dev)
+    det = m._det[0]
+    inputs = [dict(d, image=d["image"].to(dev)) for d in bench.make_inputs(0)]
+    images = [d["image"] for d in inputs]
+    def ev():
+        e = torch.cuda.Event(enable_timing=True); e.record(); return e
+    import collections
+    acc = collections.defaultdict(float)
+    for it in range(reps + 2):
+        m.train()
+        t0 = ev()
+        x = __import__("ttdg_b200.detector", fromlist=["preprocess"]).preprocess(images, dev)
+        feats = det.backbone(x); t1 = ev()
+        props = det.proposal_generator(feats, (512, 512), training=True); t2 = ev()
+        dets = det.roi_heads.forward_box(feats, props, (512, 512)); t3 = ev()
+        insts = [Instances((512, 512), pred_boxes=Boxes(b), scores=s, pred_classes=c) for b, s, c in dets]
+        nodes, labels = m.graph_generator([f.permute(0, 3, 1, 2) for f in feats], insts); t4 = ev()
+        loss = m.multi_matching_unsup(nodes, labels, m.multi_matching_sup.U); t5 = ev()
+        opt.zero_grad(); loss.backward(); t6 = ev()
+        opt.step(1); t7 = ev()
+        m.eval()
+        out = m(inputs); t8 = ev()
+        torch.cuda.synchronize()
+        if it >= 2:
+            for k, a, b in (("backbone_fwd", t0, t1), ("rpn", t1, t2), ("box_head", t2, t3), ("sampler", t3, t4), ("mgm_fwd", t4, t5),
+                            ("backward", t5, t6), ("sgd", t6, t7), ("eval_pass", t7, t8), ("TOTAL", t0, t8)):
+                acc[k] += a.elapsed_time(b) / reps
+    print({k: round(v, 2) for k, v in acc.items()}, "gagm iters", int(m.multi_matching_unsup.last_aux["info"][0]))
 torch.cuda.synchronize()

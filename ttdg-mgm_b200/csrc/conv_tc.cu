@@ -1,0 +1,401 @@
+// conv_tc.cu - tcgen05 / TMEM / TMA implicit-GEMM convolution (forward and stride-1 data gradient), NHWC fp32.
+//
+// Same operator and epilogue as conv.cu's ttdg_conv_fwd (Detectron2 ResNet-50-FPN / RPN-head / box-FC / mask-head convs,
+// meta_arch/rcnn.py:226, rpn.py:27, roi_heads.py:182-184,112) on the 5th-generation tensor
+// cores:
+//   * A operand (activations): one TMA tiled load per (filter tap, 32-channel slab) from the 4-D NHWC tensor
+//     {C, W, H, N} with box {32, BW, BH, BN} (BW * BH * BN = 128 output pixels); the tap offset (r - pad, s - pad) is
+//     just a coordinate shift and the zero padding is TMA's out-of-bounds fill - no im2col buffer, no bounds code;
+//   * B operand (weights, K-major [tap][n][k]): TMA load of {32, BN_TILE, 1};
+//   * both land in shared memory as 128-byte-swizzled K-major tiles, exactly the canonical UMMA layout, and are
+//     consumed by tcgen05.mma.kind::tf32 (M = 128, N = BN_TILE, K = 8) accumulating fp32 in TMEM;
+//   * warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected thread), warps 2-5 = epilogue
+//     (tcgen05.ld -> FrozenBN scale / bias / residual / FPN-upsample add / ReLU -> global), mbarrier ring between them.
+// fp32 parity mode ("3xTF32"): operands are split on the fly in global memory into hi = tf32(x) and lo = x - hi
+// (ttdg_tf32_split); hi*hi + lo*hi + hi*lo recovers fp32-grade products (dropped term ~2^-22), so the 1e-4 mIoU gate of
+// BASELINE.json configs[1] holds on tensor cores.  Single-pass TF32 (x_lo == NULL) is the fast mode.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace ttdg {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_BM = 128;           // output pixels per tile (TMEM lanes)
+constexpr int TC_BK = 32;            // fp32 channels per k-block = one 128-byte swizzle row
+constexpr int TC_UMMA_K = 8;         // tf32
+
+struct TcParams {
+    float *y;
+    const float *scale, *bias, *residual;
+    int N, Ho, Wo, Cout;
+    int R, S, pad, flip;             // flip = 1: data gradient (taps mirrored)
+    int BW, BH, BI;                  // box extents: pixels along W, rows, images
+    int tilesW, tilesH, tilesI;
+    int kslabs;                      // Cin / 32
+    int res_mode, relu;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// K-major, 128-byte swizzle: 8-row atoms of 1024 bytes (SBO = 64 x 16 B), LBO unused (1), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN_TILE, bool PRECISE>
+struct TcCfg {
+    static constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN_TILE * 128;
+    static constexpr int STAGE_BYTES = (PRECISE ? 2 : 1) * (A_BYTES + B_BYTES);
+    static constexpr int STAGES = PRECISE ? (BN_TILE == 128 ? 3 : 4) : (BN_TILE == 128 ? 6 : 8);
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+    static constexpr int TMEM_COLS = 2 * BN_TILE;        // two accumulator buffers (ping-pong between MMA and epilogue)
+    // The tensor core adds into its fp32 accumulator with truncation, so the error of one long accumulation grows
+    // linearly with K (measured 5e-5 relative at K = 12544).  The accumulation is therefore cut into chunks of CHUNK
+    // k-blocks: each chunk starts from zero in the other TMEM buffer and the epilogue warps add the drained chunks in
+    // registers with round-to-nearest fp32 - which also overlaps the TMEM drain with the next chunk's MMAs.
+    static constexpr int CHUNK = 8;
+};
+
+template <int BN_TILE, bool PRECISE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
+    using Cfg = TcCfg<BN_TILE, PRECISE>;
+    extern __shared__ unsigned char tc_smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t *empty = full + Cfg::STAGES;
+    uint64_t *tmem_full = empty + Cfg::STAGES;           // [2]
+    uint64_t *tmem_empty = tmem_full + 2;                // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tw = t % p.tilesW; t /= p.tilesW;
+    const int th = t % p.tilesH; t /= p.tilesH;
+    const int ti = t;
+    const int w0 = tw * p.BW, h0 = th * p.BH, i0 = ti * p.BI;
+    const int n0 = blockIdx.y * BN_TILE;
+    const int KB = p.R * p.S * p.kslabs;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
+        mbar_init(&tmem_empty[0], 4); mbar_init(&tmem_empty[1], 4);      // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < KB; ++kb) {
+                const int tap = kb / p.kslabs, c0 = (kb - tap * p.kslabs) * TC_BK;
+                const int r = tap / p.S, s = tap - r * p.S;
+                const int btap = p.flip ? (p.R - 1 - r) * p.S + (p.S - 1 - s) : tap;
+                mbar_wait(&empty[stage], phase ^ 1);
+                unsigned char *st = smem + stage * Cfg::STAGE_BYTES;
+                mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                tma_load_4d(st, &tmA, &full[stage], c0, w0 + s - p.pad, h0 + r - p.pad, i0);
+                tma_load_3d(st + Cfg::A_BYTES, &tmB, &full[stage], c0, n0, btap);
+                if (PRECISE) {
+                    tma_load_4d(st + Cfg::A_BYTES + Cfg::B_BYTES, &tmAlo, &full[stage], c0, w0 + s - p.pad, h0 + r - p.pad, i0);
+                    tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tmBlo, &full[stage], c0, n0, btap);
+                }
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = TF32, both K-major, N = BN_TILE, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN_TILE >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const int buf = ch & 1;
+                mbar_wait(&tmem_empty[buf], ((ch >> 1) & 1) ^ 1);            // epilogue has drained this buffer
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * BN_TILE);
+                const int kb_end = min(KB, (ch + 1) * Cfg::CHUNK);
+                for (int kb = ch * Cfg::CHUNK; kb < kb_end; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a = smem_u32(smem + stage * Cfg::STAGE_BYTES), b = a + Cfg::A_BYTES;
+                    const uint32_t alo = b + Cfg::B_BYTES, blo = alo + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                        const uint32_t koff = k * TC_UMMA_K * 4;             // bytes inside the 128-byte swizzled row
+                        umma_tf32(tacc, umma_desc(a + koff), umma_desc(b + koff), idesc, (kb != ch * Cfg::CHUNK) || k != 0);
+                        if (PRECISE) {
+                            umma_tf32(tacc, umma_desc(alo + koff), umma_desc(b + koff), idesc, 1);
+                            umma_tf32(tacc, umma_desc(a + koff), umma_desc(blo + koff), idesc, 1);
+                        }
+                    }
+                    umma_commit(&empty[stage]);                              // frees the smem slot when these MMAs retire
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[buf]);                                // this chunk's accumulator is complete
+            }
+        }
+    } else {
+        // ===================== epilogue: warps 2..5 own TMEM lanes 32 * (warp % 4) ..
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                                       // GEMM row inside the tile = TMEM lane
+        const int bi = row / (p.BH * p.BW), rem = row - bi * p.BH * p.BW;
+        const int bh = rem / p.BW, bw = rem - bh * p.BW;
+        const int img = i0 + bi, ho = h0 + bh, wo = w0 + bw;
+        const bool ok = img < p.N && ho < p.Ho && wo < p.Wo;
+        float acc[BN_TILE];
+#pragma unroll
+        for (int j = 0; j < BN_TILE; ++j) acc[j] = 0.f;
+        const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int buf = ch & 1;
+            mbar_wait(&tmem_full[buf], (ch >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < BN_TILE; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN_TILE + c0), v);   // warp-collective
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);                      // round-to-nearest fp32
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+        }
+        const size_t pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
+        float *yrow = p.y + pix * p.Cout + n0;
+        const float *rrow = nullptr;
+        if (ok) {
+            if (p.res_mode == 1) rrow = p.residual + pix * p.Cout + n0;
+            else if (p.res_mode == 2) rrow = p.residual + (((size_t)img * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * p.Cout + n0;
+#pragma unroll
+            for (int j = 0; j < BN_TILE; j += 4) {
+                float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                const int n = n0 + j;
+                if (p.scale) { const float4 s4 = *reinterpret_cast<const float4 *>(p.scale + n); o.x *= s4.x; o.y *= s4.y; o.z *= s4.z; o.w *= s4.w; }
+                if (p.bias) { const float4 b4 = *reinterpret_cast<const float4 *>(p.bias + n); o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w; }
+                if (rrow) { const float4 r4 = *reinterpret_cast<const float4 *>(rrow + j); o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
+                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                *reinterpret_cast<float4 *>(yrow + j) = o;
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- operand preparation
+// hi = tf32(x) (round to nearest, stored as fp32), lo = x - hi (exact)
+__global__ void __launch_bounds__(256)
+tf32_split_kernel(const float *__restrict__ x, float *__restrict__ hi, float *__restrict__ lo, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+        const float4 v = reinterpret_cast<const float4 *>(x)[i];
+        float4 h, l;
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
+        reinterpret_cast<float4 *>(hi)[i] = h;
+        reinterpret_cast<float4 *>(lo)[i] = l;
+    }
+}
+
+// w [taps][Cin][Cout] -> wt_hi / wt_lo [taps][Cout][Cin] (K-major for the forward GEMM); 32 x 32 tiles through smem
+__global__ void __launch_bounds__(256)
+weight_transpose_split_kernel(const float *__restrict__ w, int Cin, int Cout, float *__restrict__ hi, float *__restrict__ lo) {
+    __shared__ float tile[32][33];
+    const int tap = blockIdx.z, ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int ci = ci0 + r, co = co0 + tx;
+        tile[r][tx] = (ci < Cin && co < Cout) ? w[((size_t)tap * Cin + ci) * Cout + co] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int co = co0 + r, ci = ci0 + tx;
+        if (co < Cout && ci < Cin) {
+            const float v = tile[tx][r];
+            uint32_t u;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+            const float h = __uint_as_float(u);
+            const size_t o = ((size_t)tap * Cout + co) * Cin + ci;
+            hi[o] = h;
+            if (lo) lo[o] = v - h;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap *m, const float *base, int rank, const cuuint64_t *dims, const cuuint32_t *box) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return TTDG_E_LIMIT;
+    cuuint64_t strides[4];
+    cuuint64_t s = sizeof(float);
+    for (int i = 0; i < rank - 1; ++i) { s *= dims[i]; strides[i] = s; }
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : TTDG_E_ARG;
+}
+
+static int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+template <int BN_TILE, bool PRECISE>
+static int launch_tc(const CUtensorMap &a, const CUtensorMap &alo, const CUtensorMap &b, const CUtensorMap &blo, const TcParams &p,
+                     cudaStream_t st) {
+    using Cfg = TcCfg<BN_TILE, PRECISE>;
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_TILE, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid(p.tilesW * p.tilesH * p.tilesI, p.Cout / BN_TILE);
+    count_launches(1);
+    conv_tc_kernel<BN_TILE, PRECISE><<<grid, TC_THREADS, Cfg::SMEM, st>>>(a, alo, b, blo, p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace ttdg
+
+using namespace ttdg;
+
+extern "C" int ttdg_tf32_split(const float *x, float *hi, float *lo, int64_t numel, void *stream) {
+    TTDG_CHECK_ARG(x && hi && lo && numel >= 0 && numel % 4 == 0);
+    if (numel == 0) return 0;
+    int64_t nb = (numel / 4 + 255) / 256;
+    if (nb > 148 * 8) nb = 148 * 8;
+    count_launches(1);
+    tf32_split_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(x, hi, lo, numel / 4);
+    TTDG_LAUNCH_RET();
+}
+
+extern "C" int ttdg_weight_transpose_split(const float *w, int taps, int Cin, int Cout, float *wt_hi, float *wt_lo, void *stream) {
+    TTDG_CHECK_ARG(w && wt_hi && taps >= 1 && Cin >= 1 && Cout >= 1);
+    count_launches(1);
+    weight_transpose_split_kernel<<<dim3(ceil_div(Cout, 32), ceil_div(Cin, 32), taps), 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, wt_hi, wt_lo);
+    TTDG_LAUNCH_RET();
+}
+
+extern "C" int ttdg_conv_tc_supported(int Cin, int Cout, int stride) {
+    return (Cin % 32 == 0 && Cout % 64 == 0 && stride == 1) ? 1 : 0;
+}
+
+// x_hi / x_lo: N x H x W x Cin (x_lo NULL = single-pass TF32 on x_hi as is); wk_hi / wk_lo: weights K-major
+// [taps][n][k] - for the forward conv [R*S][Cout][Cin] (ttdg_weight_transpose_split), for the data gradient (flip = 1)
+// the conv's own [R*S][Cin_fwd][Cout_fwd] array with n = Cin_fwd, k = Cout_fwd.  (Cin, Cout) here are the GEMM's k and n.
+extern "C" int ttdg_conv_tc(const float *x_hi, const float *x_lo, const float *wk_hi, const float *wk_lo, const float *scale,
+                            const float *bias, const float *residual, int res_mode, int relu, int flip, int N, int H, int W,
+                            int Cin, int Cout, int R, int S, int pad, float *y, void *stream) {
+    TTDG_CHECK_ARG(x_hi && wk_hi && y && N >= 0 && H > 0 && W > 0 && R > 0 && S > 0 && pad >= 0);
+    TTDG_CHECK_ARG((x_lo == nullptr) == (wk_lo == nullptr) && (res_mode == 0 || residual));
+    if (!ttdg_conv_tc_supported(Cin, Cout, 1)) return TTDG_E_LIMIT;
+    if (N == 0) return 0;
+    TcParams p = {};
+    p.y = y; p.scale = scale; p.bias = bias; p.residual = residual; p.res_mode = res_mode; p.relu = relu;
+    p.N = N; p.Ho = H + 2 * pad - R + 1; p.Wo = W + 2 * pad - S + 1; p.Cout = Cout;
+    p.R = R; p.S = S; p.pad = pad; p.flip = flip; p.kslabs = Cin / TC_BK;
+    if (p.Ho < 1 || p.Wo < 1) return TTDG_E_ARG;
+    if (res_mode == 2 && ((p.Ho | p.Wo) & 1)) return TTDG_E_ARG;
+    p.BW = pow2_ge(p.Wo) < TC_BM ? pow2_ge(p.Wo) : TC_BM;
+    p.BH = pow2_ge(p.Ho) < TC_BM / p.BW ? pow2_ge(p.Ho) : TC_BM / p.BW;
+    p.BI = TC_BM / (p.BW * p.BH);
+    p.tilesW = ceil_div(p.Wo, p.BW); p.tilesH = ceil_div(p.Ho, p.BH); p.tilesI = ceil_div(N, p.BI);
+    CUtensorMap ma, malo, mb, mblo;
+    const cuuint64_t adims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint32_t abox[4] = {TC_BK, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BI};
+    const cuuint64_t bdims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(R * S)};
+    const int bn_tile = Cout % 128 == 0 ? 128 : 64;
+    const cuuint32_t bbox[3] = {TC_BK, (cuuint32_t)bn_tile, 1};
+    int rc = make_map(&ma, x_hi, 4, adims, abox);
+    if (!rc) rc = make_map(&mb, wk_hi, 3, bdims, bbox);
+    if (!rc && x_lo) rc = make_map(&malo, x_lo, 4, adims, abox);
+    if (!rc && wk_lo) rc = make_map(&mblo, wk_lo, 3, bdims, bbox);
+    if (rc) return rc;
+    if (!x_lo) { malo = ma; mblo = mb; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_lo) return bn_tile == 128 ? launch_tc<128, true>(ma, malo, mb, mblo, p, st) : launch_tc<64, true>(ma, malo, mb, mblo, p, st);
+    return bn_tile == 128 ? launch_tc<128, false>(ma, malo, mb, mblo, p, st) : launch_tc<64, false>(ma, malo, mb, mblo, p, st);
+}

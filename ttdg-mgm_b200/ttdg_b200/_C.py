@@ -49,6 +49,10 @@ SIGNATURES = {
     "ttdg_maxpool3x3s2": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "ttdg_resample2": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "ttdg_preprocess": (c_int, [P, c_int, c_int, c_int, c_float, c_float, c_float, P, P]),
+    "ttdg_conv_tc_supported": (c_int, [c_int, c_int, c_int]),
+    "ttdg_conv_tc": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "ttdg_tf32_split": (c_int, [P, P, P, c_int64, P]),
+    "ttdg_weight_transpose_split": (c_int, [P, c_int, c_int, c_int, P, P, P]),
     "ttdg_rpn_decode": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_float, c_float, P, P, P]),
     "ttdg_box_predict": (c_int, [P, c_int, P, c_int, P, c_int, c_int, c_float, c_float, c_float, P, P, P]),
     "ttdg_nms_scratch_bytes": (c_int64, [c_int]),

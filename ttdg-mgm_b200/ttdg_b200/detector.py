@@ -10,6 +10,7 @@ top-k for ordering); there is no eager or CPU fallback.
 """
 import ctypes
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -29,13 +30,67 @@ def _pad4(c):
     return (c + 3) // 4 * 4
 
 
+# Convolution math: "tf32x3" = tcgen05 tensor cores with the hi/lo operand split (fp32-grade, the parity config),
+# "tf32" = single-pass TF32 (fast config), "simt" = the CUDA-core fp32 kernel everywhere.  Layers the tensor-core
+# kernel does not cover (stride 2, Cin % 32 != 0, Cout % 64 != 0) always use the CUDA-core kernel.
+CONV_MODE = [os.environ.get("TTDG_CONV", "tf32x3")]
+PARAM_EPOCH = [0]              # bumped by FlatSGD.step: invalidates the K-major weight copies below
+
+
+def set_conv_mode(mode):
+    assert mode in ("simt", "tf32x3", "tf32")
+    CONV_MODE[0] = mode
+
+
+def tf32_split(x):
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    check(_C.lib().ttdg_tf32_split(_p(x), _p(hi), _p(lo), x.numel(), _stream()), "tf32_split")
+    return hi, lo
+
+
+def _weights_kmajor(w, transposed, precise, owner=None):
+    """K-major tensor-core operand copies of a [R][S][Cin][Cout] parameter: transposed = forward ([taps][Cout][Cin]),
+    not transposed = data gradient (the array itself).  Cached on the owning layer until the parameter changes: an
+    optimizer step (PARAM_EPOCH; the fused SGD kernel writes through raw pointers), an in-place torch update
+    (``_version``) or a re-allocation (``data_ptr``)."""
+    stamp = (PARAM_EPOCH[0], w._version, w.data_ptr())
+    cache = owner.__dict__.setdefault("_wk_cache", {}) if owner is not None else None
+    if cache is not None:
+        hit = cache.get((transposed, precise))
+        if hit is not None and hit[0] == stamp:
+            return hit[1], hit[2]
+    R, S, Cin, Cout = w.shape
+    if transposed:
+        hi = torch.empty(R * S, Cout, Cin, dtype=torch.float32, device=w.device)
+        lo = torch.empty_like(hi) if precise else None
+        check(_C.lib().ttdg_weight_transpose_split(_p(w), R * S, Cin, Cout, _p(hi), _p(lo), _stream()), "weight_transpose_split")
+    else:
+        hi, lo = tf32_split(w.detach().contiguous())
+        if not precise:
+            lo = None
+    if cache is not None:
+        cache[(transposed, precise)] = (stamp, hi, lo)
+    return hi, lo
+
+
+def _tc_ok(Cin, Cout, stride):
+    return CONV_MODE[0] != "simt" and stride == 1 and Cin % 32 == 0 and Cout % 64 == 0
+
+
 # ---------------------------------------------------------------------------------------------- raw op wrappers
-def conv_forward(x, w, scale, bias, residual, res_mode, relu, R, S, stride, pad, out=None):
+def conv_forward(x, w, scale, bias, residual, res_mode, relu, R, S, stride, pad, out=None, owner=None):
     """x: N x H x W x Cin (NHWC contiguous) -> N x Ho x Wo x Cout."""
     N, H, W, Cin = x.shape
     Cout = w.shape[-1]
     Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
     y = torch.empty(N, Ho, Wo, Cout, dtype=torch.float32, device=x.device) if out is None else out
+    if _tc_ok(Cin, Cout, stride):
+        precise = CONV_MODE[0] == "tf32x3"
+        w_hi, w_lo = _weights_kmajor(w, True, precise, owner)
+        x_hi, x_lo = tf32_split(x) if precise else (x, None)
+        check(_C.lib().ttdg_conv_tc(_p(x_hi), _p(x_lo), _p(w_hi), _p(w_lo), _p(scale), _p(bias), _p(residual), int(res_mode), int(relu),
+                                    0, N, H, W, Cin, Cout, R, S, pad, _p(y), _stream()), "conv_tc")
+        return y
     check(_C.lib().ttdg_conv_fwd(_p(x), _p(w), _p(scale), _p(bias), _p(residual), int(res_mode), int(relu), N, H, W, Cin, Cout, R, S,
                                  stride, pad, _p(y), _stream()), "conv_fwd")
     return y
@@ -45,9 +100,10 @@ class _ConvFn(torch.autograd.Function):
     """y = relu?(conv(x, w) * scale + bias + residual) with the gradients the TTT loss needs."""
 
     @staticmethod
-    def forward(ctx, x, w, bias_param, residual, scale, bias_const, res_mode, relu, R, S, stride, pad):
+    def forward(ctx, x, w, bias_param, residual, scale, bias_const, res_mode, relu, R, S, stride, pad, owner):
         bias = bias_param if bias_param is not None else bias_const
-        y = conv_forward(x, w, scale, bias, residual, res_mode, relu, R, S, stride, pad)
+        y = conv_forward(x, w, scale, bias, residual, res_mode, relu, R, S, stride, pad, owner=owner)
+        ctx.owner = owner
         ctx.save_for_backward(x, w, y if relu else None, scale)
         ctx.meta = (res_mode, relu, R, S, stride, pad, bias_param is not None, residual is not None and residual.requires_grad)
         return y
@@ -86,11 +142,18 @@ class _ConvFn(torch.autograd.Function):
         g_x = g_w = None
         if ctx.needs_input_grad[0]:
             g_x = (torch.zeros if stride == 2 else torch.empty)(N, H, W, Cin, dtype=torch.float32, device=g.device)
-            check(L.ttdg_conv_dgrad(_p(d_conv), _p(w), N, H, W, Cin, Cout, R, S, stride, pad, _p(g_x), s), "conv_dgrad")
+            if _tc_ok(Cout, Cin, stride):                  # GEMM k = Cout, n = Cin; taps mirrored, pad' = R - 1 - pad
+                precise = CONV_MODE[0] == "tf32x3"
+                w_hi, w_lo = _weights_kmajor(w, False, precise, ctx.owner)
+                d_hi, d_lo = tf32_split(d_conv) if precise else (d_conv, None)
+                check(L.ttdg_conv_tc(_p(d_hi), _p(d_lo), _p(w_hi), _p(w_lo), None, None, None, 0, 0, 1, N, g.shape[1], g.shape[2], Cout,
+                                     Cin, R, S, R - 1 - pad, _p(g_x), s), "conv_tc_dgrad")
+            else:
+                check(L.ttdg_conv_dgrad(_p(d_conv), _p(w), N, H, W, Cin, Cout, R, S, stride, pad, _p(g_x), s), "conv_dgrad")
         if ctx.needs_input_grad[1]:
             g_w = torch.zeros_like(w)
             check(L.ttdg_conv_wgrad(_p(x), _p(d_conv), N, H, W, Cin, Cout, R, S, stride, pad, _p(g_w), s), "conv_wgrad")
-        return g_x, g_w, g_bias, g_res, None, None, None, None, None, None, None, None
+        return g_x, g_w, g_bias, g_res, None, None, None, None, None, None, None, None, None
 
 
 class FrozenBN(nn.Module):
@@ -198,10 +261,10 @@ class Conv2d(nn.Module):
         bias_const = self.fold_bias if self.norm is not None else None
         k = 1 if self.kind != "conv" else self.k
         if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
-            return _ConvFn.apply(x, self.weight, self.bias, residual, scale, bias_const, res_mode, relu, k, k, self.stride, self.pad)
+            return _ConvFn.apply(x, self.weight, self.bias, residual, scale, bias_const, res_mode, relu, k, k, self.stride, self.pad, self)
         bias = self.bias if self.bias is not None else bias_const
-        return conv_forward(x, self.weight.detach(), scale, None if bias is None else bias.detach(), residual, res_mode, relu, k, k,
-                            self.stride, self.pad)
+        return conv_forward(x, self.weight, scale, None if bias is None else bias.detach(), residual, res_mode, relu, k, k,
+                            self.stride, self.pad, owner=self)
 
 
 class Bottleneck(nn.Module):

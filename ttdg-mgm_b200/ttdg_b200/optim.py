@@ -50,3 +50,5 @@ class FlatSGD:
                                      ctypes.c_void_p(self.flat_m.data_ptr()), self.numel, self.lr, self.momentum,
                                      self.weight_decay, 1.0 / world_size, int(self.steps == 0), s), "sgd_step")
         self.steps += 1
+        from . import detector
+        detector.PARAM_EPOCH[0] += 1          # K-major tensor-core copies of the weights are stale now
