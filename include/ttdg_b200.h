@@ -264,11 +264,13 @@ int ttdg_rpn_decode(const float *deltas, int ld_deltas, const int64_t *idx, int 
  * class-specific deltas with weights (10, 10, 5, 5), clip; cand_scores = -1 where score <= thresh. */
 int ttdg_box_predict(const float *cls, int ld_cls, const float *reg, int ld_reg, const float *proposals, int R, int K,
                      float img_h, float img_w, float score_thresh, float *cand_boxes, float *cand_scores, void *stream);
-/* Per-category NMS (torchvision batched_nms semantics) over boxes already sorted by descending score.
- * keep [max_keep] receives indices in order, *n_keep their number.  scratch: ttdg_nms_scratch_bytes(n). */
-int64_t ttdg_nms_scratch_bytes(int n);
-int ttdg_nms(const float *boxes_sorted, const int32_t *category, int n, float iou_thresh, int max_keep, int32_t *keep,
-             int32_t *n_keep, void *scratch, void *stream);
+/* Per-category NMS (torchvision batched_nms semantics) for `batch` images at once: boxes_sorted [batch][n][4] already
+ * sorted by descending score, category [batch][n] (boxes of different categories never suppress each other).
+ * keep [batch][max_keep] receives indices in order, n_keep [batch] their number.
+ * scratch: ttdg_nms_scratch_bytes(batch, n). */
+int64_t ttdg_nms_scratch_bytes(int batch, int n);
+int ttdg_nms(const float *boxes_sorted, const int32_t *category, int batch, int n, float iou_thresh, int max_keep,
+             int32_t *keep, int32_t *n_keep, void *scratch, void *stream);
 /* ROIPooler + ROIAlignV2 (aligned, sampling_ratio 0) over p2..p5: rois [n][5] = {image, x0, y0, x1, y1};
  * out [n][pooled][pooled][C].  feat_ptrs_h = HOST array of 4 device pointers, lvl_hw_h = HOST int32[4][2]. */
 int ttdg_roi_align(const float *const *feat_ptrs_h, const int32_t *lvl_hw_h, const float *rois, int n_rois, int C,

@@ -313,5 +313,5 @@ def test_nms_vs_torchvision():
         ref = tvo.batched_nms(boxes, scores, cats, 0.5)
         order = torch.argsort(scores, descending=True, stable=True)
         keep, nk = det.nms_sorted(boxes[order].cuda().contiguous(), cats[order].int().cuda().contiguous(), 0.5, n)
-        got = order[keep[:int(nk)].long().cpu()]
+        got = order[keep[:int(nk[0])].long().cpu()]
         assert torch.equal(got, ref)

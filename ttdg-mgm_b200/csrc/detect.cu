@@ -84,6 +84,7 @@ nms_mask_kernel(const float *__restrict__ boxes, const int32_t *__restrict__ cat
                 int words) {
     const int rb = blockIdx.y, cb = blockIdx.x;
     if (cb < rb) return;
+    boxes += (size_t)blockIdx.z * n * 4; cat += (size_t)blockIdx.z * n; mask += (size_t)blockIdx.z * n * words;   // image
     __shared__ float sb[64][4];
     __shared__ int sc[64];
     const int cj = cb * 64 + threadIdx.x;
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(256)
 nms_sweep_kernel(const unsigned long long *__restrict__ mask, int n, int words, int max_keep, int32_t *__restrict__ keep,
                  int32_t *__restrict__ n_keep) {
     extern __shared__ unsigned long long removed[];
+    mask += (size_t)blockIdx.x * n * words; keep += (size_t)blockIdx.x * max_keep; n_keep += blockIdx.x;              // image
     __shared__ unsigned long long diag[64];
     __shared__ unsigned long long kept_bits;
     __shared__ int cnt;
@@ -279,22 +281,22 @@ extern "C" int ttdg_box_predict(const float *cls, int ld_cls, const float *reg, 
     TTDG_LAUNCH_RET();
 }
 
-extern "C" int64_t ttdg_nms_scratch_bytes(int n) { return (int64_t)n * ((n + 63) / 64) * 8; }
+extern "C" int64_t ttdg_nms_scratch_bytes(int batch, int n) { return (int64_t)batch * n * ((n + 63) / 64) * 8; }
 
-extern "C" int ttdg_nms(const float *boxes_sorted, const int32_t *category, int n, float iou_thresh, int max_keep, int32_t *keep,
-                        int32_t *n_keep, void *scratch, void *stream) {
-    TTDG_CHECK_ARG(boxes_sorted && category && keep && n_keep && scratch && n >= 0 && max_keep >= 1);
-    if (n == 0) return (int)cudaMemsetAsync(n_keep, 0, sizeof(int32_t), (cudaStream_t)stream);
+extern "C" int ttdg_nms(const float *boxes_sorted, const int32_t *category, int batch, int n, float iou_thresh, int max_keep,
+                        int32_t *keep, int32_t *n_keep, void *scratch, void *stream) {
+    TTDG_CHECK_ARG(boxes_sorted && category && keep && n_keep && scratch && n >= 0 && max_keep >= 1 && batch >= 1 && batch <= 65535);
+    if (n == 0) return (int)cudaMemsetAsync(n_keep, 0, sizeof(int32_t) * batch, (cudaStream_t)stream);
     const int words = (n + 63) / 64;
     if ((size_t)words * 8 > 200 * 1024) return TTDG_E_LIMIT;
     unsigned long long *mask = reinterpret_cast<unsigned long long *>(scratch);
-    cudaError_t e = cudaMemsetAsync(mask, 0, (size_t)n * words * 8, (cudaStream_t)stream);
+    cudaError_t e = cudaMemsetAsync(mask, 0, (size_t)batch * n * words * 8, (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
     count_launches(2);
-    nms_mask_kernel<<<dim3(words, words), 64, 0, (cudaStream_t)stream>>>(boxes_sorted, category, n, iou_thresh, mask, words);
+    nms_mask_kernel<<<dim3(words, words, batch), 64, 0, (cudaStream_t)stream>>>(boxes_sorted, category, n, iou_thresh, mask, words);
     e = cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, words * 8);
     if (e != cudaSuccess) return (int)e;
-    nms_sweep_kernel<<<1, 256, words * 8, (cudaStream_t)stream>>>(mask, n, words, max_keep, keep, n_keep);
+    nms_sweep_kernel<<<batch, 256, words * 8, (cudaStream_t)stream>>>(mask, n, words, max_keep, keep, n_keep);
     TTDG_LAUNCH_RET();
 }
 

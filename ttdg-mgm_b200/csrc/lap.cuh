@@ -15,21 +15,40 @@
 namespace ttdg {
 
 constexpr int LAP_MAX_DIM = 128;     // rows, cols <= 128 (graphs have <= ~95 nodes, universe is 32)
+constexpr int LAP_SLOTS = LAP_MAX_DIM / 32;
 
-struct LapWork {                     // per-warp shared-memory workspace
+struct LapWork {                     // per-warp shared-memory workspace (state that crosses lanes / augmentations)
     double u[LAP_MAX_DIM];
     double v[LAP_MAX_DIM];
-    double shortest[LAP_MAX_DIM];
+    double shortest[LAP_MAX_DIM];    // final shortest[] of the columns scanned in the current augmentation
     int path[LAP_MAX_DIM];
     int col4row[LAP_MAX_DIM];
     int row4col[LAP_MAX_DIM];
-    int remaining[LAP_MAX_DIM];
-    unsigned char SR[LAP_MAX_DIM];
-    unsigned char SC[LAP_MAX_DIM];
+    int visited[LAP_MAX_DIM];        // rows put into SR in the current augmentation, in order
 };
+
+// order-preserving map double -> uint64 (no NaNs here)
+__device__ __forceinline__ unsigned long long lap_ord(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double lap_unord(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double((long long)b);
+}
 
 // Cost: functor double operator()(int i, int j) for the WORKING matrix (nr <= nc).
 // On return w.col4row[i] (i < nr) holds the column assigned to row i.  Must be called by a full warp.
+//
+// Per-column state (shortest, v, path, position in SciPy's `remaining` list, row4col) lives in REGISTERS of the lane
+// that owns the column (j = lane + 32 t); one inner iteration is a few FP64 ops per owned column plus three
+// redux.sync reductions (value high word, value low word, tie key) instead of shuffle butterflies over shared memory.
+// SciPy's selection rule "strictly lower, or equal and unassigned" over the scan order it = 0 .. num_remaining-1 picks,
+// among the minima, the LAST unassigned position if any, else the FIRST position; with the tie key
+//     unassigned: 256 + it,   assigned: 255 - it      (maximised)
+// the winner of (value ascending, key descending) is exactly that element.  `remaining` is filled in reverse
+// (position it holds column nc-1-it) and compacted by moving the last element into the freed position - tracked here
+// as a per-column position register.
 template <class Cost>
 __device__ void lap_solve_warp(int nr, int nc, Cost cost, LapWork &w) {
     const int lane = threadIdx.x & 31;
@@ -37,57 +56,69 @@ __device__ void lap_solve_warp(int nr, int nc, Cost cost, LapWork &w) {
     for (int k = lane; k < nc; k += 32) { w.v[k] = 0.0; w.row4col[k] = -1; }
     __syncwarp();
     for (int cur = 0; cur < nr; ++cur) {
-        for (int k = lane; k < nc; k += 32) {
-            w.remaining[k] = nc - k - 1;
-            w.shortest[k] = INFINITY;
-            w.path[k] = -1;
-            w.SC[k] = 0;
-        }
-        for (int k = lane; k < nr; k += 32) w.SR[k] = 0;
-        __syncwarp();
-        double minVal = 0.0;
-        int num_remaining = nc;
-        int sink = -1;
-        int i = cur;
-        while (sink == -1) {
-            if (lane == 0) w.SR[i] = 1;
-            const double ui = w.u[i];
-            double m = INFINITY;     // lane-local minimum of shortest[]
-            int first = 0x7fffffff;  // first position holding m
-            int lastfree = -1;       // last unassigned position holding m
-            for (int it = lane; it < num_remaining; it += 32) {
-                const int j = w.remaining[it];
-                const double r = ((minVal + cost(i, j)) - ui) - w.v[j];
-                double s = w.shortest[j];
-                if (r < s) { w.path[j] = i; w.shortest[j] = r; s = r; }
-                const bool fr = (w.row4col[j] == -1);
-                if (s < m) { m = s; first = it; lastfree = fr ? it : -1; }
-                else if (s == m && fr) { lastfree = it; }
-            }
-            double gm = m;
+        double sh[LAP_SLOTS], vj[LAP_SLOTS];
+        int pos[LAP_SLOTS], r4c[LAP_SLOTS], pth[LAP_SLOTS];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) gm = fmin(gm, __shfl_xor_sync(TTDG_FULL, gm, o));
-            const bool mine = (m == gm) && (first != 0x7fffffff);
-            const int gfirst = warp_min_i(mine ? first : 0x7fffffff);
-            const int glast = warp_max_i(mine ? lastfree : -1);
-            const int index = (glast != -1) ? glast : gfirst;
-            minVal = gm;
-            __syncwarp();
-            const int j = w.remaining[index];
-            const int r4c = w.row4col[j];
-            if (r4c == -1) sink = j; else i = r4c;
-            --num_remaining;
-            __syncwarp();
-            if (lane == 0) { w.SC[j] = 1; w.remaining[index] = w.remaining[num_remaining]; }
-            __syncwarp();
+        for (int t = 0; t < LAP_SLOTS; ++t) {
+            const int j = lane + 32 * t;
+            sh[t] = INFINITY; pth[t] = -1;
+            if (j < nc) { vj[t] = w.v[j]; pos[t] = nc - 1 - j; r4c[t] = w.row4col[j]; }
+            else { vj[t] = 0.0; pos[t] = -1; r4c[t] = 0; }
         }
+        double minVal = 0.0;
+        int num_remaining = nc, sink = -1, i = cur, nvis = 0;
+        while (sink == -1) {
+            if (lane == 0) w.visited[nvis] = i;
+            ++nvis;
+            const double ui = w.u[i];
+            unsigned long long bk = 0xFFFFFFFFFFFFFFFFull;      // lane-local best (ordered value)
+            unsigned bkey = 0;                                  // its tie key
+            int bslot = 0;
+#pragma unroll
+            for (int t = 0; t < LAP_SLOTS; ++t) {
+                if (pos[t] >= 0) {
+                    const double r = ((minVal + cost(i, lane + 32 * t)) - ui) - vj[t];
+                    if (r < sh[t]) { sh[t] = r; pth[t] = i; }
+                    const unsigned long long k = lap_ord(sh[t]);
+                    const unsigned key = (r4c[t] == -1) ? 256u + (unsigned)pos[t] : 255u - (unsigned)pos[t];
+                    if (k < bk || (k == bk && key > bkey)) { bk = k; bkey = key; bslot = t; }
+                }
+            }
+            const unsigned hi = (unsigned)(bk >> 32), lo = (unsigned)bk;
+            const unsigned mhi = __reduce_min_sync(TTDG_FULL, hi);
+            const unsigned mlo = __reduce_min_sync(TTDG_FULL, hi == mhi ? lo : 0xFFFFFFFFu);
+            const bool cand = (hi == mhi) && (lo == mlo) && (bk != 0xFFFFFFFFFFFFFFFFull);
+            const unsigned mkey = __reduce_max_sync(TTDG_FULL, cand ? bkey : 0u);
+            const bool win = cand && (bkey == mkey);
+            const int src = __ffs(__ballot_sync(TTDG_FULL, win)) - 1;
+            minVal = lap_unord(((unsigned long long)mhi << 32) | mlo);
+            const int psel = mkey >= 256u ? (int)(mkey - 256u) : (int)(255u - mkey);
+            int jsel = lane + 32 * bslot, rsel = 0;
+#pragma unroll
+            for (int t = 0; t < LAP_SLOTS; ++t) if (t == bslot) rsel = r4c[t];
+            jsel = __shfl_sync(TTDG_FULL, jsel, src);
+            rsel = __shfl_sync(TTDG_FULL, rsel, src);
+            if (rsel == -1) sink = jsel; else i = rsel;
+            const int last = num_remaining - 1;
+#pragma unroll
+            for (int t = 0; t < LAP_SLOTS; ++t) {
+                const int j = lane + 32 * t;
+                if (j == jsel) {                                  // scanned: SC[j] = true, leaves `remaining`
+                    w.shortest[j] = sh[t]; w.path[j] = pth[t]; pos[t] = -2;
+                } else if (pos[t] == last) pos[t] = psel;         // remaining[index] = remaining[--num_remaining]
+            }
+            num_remaining = last;
+        }
+        __syncwarp();
         // dual update
-        for (int r = lane; r < nr; r += 32) {
+        for (int k = lane; k < nvis; k += 32) {
+            const int r = w.visited[k];
             if (r == cur) w.u[r] += minVal;
-            else if (w.SR[r]) w.u[r] += minVal - w.shortest[w.col4row[r]];
+            else w.u[r] += minVal - w.shortest[w.col4row[r]];
         }
-        for (int j = lane; j < nc; j += 32)
-            if (w.SC[j]) w.v[j] -= minVal - w.shortest[j];
+#pragma unroll
+        for (int t = 0; t < LAP_SLOTS; ++t)
+            if (pos[t] == -2) w.v[lane + 32 * t] = vj[t] - (minVal - sh[t]);
         __syncwarp();
         // augment along the path (sequential, short)
         if (lane == 0) {

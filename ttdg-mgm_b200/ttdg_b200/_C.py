@@ -55,8 +55,8 @@ SIGNATURES = {
     "ttdg_weight_transpose_split": (c_int, [P, c_int, c_int, c_int, P, P, P]),
     "ttdg_rpn_decode": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_float, c_float, P, P, P]),
     "ttdg_box_predict": (c_int, [P, c_int, P, c_int, P, c_int, c_int, c_float, c_float, c_float, P, P, P]),
-    "ttdg_nms_scratch_bytes": (c_int64, [c_int]),
-    "ttdg_nms": (c_int, [P, P, c_int, c_float, c_int, P, P, P, P]),
+    "ttdg_nms_scratch_bytes": (c_int64, [c_int, c_int]),
+    "ttdg_nms": (c_int, [P, P, c_int, c_int, c_float, c_int, P, P, P, P]),
     "ttdg_roi_align": (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
     "ttdg_pixel_shuffle2": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "ttdg_mask_paste": (c_int, [P, c_int, c_int, P, P, c_int, c_int, c_int, c_float, P, P]),

@@ -373,15 +373,27 @@ def cell_anchors():
     return torch.tensor(a, dtype=torch.float32)
 
 
+_NMS_SCRATCH = {}
+
+
 def nms_sorted(boxes, cats, thresh, max_keep):
-    """Per-category NMS over boxes sorted by descending score: returns (keep int32[max_keep], n_keep int32[1])."""
-    n = boxes.shape[0]
+    """Per-category NMS over boxes sorted by descending score, for a batch of images in one launch pair.
+    boxes: B x n x 4 (or n x 4), cats: B x n int32.  Returns (keep int32 [B][max_keep], n_keep int32 [B])."""
+    single = boxes.dim() == 2
+    if single:
+        boxes, cats = boxes.unsqueeze(0), cats.unsqueeze(0)
+    boxes, cats = boxes.contiguous(), cats.contiguous()
+    B, n = boxes.shape[0], boxes.shape[1]
     L = _C.lib()
-    keep = torch.zeros(max_keep, dtype=torch.int32, device=boxes.device)
-    n_keep = torch.zeros(1, dtype=torch.int32, device=boxes.device)
-    scratch = torch.empty(max(L.ttdg_nms_scratch_bytes(n), 8), dtype=torch.uint8, device=boxes.device)
-    check(L.ttdg_nms(_p(boxes), _p(cats), n, float(thresh), int(max_keep), _p(keep), _p(n_keep), _p(scratch), _stream()), "nms")
-    return keep, n_keep
+    keep = torch.zeros(B, max_keep, dtype=torch.int32, device=boxes.device)
+    n_keep = torch.zeros(B, dtype=torch.int32, device=boxes.device)
+    need = max(L.ttdg_nms_scratch_bytes(B, n), 8)
+    scratch = _NMS_SCRATCH.get(boxes.device)
+    if scratch is None or scratch.numel() < need:       # persistent, grow-only: an 80 MB block that comes and goes makes
+        scratch = torch.empty(need, dtype=torch.uint8, device=boxes.device)     # the caching allocator cudaMalloc/cudaFree every step
+        _NMS_SCRATCH[boxes.device] = scratch
+    check(L.ttdg_nms(_p(boxes), _p(cats), B, n, float(thresh), int(max_keep), _p(keep), _p(n_keep), _p(scratch), _stream()), "nms")
+    return (keep[0], n_keep) if single else (keep, n_keep)
 
 
 class RPN(nn.Module):
@@ -424,22 +436,18 @@ class RPN(nn.Module):
         key = torch.where(valid & torch.isfinite(scores), scores, torch.full_like(scores, -float("inf")))
         order = torch.argsort(key, dim=1, descending=True, stable=True)
         n_valid = (key > -float("inf")).sum(1).to(torch.int32)
-        res, meta = [], []
         Kt = boxes.shape[1]
-        neg = -1 - torch.arange(Kt, dtype=torch.int32, device=dev)
-        for n in range(N):
-            b = boxes[n][order[n]].contiguous()
-            s = scores[n][order[n]]
-            c = torch.where(torch.arange(Kt, device=dev) < n_valid[n], lvl[order[n]], neg).contiguous()
-            keep, n_keep = nms_sorted(b, c, self.nms_thresh, self.post_topk)
-            res.append((b, s, keep))
-            meta.append(n_keep)
-        counts = torch.stack([torch.minimum(m[0], ((r[2][:self.post_topk] < nv) & (torch.arange(self.post_topk, device=dev) < m[0])).sum().to(torch.int32))
-                              for m, r, nv in zip(meta, res, n_valid)]).cpu().tolist()      # one host sync per batch
+        ar = torch.arange(Kt, device=dev)
+        b_sorted = torch.gather(boxes, 1, order.unsqueeze(-1).expand(-1, -1, 4))
+        s_sorted = torch.gather(scores, 1, order)
+        cats = torch.where(ar.unsqueeze(0) < n_valid.unsqueeze(1), lvl[order], (-1 - ar).to(torch.int32).unsqueeze(0)).to(torch.int32)
+        keep, n_keep = nms_sorted(b_sorted, cats, self.nms_thresh, self.post_topk)          # all images, one launch pair
+        ak = torch.arange(self.post_topk, device=dev).unsqueeze(0)
+        counts = ((keep < n_valid.unsqueeze(1)) & (ak < n_keep.unsqueeze(1))).sum(1).cpu().tolist()      # one host sync per batch
         out = []
-        for (b, s, keep), cnt in zip(res, counts):
-            kk = keep[:cnt].long()
-            out.append((b[kk], s[kk]))
+        for n in range(N):
+            kk = keep[n, :counts[n]].long()
+            out.append((b_sorted[n][kk], s_sorted[n][kk]))
         return out
 
 
@@ -515,25 +523,30 @@ class ROIHeads(nn.Module):
         cand_s = torch.empty(R * K, dtype=torch.float32, device=dev)
         check(L.ttdg_box_predict(_p(cls), cls.shape[1], _p(reg), reg.shape[1], _p(pb), R, K, float(image_size[0]), float(image_size[1]),
                                  self.score_thresh, _p(cand_b), _p(cand_s), _stream()), "box_predict")
-        res, metas, o = [], [], 0
-        cls_id = torch.arange(K, dtype=torch.int32, device=dev)
-        for p in props:
+        # pad every image to the same candidate count (invalid candidates: score -1, unique negative category)
+        B = len(props)
+        nmax = max(len(p) for p in props) * K
+        cs = torch.full((B, nmax), -1.0, dtype=torch.float32, device=dev)
+        cb = torch.zeros(B, nmax, 4, dtype=torch.float32, device=dev)
+        o = 0
+        for i, p in enumerate(props):
             n = len(p) * K
-            s, b = cand_s[o:o + n], cand_b[o:o + n]
+            cs[i, :n], cb[i, :n] = cand_s[o:o + n], cand_b[o:o + n]
             o += n
-            order = torch.argsort(s, descending=True, stable=True)
-            ss, bb = s[order], b[order].contiguous()
-            cc = cls_id.repeat(len(p))[order]
-            n_valid = (ss > 0).sum().to(torch.int32)
-            cats = torch.where(torch.arange(n, device=dev) < n_valid, cc, -1 - torch.arange(n, dtype=torch.int32, device=dev)).contiguous()
-            keep, n_keep = nms_sorted(bb, cats, self.nms_thresh, self.topk)
-            res.append((bb, ss, cc, keep))
-            metas.append(torch.minimum(n_keep[0], ((keep < n_valid) & (torch.arange(self.topk, device=dev) < n_keep[0])).sum().to(torch.int32)))
-        counts = torch.stack(metas).cpu().tolist()                       # one host sync per batch
+        order = torch.argsort(cs, dim=1, descending=True, stable=True)
+        ss = torch.gather(cs, 1, order)
+        bb = torch.gather(cb, 1, order.unsqueeze(-1).expand(-1, -1, 4))
+        cc = (order % K).to(torch.int32)                                 # candidate t = roi * K + class
+        n_valid = (ss > 0).sum(1).to(torch.int32)
+        ar = torch.arange(nmax, device=dev)
+        cats = torch.where(ar.unsqueeze(0) < n_valid.unsqueeze(1), cc, (-1 - ar).to(torch.int32).unsqueeze(0)).to(torch.int32)
+        keep, n_keep = nms_sorted(bb, cats, self.nms_thresh, self.topk)
+        ak = torch.arange(self.topk, device=dev).unsqueeze(0)
+        counts = ((keep < n_valid.unsqueeze(1)) & (ak < n_keep.unsqueeze(1))).sum(1).cpu().tolist()      # one host sync per batch
         out = []
-        for (bb, ss, cc, keep), cnt in zip(res, counts):
-            kk = keep[:cnt].long()
-            out.append((bb[kk], ss[kk], cc[kk].long()))
+        for i in range(B):
+            kk = keep[i, :counts[i]].long()
+            out.append((bb[i][kk], ss[i][kk], cc[i][kk].long()))
         return out
 
     @torch.no_grad()
