@@ -174,7 +174,9 @@ def main():
                 "test-time-adaptation step (Mask R-CNN R50-FPN fwd in train mode, node sampler, MGM3_unsup with Sinkhorn 20 "
                 "iters + GA-GM, backward through FPN+res3-5, SGD) plus one eval forward with masks pasted at 512x512")
     config = {"workload": workload, "images_per_gpu": IMAGES_PER_GPU, "image_size": IMG, "num_classes": 2, "universe": 32,
-              "sinkhorn_iters": 20, "conv_math": "fp32 CUDA-core FMA (parity config; tcgen05 path is next)",
+              "sinkhorn_iters": 20,
+              "conv_math": {"tf32x3": "tcgen05 kind::tf32 with hi/lo operand split + chunked TMEM accumulation (fp32-grade, 2e-6 per layer)",
+                            "tf32": "tcgen05 single-pass TF32", "simt": "fp32 CUDA-core FMA"}[os.environ.get("TTDG_CONV", "tf32x3")],
               "weights": "random init, FrozenBN statistics calibrated on synthetic images (no checkpoint offline)",
               "parallelism": f"image-sharded x{world}, NCCL all-reduce of the gradient bucket",
               "l2": "flushed between timed steps (256 MiB memset outside the per-step event pairs)"}
@@ -201,6 +203,8 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"                 # keep stdout to the single JSON line
         torch.distributed.init_process_group("nccl", device_id=device)
     from ttdg_b200 import _C
     lib = _C.lib()
@@ -273,7 +277,7 @@ def main():
     if rank == 0:
         roof = sinkhorn_roofline(device)
         n_cpu = 2
-        cpu_val, cpu_dt = cpu_baseline([d["image"] for d in make_inputs(0)[:n_cpu]], 1)
+        cpu_val, cpu_dt = (cpu_baseline([d["image"] for d in make_inputs(0)[:n_cpu]], 1) if world == 1 else (None, None))
         aux = m.multi_matching_unsup.last_aux
         info = aux["info"].cpu().tolist()
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -285,9 +289,9 @@ def main():
                 "gpu_launches": int(launches), "skipped_steps": stats["skipped"],
                 "gagm": {"iterations": info[0], "lap_calls": info[3], "graphs": len(aux["sizes"]), "nodes": int(sum(aux["sizes"]))},
                 "clocks": clk, "roofline": roof,
-                "cpu_baseline": {"value": round(cpu_val, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                 "sample": f"1 step of {n_cpu} of the 8 images (TTT step + eval pass) with the oracle port on torch "
-                                           f"CPU, {cpu_dt:.1f} s"}}
+                "cpu_baseline": ({"value": round(cpu_val, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                  "sample": f"1 step of {n_cpu} of the 8 images (TTT step + eval pass) with the oracle port on torch "
+                                            f"CPU, {cpu_dt:.1f} s"} if world == 1 else None)}
         print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()

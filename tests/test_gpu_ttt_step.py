@@ -91,3 +91,26 @@ def test_ttt_single_image_is_skipped():
     m.train()
     loss, _, _, _ = m([{"image": synth.fundus_like_image(1, 128)["image"]}], branch="TTT")
     assert loss is None
+
+
+def test_baseline_trainer_test_end_to_end():
+    """BaselineTrainer.test (trainer.py:430-529) with the real model: adapt on every batch, then Dice / E / S evaluation
+    with the adapted weights; DICE_THRES 0 because a random-init detector has no confident detections."""
+    from adapteacher.config import add_ateacher_config
+    from adapteacher.engine.trainer import BaselineTrainer
+    m = build()
+    opt = FlatSGD(m.adapted_parameters(), lr=0.005, momentum=0.9, weight_decay=1e-4)
+    size = 128
+    ims = [synth.fundus_like_image(400 + i, size) for i in range(5)]
+    dicts = [{"image_id": i, "annotations": [{"category_id": int(c), "mask": mk.numpy()} for c, mk in zip(im["gt_classes"], im["gt_masks"])]}
+             for i, im in enumerate(ims)]
+    inputs = [{"image": im["image"], "height": size, "width": size, "image_id": i} for i, im in enumerate(ims)]
+    loader = [inputs[:3], inputs[3:]]                       # TEST.BATCH 3, drop_last False
+    cfg = add_ateacher_config()
+    cfg.DATASETS.TEST = ("REFUGE_test",)
+    cfg.TEST.DICE_THRES = 0.0
+    w0 = opt.flat_p.clone()
+    res = BaselineTrainer.test(cfg, m, opt, data_loaders={"REFUGE_test": loader}, dataset_dicts={"REFUGE_test": dicts})
+    assert opt.steps == 2 and not torch.equal(w0, opt.flat_p)
+    for k in ("Dice Coefficient", "Enhanced Alignment Metric", "Structural Similarity Metric"):
+        assert 0.0 <= res["REFUGE_test"][k] <= 100.0 and np.isfinite(res["REFUGE_mean"][k])

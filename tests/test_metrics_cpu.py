@@ -1,0 +1,63 @@
+"""DiceEvaluator metric definitions against golden values computed by the reference's own functions
+(oracle/gen_metric_golden.py), and the TTT driver's control flow on a stub model (CPU only)."""
+import numpy as np
+import torch
+
+from adapteacher.evaluation.dice_metric import DiceEvaluator, Structure_measure, dice, enhanced_align
+from adapteacher.engine.trainer import BaselineTrainer
+from adapteacher.config import add_ateacher_config
+from oracle.gen_metric_golden import cases
+from ttdg_b200.structures import Boxes, Instances
+
+
+def test_metric_definitions_match_reference(golden_dir):
+    g = np.load(f"{golden_dir}/metrics.npz")
+    for i, (pred, gt) in enumerate(cases()):
+        np.testing.assert_allclose(dice(pred, gt), float(g[f"dice_{i}"]), rtol=1e-12)
+        np.testing.assert_allclose(enhanced_align(pred, gt), float(g[f"ea_{i}"]), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(Structure_measure().get_score(pred, gt), float(g[f"sm_{i}"]), rtol=1e-6, atol=1e-9)
+
+
+class _StubModel(torch.nn.Module):
+    """Behaves like the meta-arch at its boundary: branch='TTT' -> (loss | None, [], [], feats); eval -> instances."""
+
+    def __init__(self, gts):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.ones(1))
+        self.gts = gts
+        self.ttt_calls = 0
+
+    def forward(self, inputs, branch="supervised"):
+        if self.training:
+            self.ttt_calls += 1
+            if len(inputs) < 2:
+                return None, [], [], []                     # single graph: skipped (trainer.py:477-478)
+            return (self.w * 2).sum(), [], [], []
+        out = []
+        for d in inputs:
+            m = torch.from_numpy(self.gts[d["image_id"]])[None]
+            out.append({"instances": Instances(m.shape[-2:], pred_boxes=Boxes(torch.zeros(1, 4)), scores=torch.tensor([0.95]),
+                                               pred_classes=torch.tensor([0]), pred_masks=m)})
+        return out
+
+
+def test_baseline_trainer_test_loop():
+    pairs = cases()[:4]
+    gts = {i: gt for i, (_, gt) in enumerate(pairs)}
+    dicts = [{"image_id": i, "annotations": [{"category_id": 0, "mask": gt}]} for i, gt in gts.items()]
+    batches = [[{"image_id": 0}, {"image_id": 1}], [{"image_id": 2}], [{"image_id": 3}]]
+    cfg = add_ateacher_config()
+    cfg.DATASETS.TEST = ("Fundus_a", "Fundus_b")
+    model = _StubModel(gts)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    res = BaselineTrainer.test(cfg, model, opt, data_loaders={"Fundus_a": batches, "Fundus_b": batches},
+                               dataset_dicts={"Fundus_a": dicts, "Fundus_b": dicts})
+    assert model.ttt_calls == 6                              # every batch of both datasets is visited in pass 1
+    np.testing.assert_allclose(float(model.w), 1.0 - 2 * 0.1 * 2)        # two non-skipped steps; weights carry over datasets
+    for name in ("Fundus_a", "Fundus_b", "Fundus_mean"):
+        np.testing.assert_allclose(res[name]["Dice Coefficient"], 100.0, rtol=1e-6)    # predictions == ground truth
+    cfg.TEST.MIN_BATCH_NUM = 1
+    model.ttt_calls = 0
+    BaselineTrainer.test(cfg, model, opt, data_loaders={"Fundus_a": batches, "Fundus_b": batches},
+                         dataset_dicts={"Fundus_a": dicts, "Fundus_b": dicts})
+    assert model.ttt_calls == 2
