@@ -250,6 +250,14 @@ int ttdg_conv_tc_supported(int Cin, int Cout, int stride);
 int ttdg_conv_tc(const float *x_hi, const float *x_lo, const float *wk_hi, const float *wk_lo, const float *scale,
                  const float *bias, const float *residual, int res_mode, int relu, int flip, int N, int H, int W,
                  int Cin, int Cout, int R, int S, int pad, float *y, void *stream);
+/* Weight gradient on tensor cores (stride-1 convs, Cin % 128 == 0, Cout % 64 == 0): dw [R][S][Cin][Cout] +=
+ * sum_pixels X[pixel + tap][ci] dY[pixel][co].  Both operands are MN-major (pixels = GEMM k = slow memory dimension):
+ * TMA boxes of {32 channels, 32 pixels} with the 128-byte / 32-byte-atom swizzle, the only MN-major layout tcgen05
+ * takes for 32-bit operands.  Accumulated into dw with fp32 atomics over the pixel splits.  *_lo NULL = single-pass
+ * TF32.  Replaces the weight half of torch autograd's conv backward behind loss.backward() (engine/trainer.py:481). */
+int ttdg_wgrad_tc_supported(int Cin, int Cout, int stride);
+int ttdg_wgrad_tc(const float *x_hi, const float *x_lo, const float *dy_hi, const float *dy_lo, int N, int H, int W, int Cin,
+                  int Cout, int R, int S, int pad, float *dw, void *stream);
 int ttdg_tf32_split(const float *x, float *hi, float *lo, int64_t numel, void *stream);
 /* w [taps][Cin][Cout] -> wt_hi, wt_lo (may be NULL) [taps][Cout][Cin] */
 int ttdg_weight_transpose_split(const float *w, int taps, int Cin, int Cout, float *wt_hi, float *wt_lo, void *stream);

@@ -77,7 +77,59 @@ def test_conv_tc_dgrad(mode, rtol, cin, cout, k, pad, H, W, N):
     err = float((nchw(xc.grad.cpu()) - x.grad).abs().max() / x.grad.abs().max())
     assert err < rtol, err
     gw = layer.weight.grad[:, :, :cin, :cout].permute(3, 2, 0, 1).cpu()
-    assert float((gw - w.grad).abs().max() / w.grad.abs().max()) < 3e-5          # wgrad stays on the fp32 CUDA-core kernel
+    assert float((gw - w.grad).abs().max() / w.grad.abs().max()) < rtol           # weight gradient: tensor cores too (below)
+
+
+WGRAD_CASES = [
+    # cin, cout, k, pad, H, W, N
+    (128, 64, 1, 0, 8, 8, 2),              # BN_TILE 64, one 32-pixel patch = 4 x 8 pixels
+    (128, 128, 3, 1, 10, 12, 2),           # partial patches in both directions + padding taps
+    (256, 256, 3, 1, 14, 14, 5),           # mask-head shape
+    (256, 256, 3, 1, 64, 64, 2),           # many pixel blocks: split over CTAs, fp32 atomics
+    (512, 512, 3, 1, 4, 4, 3),             # res5 shape: patch spans images
+    (256, 1024, 1, 0, 16, 16, 1),
+    (1024, 256, 1, 0, 16, 16, 2),
+    (12544, 1024, 1, 0, 1, 1, 70),         # box-head fc1: pixels = rows
+    (1024, 1024, 1, 0, 1, 1, 33),
+]
+
+
+@pytest.mark.parametrize("mode,rtol", [("tf32x3", 2e-5), ("tf32", 5e-3)])
+@pytest.mark.parametrize("cin,cout,k,pad,H,W,N", WGRAD_CASES)
+def test_wgrad_tc(mode, rtol, cin, cout, k, pad, H, W, N):
+    """Weight gradient with MN-major tcgen05 operands (pixels = GEMM k) against torch autograd and against the
+    CUDA-core fp32 kernel; the gradient is accumulated INTO dw (checked with a non-zero start)."""
+    L = det._C.lib()
+    assert L.ttdg_wgrad_tc_supported(cin, cout, 1) == 1 and L.ttdg_wgrad_tc_supported(cin, cout, 2) == 0
+    g = torch.Generator().manual_seed(cin * 3 + cout + k + H)
+    x = torch.randn(N, cin, H, W, generator=g)
+    w = torch.zeros(cout, cin, k, k, requires_grad=True)
+    dy = torch.randn(N, cout, H + 2 * pad - k + 1, W + 2 * pad - k + 1, generator=g)
+    F.conv2d(x, w, None, 1, pad).backward(dy)
+    ref = w.grad.permute(2, 3, 1, 0).contiguous()                                # [R][S][Cin][Cout]
+    xc, dc = nhwc(x).cuda(), nhwc(dy).cuda()
+    start = torch.randn(k, k, cin, cout, generator=g)
+    dw = start.cuda()
+    if mode == "tf32x3":
+        (xh, xl), (dh, dl) = det.tf32_split(xc), det.tf32_split(dc)
+    else:
+        xh, xl, dh, dl = xc, None, dc, None
+    p = lambda t: None if t is None else t.data_ptr()
+    rc = L.ttdg_wgrad_tc(p(xh), p(xl), p(dh), p(dl), N, H, W, cin, cout, k, k, pad, p(dw), None)
+    torch.cuda.synchronize()
+    assert rc == 0
+    got = dw.cpu() - start
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) / scale < rtol * max(1.0, (N * H * W / 1024.0) ** 0.5)
+    dw2 = torch.zeros(k, k, cin, cout, device="cuda")
+    assert L.ttdg_conv_wgrad(p(xc), p(dc), N, H, W, cin, cout, k, k, 1, pad, p(dw2), None) == 0
+    assert float((dw2.cpu() - got).abs().max()) / scale < rtol * max(1.0, (N * H * W / 1024.0) ** 0.5)
+
+
+def test_wgrad_tc_rejects_unsupported():
+    L = det._C.lib()
+    x = torch.zeros(1, 4, 4, 64, device="cuda")
+    assert L.ttdg_wgrad_tc(x.data_ptr(), None, x.data_ptr(), None, 1, 4, 4, 64, 64, 1, 1, 0, x.data_ptr(), None) != 0
 
 
 def test_fpn_upsample_add_epilogue_tc():

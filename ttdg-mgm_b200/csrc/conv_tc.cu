@@ -16,6 +16,8 @@
 // BASELINE.json configs[1] holds on tensor cores.  Single-pass TF32 (x_lo == NULL) is the fast mode.
 #include "common.cuh"
 #include <cuda.h>
+#include <mutex>
+#include <unordered_map>
 
 namespace ttdg {
 
@@ -253,6 +255,173 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------- weight gradient
+// dW[tap][ci][co] += sum over pixels X[pixel + tap][ci] * dY[pixel][co]   (stride-1 convolutions)
+// GEMM: M = 128 input channels, N = BN output channels, K = pixels.  Pixels are the slow memory dimension of both NHWC
+// operands, so both are MN-major: a TMA box {32 channels, 32 pixels} lands as 32 rows (k = pixel) of 128 bytes
+// (mn = channel).  For 32-bit MN-major operands tcgen05 accepts only the 128-byte swizzle with 32-BYTE atoms (the
+// 16-byte-atom swizzle of the K-major kernels silently yields zeros), so these tensor maps use
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B and the descriptors layout type 1 (see umma_desc_mn_hi).  The tap shift and the
+// zero padding are again TMA coordinates / OOB fill.
+struct WgParams {
+    float *dw;
+    int Cin, Cout, R, S, pad;
+    int BW, BH, BI, tilesW, tilesH, tilesI;      // 32-pixel patches of the OUTPUT grid
+    int kblocks;                                 // patches in total
+    int splits;
+    uint64_t desc_hi;                            // shared-memory descriptor without the start address (see umma_desc_mn)
+};
+
+template <int BN_TILE, bool PRECISE>
+struct WgCfg {
+    static constexpr int A_BYTES = 128 * 128, B_BYTES = BN_TILE * 128;      // 32 pixels x (128 | BN) channels x 4 B
+    static constexpr int STAGE_BYTES = (PRECISE ? 2 : 1) * (A_BYTES + B_BYTES);
+    static constexpr int STAGES = PRECISE ? (BN_TILE == 128 ? 3 : 4) : (BN_TILE == 128 ? 6 : 8);
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int TMEM_COLS = 2 * BN_TILE;
+    static constexpr int CHUNK = 8;
+};
+
+// MN-major 32-bit operands have exactly one legal shared-memory layout on sm_100: the 128-byte swizzle with 32-byte
+// atoms (layout type 1; TMA swizzle CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), whose canonical atom is 32 channels (128 B) x
+// 4 pixels.  LBO = 4096 B (next 32-channel block), SBO = 512 B (next 4-pixel atom); one K = 8 MMA spans two atoms.
+__host__ __device__ __forceinline__ uint64_t umma_desc_mn_hi(uint32_t lbo16, uint32_t sbo16, uint32_t type) {
+    return ((uint64_t)lbo16 << 16) | ((uint64_t)sbo16 << 32) | ((uint64_t)1 << 46) | ((uint64_t)type << 61);
+}
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint64_t hi) { return (uint64_t)((saddr & 0x3FFFF) >> 4) | hi; }
+
+template <int BN_TILE, bool PRECISE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXlo,
+                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmDlo, const WgParams p) {
+    using Cfg = WgCfg<BN_TILE, PRECISE>;
+    extern __shared__ unsigned char tc_smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t *empty = full + Cfg::STAGES;
+    uint64_t *tmem_full = empty + Cfg::STAGES;
+    uint64_t *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cblocks = p.Cin / 128;
+    const int tap = blockIdx.x / cblocks, ci0 = (blockIdx.x - tap * cblocks) * 128;
+    const int r = tap / p.S, s = tap - r * p.S;
+    const int n0 = blockIdx.y * BN_TILE;
+    const int per = (p.kblocks + p.splits - 1) / p.splits;
+    const int kb0 = blockIdx.z * per, kb1 = min(p.kblocks, kb0 + per);
+    const int KB = max(0, kb1 - kb0);
+
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < Cfg::STAGES; ++st) { mbar_init(&full[st], 1); mbar_init(&empty[st], 1); }
+        mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
+        mbar_init(&tmem_empty[0], 4); mbar_init(&tmem_empty[1], 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                int t = kb;
+                const int tw = t % p.tilesW; t /= p.tilesW;
+                const int th = t % p.tilesH; t /= p.tilesH;
+                const int w0 = tw * p.BW, h0 = th * p.BH, i0 = t * p.BI;
+                mbar_wait(&empty[stage], phase ^ 1);
+                unsigned char *st = smem + stage * Cfg::STAGE_BYTES;
+                mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) {
+                    tma_load_4d(st + cb * 4096, &tmX, &full[stage], ci0 + 32 * cb, w0 + s - p.pad, h0 + r - p.pad, i0);
+                    if (PRECISE) tma_load_4d(st + Cfg::A_BYTES + Cfg::B_BYTES + cb * 4096, &tmXlo, &full[stage], ci0 + 32 * cb, w0 + s - p.pad, h0 + r - p.pad, i0);
+                }
+#pragma unroll
+                for (int nb = 0; nb < BN_TILE / 32; ++nb) {
+                    tma_load_4d(st + Cfg::A_BYTES + nb * 4096, &tmD, &full[stage], n0 + 32 * nb, w0, h0, i0);
+                    if (PRECISE) tma_load_4d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + nb * 4096, &tmDlo, &full[stage], n0 + 32 * nb, w0, h0, i0);
+                }
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // D = F32, A = B = TF32, both MN-major (bits 15, 16), N = BN_TILE, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN_TILE >> 3) << 17) |
+                                   ((uint32_t)(TC_BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const int buf = ch & 1;
+                mbar_wait(&tmem_empty[buf], ((ch >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * BN_TILE);
+                const int kend = min(KB, (ch + 1) * Cfg::CHUNK);
+                for (int kb = ch * Cfg::CHUNK; kb < kend; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a = smem_u32(smem + stage * Cfg::STAGE_BYTES), b = a + Cfg::A_BYTES;
+                    const uint32_t alo = b + Cfg::B_BYTES, blo = alo + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {                            // 32 pixels = 4 atoms of 8
+                        const uint32_t koff = k * 1024;
+                        umma_tf32(tacc, umma_desc_mn(a + koff, p.desc_hi), umma_desc_mn(b + koff, p.desc_hi), idesc, (kb != ch * Cfg::CHUNK) || k != 0);
+                        if (PRECISE) {
+                            umma_tf32(tacc, umma_desc_mn(alo + koff, p.desc_hi), umma_desc_mn(b + koff, p.desc_hi), idesc, 1);
+                            umma_tf32(tacc, umma_desc_mn(a + koff, p.desc_hi), umma_desc_mn(blo + koff, p.desc_hi), idesc, 1);
+                        }
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                                       // input channel inside the tile
+        float acc[BN_TILE];
+#pragma unroll
+        for (int j = 0; j < BN_TILE; ++j) acc[j] = 0.f;
+        const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int buf = ch & 1;
+            mbar_wait(&tmem_full[buf], (ch >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < BN_TILE; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN_TILE + c0), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+        }
+        if (KB > 0) {
+            float *dst = p.dw + ((size_t)tap * p.Cin + ci0 + row) * p.Cout + n0;
+#pragma unroll
+            for (int j = 0; j < BN_TILE; ++j) atomicAdd(dst + j, acc[j]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- operand preparation
 // hi = tf32(x) (round to nearest, stored as fp32), lo = x - hi (exact)
 __global__ void __launch_bounds__(256)
@@ -311,7 +480,37 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int make_map(CUtensorMap *m, const float *base, int rank, const cuuint64_t *dims, const cuuint32_t *box) {
+// Encoding a tensor map costs a few microseconds of host time and a step issues ~800 of them, mostly for buffers the
+// caching allocator hands back at the same address with the same geometry: keep a small cache keyed by
+// (base, dims, box).  The descriptor only names the address and the geometry, so a hit is always valid.
+struct MapKey {
+    const void *base; int rank; int swizzle; cuuint64_t d[4]; cuuint32_t b[4];
+    bool operator==(const MapKey &o) const {
+        if (base != o.base || rank != o.rank || swizzle != o.swizzle) return false;
+        for (int i = 0; i < rank; ++i) if (d[i] != o.d[i] || b[i] != o.b[i]) return false;
+        return true;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey &k) const {
+        size_t h = std::hash<const void *>()(k.base) ^ (size_t)(k.rank + 8 * k.swizzle) * 0x9E3779B97F4A7C15ull;
+        for (int i = 0; i < k.rank; ++i) h = h * 1099511628211ull ^ (size_t)k.d[i] * 31 ^ (size_t)k.b[i];
+        return h;
+    }
+};
+
+static int make_map(CUtensorMap *m, const float *base, int rank, const cuuint64_t *dims, const cuuint32_t *box,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    MapKey key = {};
+    key.base = base; key.rank = rank; key.swizzle = (int)swizzle;
+    for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *m = it->second; return 0; }
+    }
     EncodeTiledFn enc = get_encode();
     if (!enc) return TTDG_E_LIMIT;
     cuuint64_t strides[4];
@@ -319,9 +518,13 @@ static int make_map(CUtensorMap *m, const float *base, int rank, const cuuint64_
     for (int i = 0; i < rank - 1; ++i) { s *= dims[i]; strides[i] = s; }
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : TTDG_E_ARG;
+    if (r != CUDA_SUCCESS) return TTDG_E_ARG;
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(key, *m);
+    return 0;
 }
 
 static int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -341,6 +544,62 @@ static int launch_tc(const CUtensorMap &a, const CUtensorMap &alo, const CUtenso
 }  // namespace ttdg
 
 using namespace ttdg;
+
+template <int BN_TILE, bool PRECISE>
+static int launch_wg(const CUtensorMap &x, const CUtensorMap &xlo, const CUtensorMap &d, const CUtensorMap &dlo, const WgParams &p,
+                     cudaStream_t st) {
+    using Cfg = WgCfg<BN_TILE, PRECISE>;
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN_TILE, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((p.Cin / 128) * p.R * p.S, p.Cout / BN_TILE, p.splits);
+    count_launches(1);
+    wgrad_tc_kernel<BN_TILE, PRECISE><<<grid, TC_THREADS, Cfg::SMEM, st>>>(x, xlo, d, dlo, p);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int ttdg_wgrad_tc_supported(int Cin, int Cout, int stride) {
+    return (Cin % 128 == 0 && Cout % 64 == 0 && stride == 1) ? 1 : 0;
+}
+
+// dw [R][S][Cin][Cout] += X^T dY on tensor cores (stride-1 convs).  x_*: N x H x W x Cin; dy_*: N x Ho x Wo x Cout;
+// *_lo NULL -> single-pass TF32.  dw is accumulated into (fp32 atomics over the pixel splits).
+extern "C" int ttdg_wgrad_tc(const float *x_hi, const float *x_lo, const float *dy_hi, const float *dy_lo, int N, int H, int W, int Cin,
+                             int Cout, int R, int S, int pad, float *dw, void *stream) {
+    TTDG_CHECK_ARG(x_hi && dy_hi && dw && N >= 0 && (x_lo == nullptr) == (dy_lo == nullptr));
+    if (!ttdg_wgrad_tc_supported(Cin, Cout, 1)) return TTDG_E_LIMIT;
+    if (N == 0) return 0;
+    const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
+    if (Ho < 1 || Wo < 1) return TTDG_E_ARG;
+    WgParams p = {};
+    p.dw = dw; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad = pad;
+    p.BW = pow2_ge(Wo) < 32 ? pow2_ge(Wo) : 32;
+    p.BH = pow2_ge(Ho) < 32 / p.BW ? pow2_ge(Ho) : 32 / p.BW;
+    p.BI = 32 / (p.BW * p.BH);
+    p.tilesW = ceil_div(Wo, p.BW); p.tilesH = ceil_div(Ho, p.BH); p.tilesI = ceil_div(N, p.BI);
+    p.kblocks = p.tilesW * p.tilesH * p.tilesI;
+    const int bn_tile = Cout % 128 == 0 ? 128 : 64;
+    const int tiles = (Cin / 128) * R * S * (Cout / bn_tile);
+    int splits = (148 * 2 + tiles - 1) / tiles;
+    const int max_splits = (p.kblocks + 7) / 8;                 // at least 8 pixel blocks (256 pixels) per CTA
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.splits = splits;
+    CUtensorMap mx, mxlo, md, mdlo;
+    const cuuint64_t xdims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t ddims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+    const cuuint32_t box[4] = {32, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BI};
+    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    p.desc_hi = umma_desc_mn_hi(4096 >> 4, 512 >> 4, 1);
+    int rc = make_map(&mx, x_hi, 4, xdims, box, sw);
+    if (!rc) rc = make_map(&md, dy_hi, 4, ddims, box, sw);
+    if (!rc && x_lo) rc = make_map(&mxlo, x_lo, 4, xdims, box, sw);
+    if (!rc && dy_lo) rc = make_map(&mdlo, dy_lo, 4, ddims, box, sw);
+    if (rc) return rc;
+    if (!x_lo) { mxlo = mx; mdlo = md; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_lo) return bn_tile == 128 ? launch_wg<128, true>(mx, mxlo, md, mdlo, p, st) : launch_wg<64, true>(mx, mxlo, md, mdlo, p, st);
+    return bn_tile == 128 ? launch_wg<128, false>(mx, mxlo, md, mdlo, p, st) : launch_wg<64, false>(mx, mxlo, md, mdlo, p, st);
+}
 
 extern "C" int ttdg_tf32_split(const float *x, float *hi, float *lo, int64_t numel, void *stream) {
     TTDG_CHECK_ARG(x && hi && lo && numel >= 0 && numel % 4 == 0);

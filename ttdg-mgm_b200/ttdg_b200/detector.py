@@ -35,6 +35,7 @@ def _pad4(c):
 # kernel does not cover (stride 2, Cin % 32 != 0, Cout % 64 != 0) always use the CUDA-core kernel.
 CONV_MODE = [os.environ.get("TTDG_CONV", "tf32x3")]
 PARAM_EPOCH = [0]              # bumped by FlatSGD.step: invalidates the K-major weight copies below
+WGRAD_TC = [os.environ.get("TTDG_WGRAD_TC", "1") == "1"]       # weight gradients on tensor cores (MN-major operands)
 
 
 def set_conv_mode(mode):
@@ -139,7 +140,7 @@ class _ConvFn(torch.autograd.Function):
             check(L.ttdg_relu_bn_bwd(_p(d_pre), None, _p(scale), Cout, d_pre.numel(), _p(d_conv), s), "bn_bwd")
         else:
             d_conv = d_pre
-        g_x = g_w = None
+        g_x = g_w = d_hi = d_lo = None
         if ctx.needs_input_grad[0]:
             g_x = (torch.zeros if stride == 2 else torch.empty)(N, H, W, Cin, dtype=torch.float32, device=g.device)
             if _tc_ok(Cout, Cin, stride):                  # GEMM k = Cout, n = Cin; taps mirrored, pad' = R - 1 - pad
@@ -152,7 +153,17 @@ class _ConvFn(torch.autograd.Function):
                 check(L.ttdg_conv_dgrad(_p(d_conv), _p(w), N, H, W, Cin, Cout, R, S, stride, pad, _p(g_x), s), "conv_dgrad")
         if ctx.needs_input_grad[1]:
             g_w = torch.zeros_like(w)
-            check(L.ttdg_conv_wgrad(_p(x), _p(d_conv), N, H, W, Cin, Cout, R, S, stride, pad, _p(g_w), s), "conv_wgrad")
+            if CONV_MODE[0] != "simt" and WGRAD_TC[0] and stride == 1 and Cin % 128 == 0 and Cout % 64 == 0:
+                precise = CONV_MODE[0] == "tf32x3"
+                if precise:
+                    x_hi, x_lo = tf32_split(x)
+                    if d_hi is None:
+                        d_hi, d_lo = tf32_split(d_conv)
+                else:
+                    x_hi, x_lo, d_hi, d_lo = x, None, d_conv, None
+                check(L.ttdg_wgrad_tc(_p(x_hi), _p(x_lo), _p(d_hi), _p(d_lo), N, H, W, Cin, Cout, R, S, pad, _p(g_w), s), "wgrad_tc")
+            else:
+                check(L.ttdg_conv_wgrad(_p(x), _p(d_conv), N, H, W, Cin, Cout, R, S, stride, pad, _p(g_w), s), "conv_wgrad")
         return g_x, g_w, g_bias, g_res, None, None, None, None, None, None, None, None, None
 
 
