@@ -240,24 +240,30 @@ int ttdg_preprocess(const unsigned char *img_u8, int N, int H, int W, float mean
 /* Tensor-core version of ttdg_conv_fwd / stride-1 ttdg_conv_dgrad: tcgen05.mma.kind::tf32 fed by TMA (activations as a 4-D
  * NHWC tensor map - filter taps are coordinate shifts, padding is TMA's out-of-bounds zero fill), fp32 accumulators in
  * TMEM, same fused epilogue.  Requires Cin % 32 == 0, Cout % 64 == 0, stride 1 (ttdg_conv_tc_supported).
- *   x_hi, x_lo : N x H x W x Cin.  x_lo == NULL -> single-pass TF32 on x_hi.  Otherwise "3xTF32": hi = tf32(x),
- *                lo = x - hi (ttdg_tf32_split) and hi*hi + lo*hi + hi*lo gives fp32-grade products (parity config).
- *   wk_hi, wk_lo: weights K-major [taps][n][k]: forward = [R*S][Cout][Cin] (ttdg_weight_transpose_split of the
- *                [R][S][Cin][Cout] parameter); data gradient (flip = 1, pad = R-1-pad_fwd, x = dY) = the parameter array
- *                itself read as [R*S][n = Cin_fwd][k = Cout_fwd], split with ttdg_tf32_split.
- *   (Cin, Cout) are the GEMM's k and n extents. */
+ *   x          : N x H x W x Cin, fp32.
+ *   wk_hi, wk_lo: weights K-major [taps][n][k], split into hi = tf32(w) and lo = w - hi: forward = [R*S][Cout][Cin]
+ *                (ttdg_weight_transpose_split of the [R][S][Cin][Cout] parameter); data gradient (flip = 1,
+ *                pad = R-1-pad_fwd, x = dY) = the parameter array itself read as [R*S][n = Cin_fwd][k = Cout_fwd], split
+ *                with ttdg_tf32_split.  wk_lo == NULL -> single-pass TF32.  Otherwise "3xTF32": hi*hi + lo*hi + hi*lo
+ *                gives fp32-grade products (parity config); the activations are split in shared memory inside the
+ *                kernel's pipeline, between the TMA arrival and the MMA.
+ *   (Cin, Cout) are the GEMM's k and n extents.
+ *   Strided 1x1 convs (the first block of res3 / res4 / res5, STRIDE_IN_1X1): in_stride = 2 reads x[n, 2 ho, 2 wo] through
+ *   TMA element strides (forward); out_stride = 2 stores the result for (ho, wo) at (2 ho, 2 wo) of a zero-filled
+ *   outH x outW map (data gradient).  R = S = 1, pad = 0 only; outH / outW are ignored when out_stride == 1. */
 int ttdg_conv_tc_supported(int Cin, int Cout, int stride);
-int ttdg_conv_tc(const float *x_hi, const float *x_lo, const float *wk_hi, const float *wk_lo, const float *scale,
-                 const float *bias, const float *residual, int res_mode, int relu, int flip, int N, int H, int W,
-                 int Cin, int Cout, int R, int S, int pad, float *y, void *stream);
-/* Weight gradient on tensor cores (stride-1 convs, Cin % 128 == 0, Cout % 64 == 0): dw [R][S][Cin][Cout] +=
+int ttdg_conv_tc(const float *x, const float *wk_hi, const float *wk_lo, const float *scale, const float *bias,
+                 const float *residual, int res_mode, int relu, int flip, int N, int H, int W, int Cin, int Cout, int R,
+                 int S, int pad, int in_stride, int out_stride, int outH, int outW, float *y, void *stream);
+/* Weight gradient on tensor cores (stride-1 convs and 1x1 stride-2 convs, Cin % 128 == 0, Cout % 64 == 0): dw [R][S][Cin][Cout] +=
  * sum_pixels X[pixel + tap][ci] dY[pixel][co].  Both operands are MN-major (pixels = GEMM k = slow memory dimension):
  * TMA boxes of {32 channels, 32 pixels} with the 128-byte / 32-byte-atom swizzle, the only MN-major layout tcgen05
- * takes for 32-bit operands.  Accumulated into dw with fp32 atomics over the pixel splits.  *_lo NULL = single-pass
- * TF32.  Replaces the weight half of torch autograd's conv backward behind loss.backward() (engine/trainer.py:481). */
+ * takes for 32-bit operands.  Accumulated into dw with fp32 atomics over the pixel splits.  precise != 0 = 3xTF32 (both
+ * operands split inside the pipeline), 0 = single-pass TF32.  Replaces the weight half of torch autograd's conv
+ * backward behind loss.backward() (engine/trainer.py:481). */
 int ttdg_wgrad_tc_supported(int Cin, int Cout, int stride);
-int ttdg_wgrad_tc(const float *x_hi, const float *x_lo, const float *dy_hi, const float *dy_lo, int N, int H, int W, int Cin,
-                  int Cout, int R, int S, int pad, float *dw, void *stream);
+int ttdg_wgrad_tc(const float *x, const float *dy, int precise, int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
+                  int pad, float *dw, void *stream);
 int ttdg_tf32_split(const float *x, float *hi, float *lo, int64_t numel, void *stream);
 /* w [taps][Cin][Cout] -> wt_hi, wt_lo (may be NULL) [taps][Cout][Cin] */
 int ttdg_weight_transpose_split(const float *w, int taps, int Cin, int Cout, float *wt_hi, float *wt_lo, void *stream);

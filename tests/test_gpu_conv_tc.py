@@ -110,12 +110,8 @@ def test_wgrad_tc(mode, rtol, cin, cout, k, pad, H, W, N):
     xc, dc = nhwc(x).cuda(), nhwc(dy).cuda()
     start = torch.randn(k, k, cin, cout, generator=g)
     dw = start.cuda()
-    if mode == "tf32x3":
-        (xh, xl), (dh, dl) = det.tf32_split(xc), det.tf32_split(dc)
-    else:
-        xh, xl, dh, dl = xc, None, dc, None
     p = lambda t: None if t is None else t.data_ptr()
-    rc = L.ttdg_wgrad_tc(p(xh), p(xl), p(dh), p(dl), N, H, W, cin, cout, k, k, pad, p(dw), None)
+    rc = L.ttdg_wgrad_tc(p(xc), p(dc), int(mode == "tf32x3"), N, H, W, cin, cout, k, k, 1, pad, p(dw), None)
     torch.cuda.synchronize()
     assert rc == 0
     got = dw.cpu() - start
@@ -129,7 +125,9 @@ def test_wgrad_tc(mode, rtol, cin, cout, k, pad, H, W, N):
 def test_wgrad_tc_rejects_unsupported():
     L = det._C.lib()
     x = torch.zeros(1, 4, 4, 64, device="cuda")
-    assert L.ttdg_wgrad_tc(x.data_ptr(), None, x.data_ptr(), None, 1, 4, 4, 64, 64, 1, 1, 0, x.data_ptr(), None) != 0
+    assert L.ttdg_wgrad_tc(x.data_ptr(), x.data_ptr(), 1, 1, 4, 4, 64, 64, 1, 1, 1, 0, x.data_ptr(), None) != 0
+    x = torch.zeros(1, 4, 4, 128, device="cuda")                       # stride 2 is for 1x1 convs only
+    assert L.ttdg_wgrad_tc(x.data_ptr(), x.data_ptr(), 1, 1, 4, 4, 128, 128, 3, 3, 2, 1, x.data_ptr(), None) != 0
 
 
 def test_fpn_upsample_add_epilogue_tc():
@@ -177,3 +175,33 @@ def test_conv_tc_layer_vs_torch(cin, cout, k, pad, H, W, N, norm, relu):
     rel = lambda a, r: float((a - r).abs().max() / r.abs().max())
     assert rel(nchw(yc.detach().cpu()), y.detach()) < 1e-5
     assert rel(nchw(xc.grad.cpu()), x.grad) < 1e-5
+
+
+@pytest.mark.parametrize("mode,rtol", [("tf32x3", 1e-5), ("tf32", 6e-3)])
+@pytest.mark.parametrize("cin,cout,H,W,N", [(256, 128, 16, 16, 2), (256, 512, 16, 16, 2), (512, 1024, 9, 11, 3), (1024, 2048, 6, 6, 2),
+                                           (128, 64, 130, 130, 1)])
+def test_conv_tc_stride2_1x1(mode, rtol, cin, cout, H, W, N):
+    """The strided 1x1 convs of res3/res4/res5's first block (STRIDE_IN_1X1, projection shortcut): forward through TMA
+    element strides, data gradient scattered to the even pixels, weight gradient from the strided X - against torch."""
+    det.set_conv_mode(mode)
+    g = torch.Generator().manual_seed(cin + cout + H)
+    layer = det.Conv2d(cin, cout, 1, 2, 0, bias=False).cuda()
+    w = (torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5).requires_grad_(True)
+    layer.load_state_dict({"weight": w.detach()})
+    x = torch.randn(N, cin, H, W, generator=g).requires_grad_(True)
+    y = F.conv2d(x, w, None, 2, 0)
+    up = torch.randn(y.shape, generator=g)
+    (y * up).sum().backward()
+    xc = nhwc(x.detach()).cuda().requires_grad_(True)
+    yc = layer(xc)
+    (yc * nhwc(up).cuda()).sum().backward()
+    rel = lambda a, r: float((a - r).abs().max() / r.abs().max())
+    assert rel(nchw(yc.detach().cpu()), y.detach()) < rtol
+    assert rel(nchw(xc.grad.cpu()), x.grad) < rtol
+    assert rel(layer.weight.grad[:, :, :cin, :cout].permute(3, 2, 0, 1).cpu(), w.grad) < rtol * max(1.0, (N * H * W / 4096.0) ** 0.5)
+    det.set_conv_mode("simt")                                  # and the CUDA-core kernels agree
+    xs = nhwc(x.detach()).cuda().requires_grad_(True)
+    layer.weight.grad = None
+    ys = layer(xs)
+    (ys * nhwc(up).cuda()).sum().backward()
+    assert rel(ys.detach(), yc.detach()) < rtol and rel(xs.grad, xc.grad) < rtol

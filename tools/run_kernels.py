@@ -76,4 +76,39 @@ elif what == "timing":
                             ("backward", t5, t6), ("sgd", t6, t7), ("eval_pass", t7, t8), ("TOTAL", t0, t8)):
                 acc[k] += a.elapsed_time(b) / reps
     print({k: round(v, 2) for k, v in acc.items()}, "gagm iters", int(m.multi_matching_unsup.last_aux["info"][0]))
+elif what == "busy":
+    # hot (not cold-cache) per-kernel device time of the full step and the GPU-busy fraction, from CUPTI via torch.profiler
+    sys.path.insert(0, ROOT)
+    import time, collections
+    import bench
+    from torch.profiler import profile, ProfilerActivity
+    m, opt = bench.build_ours(dev)
+    inputs = [dict(d, image=d["image"].to(dev)) for d in bench.make_inputs(0)]
+    def step():
+        m.train()
+        loss, _, _, _ = m(inputs, branch="TTT")
+        opt.zero_grad(); loss.backward(); opt.step(1)
+        m.eval()
+        return m(inputs)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            step()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / reps * 1e3
+    tot, cnt = collections.defaultdict(float), collections.Counter()
+    for e in prof.events():
+        if str(e.device_type).endswith("CUDA"):
+            name = e.name.split("(")[0][:80]
+            tot[name] += e.device_time / reps / 1e3
+            cnt[name] += 1
+    busy = sum(tot.values())
+    print("wall ms/step %.2f (under the profiler), device busy ms/step %.2f (%.0f%%), launches/step %d" %
+          (wall, busy, 100 * busy / wall, sum(cnt.values()) // reps))
+    print("kernel,launches_per_step,ms_per_step,share_pct")
+    for k, v in sorted(tot.items(), key=lambda x: -x[1])[:45]:
+        print('"%s",%d,%.3f,%.1f' % (k, cnt[k] // reps, v, 100 * v / busy))
 torch.cuda.synchronize()

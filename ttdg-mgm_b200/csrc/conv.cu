@@ -28,7 +28,7 @@ struct ConvParams {
     int N, H, W_, Cin;   // gathered tensor: N x H x W_ x Cin (channels of the gathered operand)
     int Ho, Wo, Cout;    // GEMM pixel grid (Ho x Wo per image) and GEMM n extent
     int R, S, stride, pad;
-    int os;              // output scatter stride (Y is N x Ho*os x Wo*os x Cout)
+    int os, Hy, Wy;      // output scatter stride: pixel (ho, wo) is stored at (ho, wo) * os of the N x Hy x Wy x Cout map Y
     int res_mode;        // 0 none, 1 same pixel, 2 nearest-upsampled from (Ho/2 x Wo/2)
     int relu;
     int wR, wS, wCin, wCout;   // real weight dims for DGRAD's transposed read
@@ -198,7 +198,7 @@ conv_gemm_kernel(const ConvParams p) {
     }
 
     // ---------------- epilogue
-    const int Hy = p.Ho * p.os, Wy = p.Wo * p.os;
+    const int Hy = p.Hy, Wy = p.Wy;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int m = m0 + tm + (i & 3) + (i >> 2) * 64;
@@ -372,7 +372,7 @@ extern "C" int ttdg_conv_fwd(const float *x, const float *w, const float *scale,
     p.X = x; p.W = w; p.Y = y; p.scale = scale; p.bias = bias; p.residual = residual;
     p.N = N; p.H = H; p.W_ = W; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.stride = stride; p.pad = pad;
     p.Ho = (H + 2 * pad - R) / stride + 1; p.Wo = (W + 2 * pad - S) / stride + 1;
-    p.os = 1; p.res_mode = res_mode; p.relu = relu;
+    p.os = 1; p.Hy = p.Ho; p.Wy = p.Wo; p.res_mode = res_mode; p.relu = relu;
     if (res_mode == 2 && ((p.Ho | p.Wo) & 1)) return TTDG_E_ARG;
     return launch_conv(Cin % 16 == 0 ? MODE_FWD : MODE_FWD_GENERIC, p, (cudaStream_t)stream);
 }
@@ -390,7 +390,7 @@ extern "C" int ttdg_conv_dgrad(const float *dy, const float *w, int N, int H, in
     p.Cout = Cin;                                        // GEMM n = cin
     p.R = R; p.S = S; p.stride = 1; p.pad = R - 1 - pad;
     p.Ho = stride == 1 ? H : Ho; p.Wo = stride == 1 ? W : Wo;
-    p.os = stride;
+    p.os = stride; p.Hy = H; p.Wy = W;                   // odd H / W: the last input row / column gets no gradient
     p.wR = R; p.wS = S; p.wCin = Cin; p.wCout = Cout;
     return launch_conv(MODE_DGRAD, p, (cudaStream_t)stream);
 }

@@ -9,11 +9,13 @@
 //   * B operand (weights, K-major [tap][n][k]): TMA load of {32, BN_TILE, 1};
 //   * both land in shared memory as 128-byte-swizzled K-major tiles, exactly the canonical UMMA layout, and are
 //     consumed by tcgen05.mma.kind::tf32 (M = 128, N = BN_TILE, K = 8) accumulating fp32 in TMEM;
-//   * warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected thread), warps 2-5 = epilogue
-//     (tcgen05.ld -> FrozenBN scale / bias / residual / FPN-upsample add / ReLU -> global), mbarrier ring between them.
-// fp32 parity mode ("3xTF32"): operands are split on the fly in global memory into hi = tf32(x) and lo = x - hi
-// (ttdg_tf32_split); hi*hi + lo*hi + hi*lo recovers fp32-grade products (dropped term ~2^-22), so the 1e-4 mIoU gate of
-// BASELINE.json configs[1] holds on tensor cores.  Single-pass TF32 (x_lo == NULL) is the fast mode.
+//   * warps 0-7 = epilogue (tcgen05.ld -> FrozenBN scale / bias / residual / FPN-upsample add / ReLU -> global),
+//     warps 8-11 = operand split (3xTF32 mode), warp 12 = TMA producer, warp 13 = TMEM allocator + MMA issuer (one
+//     elected thread), mbarrier ring between them.
+// fp32 parity mode ("3xTF32"): hi = tf32(x), lo = x - hi; hi*hi + lo*hi + hi*lo recovers fp32-grade products (dropped
+// term ~2^-22), so the 1e-4 mIoU gate of BASELINE.json configs[1] holds on tensor cores.  Weights are split once per
+// optimizer step (ttdg_weight_transpose_split / ttdg_tf32_split); activations are split in shared memory by the split
+// warps between the TMA arrival and the MMA (no extra pass over HBM).  Single-pass TF32 (wk_lo == NULL) is the fast mode.
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
@@ -21,7 +23,10 @@
 
 namespace ttdg {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 448;       // warps 0-7 epilogue, 8-11 operand split (3xTF32 mode), 12 TMA producer, 13 MMA issuer
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_WARP_CVT0 = 8, TC_CVT_THREADS = 128;
+constexpr int TC_WARP_TMA = 12, TC_WARP_MMA = 13;
 constexpr int TC_BM = 128;           // output pixels per tile (TMEM lanes)
 constexpr int TC_BK = 32;            // fp32 channels per k-block = one 128-byte swizzle row
 constexpr int TC_UMMA_K = 8;         // tf32
@@ -35,6 +40,8 @@ struct TcParams {
     int tilesW, tilesH, tilesI;
     int kslabs;                      // Cin / 32
     int res_mode, relu;
+    int in_stride;                   // 1, or 2 for a strided 1x1 conv: the tensor map has element strides {1, 2, 2, 1}
+    int out_stride, outH, outW;      // output pixel (ho, wo) is stored at (ho, wo) * out_stride of an outH x outW map
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -92,13 +99,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 3xTF32 operand split INSIDE the pipeline.  TMA lands the raw fp32 activations; the four split warps rewrite the tile in
+// place as hi = tf32(x) and store lo = x - hi at the same offset of the stage's "lo" half, then hand the stage to the
+// MMA warp.  Elementwise on the raw bytes, so it is independent of the swizzle; activations are read from HBM once as
+// fp32 instead of twice (hi + lo written by a separate pass).
+template <int BYTES>
+__device__ __forceinline__ void split_stage(unsigned char *raw, unsigned char *lo, int t) {
+    static_assert(BYTES % (TC_CVT_THREADS * 16) == 0, "tile must divide over the split warps");
+#pragma unroll
+    for (int off = 0; off < BYTES; off += TC_CVT_THREADS * 16) {
+        const float4 v = *reinterpret_cast<const float4 *>(raw + off + t * 16);
+        float4 h, l;
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
+        *reinterpret_cast<float4 *>(raw + off + t * 16) = h;
+        *reinterpret_cast<float4 *>(lo + off + t * 16) = l;
+    }
+}
+
 template <int BN_TILE, bool PRECISE>
 struct TcCfg {
     static constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN_TILE * 128;
-    static constexpr int STAGE_BYTES = (PRECISE ? 2 : 1) * (A_BYTES + B_BYTES);
+    static constexpr int STAGE_BYTES = (PRECISE ? 2 : 1) * (A_BYTES + B_BYTES);      // [A | B | A lo | B lo]
+    static constexpr int TX_BYTES = A_BYTES + (PRECISE ? 2 : 1) * B_BYTES;           // what TMA delivers per stage
     static constexpr int STAGES = PRECISE ? (BN_TILE == 128 ? 3 : 4) : (BN_TILE == 128 ? 6 : 8);
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
     static constexpr int TMEM_COLS = 2 * BN_TILE;        // two accumulator buffers (ping-pong between MMA and epilogue)
+    static constexpr int EPI_COLS = BN_TILE / 2;         // columns per epilogue warp (two warps share a TMEM lane group)
     // The tensor core adds into its fp32 accumulator with truncation, so the error of one long accumulation grows
     // linearly with K (measured 5e-5 relative at K = 12544).  The accumulation is therefore cut into chunks of CHUNK
     // k-blocks: each chunk starts from zero in the other TMEM buffer and the epilogue warps add the drained chunks in
@@ -106,18 +136,98 @@ struct TcCfg {
     static constexpr int CHUNK = 8;
 };
 
+struct TcSmem {
+    unsigned char *tiles;
+    uint64_t *full, *empty, *conv, *tmem_full, *tmem_empty;
+    uint32_t *tmem_slot;
+};
+
+// carve the dynamic shared memory, initialise the barriers, allocate TMEM; returns the TMEM base address
+template <class Cfg>
+__device__ __forceinline__ uint32_t tc_prologue(TcSmem &sm, unsigned char *raw_smem) {
+    sm.tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(raw_smem) + 1023) & ~(uintptr_t)1023);
+    sm.full = reinterpret_cast<uint64_t *>(sm.tiles + Cfg::STAGES * Cfg::STAGE_BYTES);
+    sm.empty = sm.full + Cfg::STAGES;
+    sm.conv = sm.empty + Cfg::STAGES;
+    sm.tmem_full = sm.conv + Cfg::STAGES;                // [2]
+    sm.tmem_empty = sm.tmem_full + 2;                    // [2]
+    sm.tmem_slot = reinterpret_cast<uint32_t *>(sm.tmem_empty + 2);
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); mbar_init(&sm.conv[s], TC_CVT_THREADS); }
+        mbar_init(&sm.tmem_full[0], 1); mbar_init(&sm.tmem_full[1], 1);
+        mbar_init(&sm.tmem_empty[0], TC_EPI_WARPS); mbar_init(&sm.tmem_empty[1], TC_EPI_WARPS);      // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == TC_WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm.tmem_slot)), "n"(Cfg::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return *sm.tmem_slot;
+}
+
+template <class Cfg>
+__device__ __forceinline__ void tc_epilogue_end(uint32_t tmem_base) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == TC_WARP_MMA) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
+    }
+}
+
+// split warps: every k-block, wait for TMA, split the first SPLIT_BYTES of the stage, publish to the MMA warp
+template <class Cfg, int SPLIT_BYTES>
+__device__ __forceinline__ void tc_split_loop(const TcSmem &sm, int KB) {
+    const int t = threadIdx.x - TC_WARP_CVT0 * 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&sm.full[stage], phase);
+        unsigned char *st = sm.tiles + stage * Cfg::STAGE_BYTES;
+        split_stage<SPLIT_BYTES>(st, st + Cfg::A_BYTES + Cfg::B_BYTES, t);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> tensor-core (async proxy) reads
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.conv[stage])) : "memory");
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+    }
+}
+
+// epilogue warps: add the drained TMEM chunks (columns col0 .. col0 + EPI_COLS of lane group q) in registers
+template <class Cfg>
+__device__ __forceinline__ void tc_drain(const TcSmem &sm, uint32_t tmem_base, int KB, int q, int col0, float (&acc)[Cfg::EPI_COLS]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < Cfg::EPI_COLS; ++j) acc[j] = 0.f;
+    const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int buf = ch & 1;
+        mbar_wait(&sm.tmem_full[buf], (ch >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int c0 = 0; c0 < Cfg::EPI_COLS; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * (Cfg::TMEM_COLS / 2) + col0 + c0), v);   // warp-collective
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);                      // round-to-nearest fp32
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.tmem_empty[buf])) : "memory");
+    }
+}
+
 template <int BN_TILE, bool PRECISE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
-               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
     using Cfg = TcCfg<BN_TILE, PRECISE>;
     extern __shared__ unsigned char tc_smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-    uint64_t *empty = full + Cfg::STAGES;
-    uint64_t *tmem_full = empty + Cfg::STAGES;           // [2]
-    uint64_t *tmem_empty = tmem_full + 2;                // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    TcSmem sm;
+    const uint32_t tmem_base = tc_prologue<Cfg>(sm, tc_smem_raw);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // tile coordinates
@@ -129,23 +239,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n0 = blockIdx.y * BN_TILE;
     const int KB = p.R * p.S * p.kslabs;
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
-        mbar_init(&tmem_empty[0], 4); mbar_init(&tmem_empty[1], 4);      // one arrival per epilogue warp
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
+    if (warp == TC_WARP_TMA) {
         // ===================== TMA producer
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -156,19 +250,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int tap = kb / p.kslabs, c0 = (kb - tap * p.kslabs) * TC_BK;
                 const int r = tap / p.S, s = tap - r * p.S;
                 const int btap = p.flip ? (p.R - 1 - r) * p.S + (p.S - 1 - s) : tap;
-                mbar_wait(&empty[stage], phase ^ 1);
-                unsigned char *st = smem + stage * Cfg::STAGE_BYTES;
-                mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                tma_load_4d(st, &tmA, &full[stage], c0, w0 + s - p.pad, h0 + r - p.pad, i0);
-                tma_load_3d(st + Cfg::A_BYTES, &tmB, &full[stage], c0, n0, btap);
-                if (PRECISE) {
-                    tma_load_4d(st + Cfg::A_BYTES + Cfg::B_BYTES, &tmAlo, &full[stage], c0, w0 + s - p.pad, h0 + r - p.pad, i0);
-                    tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tmBlo, &full[stage], c0, n0, btap);
-                }
+                mbar_wait(&sm.empty[stage], phase ^ 1);
+                unsigned char *st = sm.tiles + stage * Cfg::STAGE_BYTES;
+                mbar_expect_tx(&sm.full[stage], Cfg::TX_BYTES);
+                tma_load_4d(st, &tmA, &sm.full[stage], c0, (w0 + s - p.pad) * p.in_stride, (h0 + r - p.pad) * p.in_stride, i0);
+                tma_load_3d(st + Cfg::A_BYTES, &tmB, &sm.full[stage], c0, n0, btap);
+                if (PRECISE) tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tmBlo, &sm.full[stage], c0, n0, btap);
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == TC_WARP_MMA) {
         // ===================== MMA issuer
         if (lane == 0) {
             // instruction descriptor: D = F32, A = B = TF32, both K-major, N = BN_TILE, M = 128
@@ -178,14 +269,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int buf = ch & 1;
-                mbar_wait(&tmem_empty[buf], ((ch >> 1) & 1) ^ 1);            // epilogue has drained this buffer
+                mbar_wait(&sm.tmem_empty[buf], ((ch >> 1) & 1) ^ 1);         // epilogue has drained this buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * BN_TILE);
                 const int kb_end = min(KB, (ch + 1) * Cfg::CHUNK);
                 for (int kb = ch * Cfg::CHUNK; kb < kb_end; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait(PRECISE ? &sm.conv[stage] : &sm.full[stage], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a = smem_u32(smem + stage * Cfg::STAGE_BYTES), b = a + Cfg::A_BYTES;
+                    const uint32_t a = smem_u32(sm.tiles + stage * Cfg::STAGE_BYTES), b = a + Cfg::A_BYTES;
                     const uint32_t alo = b + Cfg::B_BYTES, blo = alo + Cfg::A_BYTES;
 #pragma unroll
                     for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
@@ -196,49 +287,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             umma_tf32(tacc, umma_desc(a + koff), umma_desc(blo + koff), idesc, 1);
                         }
                     }
-                    umma_commit(&empty[stage]);                              // frees the smem slot when these MMAs retire
+                    umma_commit(&sm.empty[stage]);                           // frees the smem slot when these MMAs retire
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[buf]);                                // this chunk's accumulator is complete
+                umma_commit(&sm.tmem_full[buf]);                             // this chunk's accumulator is complete
             }
         }
+    } else if (warp >= TC_WARP_CVT0) {
+        if (PRECISE) tc_split_loop<Cfg, Cfg::A_BYTES>(sm, KB);                // activations only: the weight copies are pre-split
     } else {
-        // ===================== epilogue: warps 2..5 own TMEM lanes 32 * (warp % 4) ..
-        const int q = warp & 3;
+        // ===================== epilogue: warps 0..7; warp w owns TMEM lanes 32 * (w % 4) .. and column half w / 4
+        const int q = warp & 3, col0 = (warp >> 2) * Cfg::EPI_COLS;
         const int row = q * 32 + lane;                                       // GEMM row inside the tile = TMEM lane
         const int bi = row / (p.BH * p.BW), rem = row - bi * p.BH * p.BW;
         const int bh = rem / p.BW, bw = rem - bh * p.BW;
         const int img = i0 + bi, ho = h0 + bh, wo = w0 + bw;
         const bool ok = img < p.N && ho < p.Ho && wo < p.Wo;
-        float acc[BN_TILE];
-#pragma unroll
-        for (int j = 0; j < BN_TILE; ++j) acc[j] = 0.f;
-        const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int buf = ch & 1;
-            mbar_wait(&tmem_full[buf], (ch >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int c0 = 0; c0 < BN_TILE; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN_TILE + c0), v);   // warp-collective
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);                      // round-to-nearest fp32
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
-        }
+        float acc[Cfg::EPI_COLS];
+        tc_drain<Cfg>(sm, tmem_base, KB, q, col0, acc);
         const size_t pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
-        float *yrow = p.y + pix * p.Cout + n0;
+        const size_t opix = ((size_t)img * p.outH + ho * p.out_stride) * p.outW + wo * p.out_stride;
+        const int nb = n0 + col0;
+        float *yrow = p.y + opix * p.Cout + nb;
         const float *rrow = nullptr;
         if (ok) {
-            if (p.res_mode == 1) rrow = p.residual + pix * p.Cout + n0;
-            else if (p.res_mode == 2) rrow = p.residual + (((size_t)img * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * p.Cout + n0;
+            if (p.res_mode == 1) rrow = p.residual + pix * p.Cout + nb;
+            else if (p.res_mode == 2) rrow = p.residual + (((size_t)img * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * p.Cout + nb;
 #pragma unroll
-            for (int j = 0; j < BN_TILE; j += 4) {
+            for (int j = 0; j < Cfg::EPI_COLS; j += 4) {
                 float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-                const int n = n0 + j;
+                const int n = nb + j;
                 if (p.scale) { const float4 s4 = *reinterpret_cast<const float4 *>(p.scale + n); o.x *= s4.x; o.y *= s4.y; o.z *= s4.z; o.w *= s4.w; }
                 if (p.bias) { const float4 b4 = *reinterpret_cast<const float4 *>(p.bias + n); o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w; }
                 if (rrow) { const float4 r4 = *reinterpret_cast<const float4 *>(rrow + j); o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
@@ -246,13 +324,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 *reinterpret_cast<float4 *>(yrow + j) = o;
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
-    }
+    tc_epilogue_end<Cfg>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------- weight gradient
@@ -262,23 +335,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // (mn = channel).  For 32-bit MN-major operands tcgen05 accepts only the 128-byte swizzle with 32-BYTE atoms (the
 // 16-byte-atom swizzle of the K-major kernels silently yields zeros), so these tensor maps use
 // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B and the descriptors layout type 1 (see umma_desc_mn_hi).  The tap shift and the
-// zero padding are again TMA coordinates / OOB fill.
+// zero padding are again TMA coordinates / OOB fill.  Both operands are activations: in the 3xTF32 mode the split
+// warps rewrite BOTH tiles of a stage.
 struct WgParams {
     float *dw;
     int Cin, Cout, R, S, pad;
     int BW, BH, BI, tilesW, tilesH, tilesI;      // 32-pixel patches of the OUTPUT grid
     int kblocks;                                 // patches in total
     int splits;
+    int stride;                                  // 1, or 2 (1x1 convs): X is read through element strides {1, 2, 2, 1}
     uint64_t desc_hi;                            // shared-memory descriptor without the start address (see umma_desc_mn)
 };
 
 template <int BN_TILE, bool PRECISE>
 struct WgCfg {
     static constexpr int A_BYTES = 128 * 128, B_BYTES = BN_TILE * 128;      // 32 pixels x (128 | BN) channels x 4 B
-    static constexpr int STAGE_BYTES = (PRECISE ? 2 : 1) * (A_BYTES + B_BYTES);
+    static constexpr int STAGE_BYTES = (PRECISE ? 2 : 1) * (A_BYTES + B_BYTES);      // [X | dY | X lo | dY lo]
+    static constexpr int TX_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = PRECISE ? (BN_TILE == 128 ? 3 : 4) : (BN_TILE == 128 ? 6 : 8);
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
     static constexpr int TMEM_COLS = 2 * BN_TILE;
+    static constexpr int EPI_COLS = BN_TILE / 2;
     static constexpr int CHUNK = 8;
 };
 
@@ -292,16 +369,11 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint64_t hi) { 
 
 template <int BN_TILE, bool PRECISE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXlo,
-                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmDlo, const WgParams p) {
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, const WgParams p) {
     using Cfg = WgCfg<BN_TILE, PRECISE>;
     extern __shared__ unsigned char tc_smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-    uint64_t *empty = full + Cfg::STAGES;
-    uint64_t *tmem_full = empty + Cfg::STAGES;
-    uint64_t *tmem_empty = tmem_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    TcSmem sm;
+    const uint32_t tmem_base = tc_prologue<Cfg>(sm, tc_smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cblocks = p.Cin / 128;
     const int tap = blockIdx.x / cblocks, ci0 = (blockIdx.x - tap * cblocks) * 128;
@@ -311,23 +383,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int kb0 = blockIdx.z * per, kb1 = min(p.kblocks, kb0 + per);
     const int KB = max(0, kb1 - kb0);
 
-    if (threadIdx.x == 0) {
-        for (int st = 0; st < Cfg::STAGES; ++st) { mbar_init(&full[st], 1); mbar_init(&empty[st], 1); }
-        mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
-        mbar_init(&tmem_empty[0], 4); mbar_init(&tmem_empty[1], 4);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
+    if (warp == TC_WARP_TMA) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -336,23 +392,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 const int tw = t % p.tilesW; t /= p.tilesW;
                 const int th = t % p.tilesH; t /= p.tilesH;
                 const int w0 = tw * p.BW, h0 = th * p.BH, i0 = t * p.BI;
-                mbar_wait(&empty[stage], phase ^ 1);
-                unsigned char *st = smem + stage * Cfg::STAGE_BYTES;
-                mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                mbar_wait(&sm.empty[stage], phase ^ 1);
+                unsigned char *st = sm.tiles + stage * Cfg::STAGE_BYTES;
+                mbar_expect_tx(&sm.full[stage], Cfg::TX_BYTES);
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb) {
-                    tma_load_4d(st + cb * 4096, &tmX, &full[stage], ci0 + 32 * cb, w0 + s - p.pad, h0 + r - p.pad, i0);
-                    if (PRECISE) tma_load_4d(st + Cfg::A_BYTES + Cfg::B_BYTES + cb * 4096, &tmXlo, &full[stage], ci0 + 32 * cb, w0 + s - p.pad, h0 + r - p.pad, i0);
-                }
+                for (int cb = 0; cb < 4; ++cb)
+                    tma_load_4d(st + cb * 4096, &tmX, &sm.full[stage], ci0 + 32 * cb, (w0 + s - p.pad) * p.stride, (h0 + r - p.pad) * p.stride, i0);
 #pragma unroll
-                for (int nb = 0; nb < BN_TILE / 32; ++nb) {
-                    tma_load_4d(st + Cfg::A_BYTES + nb * 4096, &tmD, &full[stage], n0 + 32 * nb, w0, h0, i0);
-                    if (PRECISE) tma_load_4d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + nb * 4096, &tmDlo, &full[stage], n0 + 32 * nb, w0, h0, i0);
-                }
+                for (int nb = 0; nb < BN_TILE / 32; ++nb)
+                    tma_load_4d(st + Cfg::A_BYTES + nb * 4096, &tmD, &sm.full[stage], n0 + 32 * nb, w0, h0, i0);
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == TC_WARP_MMA) {
         if (lane == 0) {
             // D = F32, A = B = TF32, both MN-major (bits 15, 16), N = BN_TILE, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN_TILE >> 3) << 17) |
@@ -362,17 +414,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int buf = ch & 1;
-                mbar_wait(&tmem_empty[buf], ((ch >> 1) & 1) ^ 1);
+                mbar_wait(&sm.tmem_empty[buf], ((ch >> 1) & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * BN_TILE);
                 const int kend = min(KB, (ch + 1) * Cfg::CHUNK);
                 for (int kb = ch * Cfg::CHUNK; kb < kend; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait(PRECISE ? &sm.conv[stage] : &sm.full[stage], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a = smem_u32(smem + stage * Cfg::STAGE_BYTES), b = a + Cfg::A_BYTES;
+                    const uint32_t a = smem_u32(sm.tiles + stage * Cfg::STAGE_BYTES), b = a + Cfg::A_BYTES;
                     const uint32_t alo = b + Cfg::B_BYTES, blo = alo + Cfg::A_BYTES;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {                            // 32 pixels = 4 atoms of 8
+                    for (int k = 0; k < 4; ++k) {                            // 32 pixels = 4 MMAs of K = 8
                         const uint32_t koff = k * 1024;
                         umma_tf32(tacc, umma_desc_mn(a + koff, p.desc_hi), umma_desc_mn(b + koff, p.desc_hi), idesc, (kb != ch * Cfg::CHUNK) || k != 0);
                         if (PRECISE) {
@@ -380,46 +432,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                             umma_tf32(tacc, umma_desc_mn(a + koff, p.desc_hi), umma_desc_mn(blo + koff, p.desc_hi), idesc, 1);
                         }
                     }
-                    umma_commit(&empty[stage]);
+                    umma_commit(&sm.empty[stage]);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[buf]);
+                umma_commit(&sm.tmem_full[buf]);
             }
         }
+    } else if (warp >= TC_WARP_CVT0) {
+        if (PRECISE) tc_split_loop<Cfg, Cfg::A_BYTES + Cfg::B_BYTES>(sm, KB);
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3, col0 = (warp >> 2) * Cfg::EPI_COLS;
         const int row = q * 32 + lane;                                       // input channel inside the tile
-        float acc[BN_TILE];
-#pragma unroll
-        for (int j = 0; j < BN_TILE; ++j) acc[j] = 0.f;
-        const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int buf = ch & 1;
-            mbar_wait(&tmem_full[buf], (ch >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int c0 = 0; c0 < BN_TILE; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN_TILE + c0), v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
-        }
+        float acc[Cfg::EPI_COLS];
+        tc_drain<Cfg>(sm, tmem_base, KB, q, col0, acc);
         if (KB > 0) {
-            float *dst = p.dw + ((size_t)tap * p.Cin + ci0 + row) * p.Cout + n0;
+            float *dst = p.dw + ((size_t)tap * p.Cin + ci0 + row) * p.Cout + n0 + col0;
 #pragma unroll
-            for (int j = 0; j < BN_TILE; ++j) atomicAdd(dst + j, acc[j]);
+            for (int j = 0; j < Cfg::EPI_COLS; ++j) atomicAdd(dst + j, acc[j]);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
-    }
+    tc_epilogue_end<Cfg>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------- operand preparation
@@ -484,27 +516,29 @@ static EncodeTiledFn get_encode() {
 // caching allocator hands back at the same address with the same geometry: keep a small cache keyed by
 // (base, dims, box).  The descriptor only names the address and the geometry, so a hit is always valid.
 struct MapKey {
-    const void *base; int rank; int swizzle; cuuint64_t d[4]; cuuint32_t b[4];
+    const void *base; int rank; int swizzle; int estride; cuuint64_t d[4]; cuuint32_t b[4];
     bool operator==(const MapKey &o) const {
-        if (base != o.base || rank != o.rank || swizzle != o.swizzle) return false;
+        if (base != o.base || rank != o.rank || swizzle != o.swizzle || estride != o.estride) return false;
         for (int i = 0; i < rank; ++i) if (d[i] != o.d[i] || b[i] != o.b[i]) return false;
         return true;
     }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey &k) const {
-        size_t h = std::hash<const void *>()(k.base) ^ (size_t)(k.rank + 8 * k.swizzle) * 0x9E3779B97F4A7C15ull;
+        size_t h = std::hash<const void *>()(k.base) ^ (size_t)(k.rank + 8 * k.swizzle + 64 * k.estride) * 0x9E3779B97F4A7C15ull;
         for (int i = 0; i < k.rank; ++i) h = h * 1099511628211ull ^ (size_t)k.d[i] * 31 ^ (size_t)k.b[i];
         return h;
     }
 };
 
+// estride: traversal stride of dimensions 1 and 2 (W, H) of a 4-D activation map - 2 for strided 1x1 convolutions (the
+// box then spans 2x the pixels and TMA delivers every other one)
 static int make_map(CUtensorMap *m, const float *base, int rank, const cuuint64_t *dims, const cuuint32_t *box,
-                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, int estride = 1) {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
     MapKey key = {};
-    key.base = base; key.rank = rank; key.swizzle = (int)swizzle;
+    key.base = base; key.rank = rank; key.swizzle = (int)swizzle; key.estride = estride;
     for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
     {
         std::lock_guard<std::mutex> lock(mu);
@@ -516,7 +550,7 @@ static int make_map(CUtensorMap *m, const float *base, int rank, const cuuint64_
     cuuint64_t strides[4];
     cuuint64_t s = sizeof(float);
     for (int i = 0; i < rank - 1; ++i) { s *= dims[i]; strides[i] = s; }
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -530,14 +564,13 @@ static int make_map(CUtensorMap *m, const float *base, int rank, const cuuint64_
 static int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 template <int BN_TILE, bool PRECISE>
-static int launch_tc(const CUtensorMap &a, const CUtensorMap &alo, const CUtensorMap &b, const CUtensorMap &blo, const TcParams &p,
-                     cudaStream_t st) {
+static int launch_tc(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &blo, const TcParams &p, cudaStream_t st) {
     using Cfg = TcCfg<BN_TILE, PRECISE>;
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_TILE, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return (int)e;
     dim3 grid(p.tilesW * p.tilesH * p.tilesI, p.Cout / BN_TILE);
     count_launches(1);
-    conv_tc_kernel<BN_TILE, PRECISE><<<grid, TC_THREADS, Cfg::SMEM, st>>>(a, alo, b, blo, p);
+    conv_tc_kernel<BN_TILE, PRECISE><<<grid, TC_THREADS, Cfg::SMEM, st>>>(a, b, blo, p);
     return (int)cudaGetLastError();
 }
 
@@ -546,14 +579,13 @@ static int launch_tc(const CUtensorMap &a, const CUtensorMap &alo, const CUtenso
 using namespace ttdg;
 
 template <int BN_TILE, bool PRECISE>
-static int launch_wg(const CUtensorMap &x, const CUtensorMap &xlo, const CUtensorMap &d, const CUtensorMap &dlo, const WgParams &p,
-                     cudaStream_t st) {
+static int launch_wg(const CUtensorMap &x, const CUtensorMap &d, const WgParams &p, cudaStream_t st) {
     using Cfg = WgCfg<BN_TILE, PRECISE>;
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN_TILE, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return (int)e;
     dim3 grid((p.Cin / 128) * p.R * p.S, p.Cout / BN_TILE, p.splits);
     count_launches(1);
-    wgrad_tc_kernel<BN_TILE, PRECISE><<<grid, TC_THREADS, Cfg::SMEM, st>>>(x, xlo, d, dlo, p);
+    wgrad_tc_kernel<BN_TILE, PRECISE><<<grid, TC_THREADS, Cfg::SMEM, st>>>(x, d, p);
     return (int)cudaGetLastError();
 }
 
@@ -561,17 +593,18 @@ extern "C" int ttdg_wgrad_tc_supported(int Cin, int Cout, int stride) {
     return (Cin % 128 == 0 && Cout % 64 == 0 && stride == 1) ? 1 : 0;
 }
 
-// dw [R][S][Cin][Cout] += X^T dY on tensor cores (stride-1 convs).  x_*: N x H x W x Cin; dy_*: N x Ho x Wo x Cout;
-// *_lo NULL -> single-pass TF32.  dw is accumulated into (fp32 atomics over the pixel splits).
-extern "C" int ttdg_wgrad_tc(const float *x_hi, const float *x_lo, const float *dy_hi, const float *dy_lo, int N, int H, int W, int Cin,
-                             int Cout, int R, int S, int pad, float *dw, void *stream) {
-    TTDG_CHECK_ARG(x_hi && dy_hi && dw && N >= 0 && (x_lo == nullptr) == (dy_lo == nullptr));
-    if (!ttdg_wgrad_tc_supported(Cin, Cout, 1)) return TTDG_E_LIMIT;
+// dw [R][S][Cin][Cout] += X^T dY on tensor cores (stride-1 convs, and 1x1 stride-2 convs through TMA element strides).  x: N x H x W x Cin; dy: N x Ho x Wo x Cout (fp32);
+// precise != 0 -> 3xTF32 with both operands split inside the pipeline, else single-pass TF32.  dw is accumulated into
+// (fp32 atomics over the pixel splits).
+extern "C" int ttdg_wgrad_tc(const float *x, const float *dy, int precise, int N, int H, int W, int Cin, int Cout, int R, int S,
+                             int stride, int pad, float *dw, void *stream) {
+    TTDG_CHECK_ARG(x && dy && dw && N >= 0);
+    if (!ttdg_wgrad_tc_supported(Cin, Cout, 1) || (stride != 1 && !(stride == 2 && R == 1 && S == 1 && pad == 0))) return TTDG_E_LIMIT;
     if (N == 0) return 0;
-    const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
+    const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
     if (Ho < 1 || Wo < 1) return TTDG_E_ARG;
     WgParams p = {};
-    p.dw = dw; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad = pad;
+    p.dw = dw; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad = pad; p.stride = stride;
     p.BW = pow2_ge(Wo) < 32 ? pow2_ge(Wo) : 32;
     p.BH = pow2_ge(Ho) < 32 / p.BW ? pow2_ge(Ho) : 32 / p.BW;
     p.BI = 32 / (p.BW * p.BH);
@@ -584,21 +617,19 @@ extern "C" int ttdg_wgrad_tc(const float *x_hi, const float *x_lo, const float *
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     p.splits = splits;
-    CUtensorMap mx, mxlo, md, mdlo;
+    p.desc_hi = umma_desc_mn_hi(4096 >> 4, 512 >> 4, 1);
+    CUtensorMap mx, md;
     const cuuint64_t xdims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t ddims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
     const cuuint32_t box[4] = {32, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BI};
+    const cuuint32_t xbox[4] = {32, (cuuint32_t)(p.BW * stride), (cuuint32_t)(p.BH * stride), (cuuint32_t)p.BI};
     const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    p.desc_hi = umma_desc_mn_hi(4096 >> 4, 512 >> 4, 1);
-    int rc = make_map(&mx, x_hi, 4, xdims, box, sw);
-    if (!rc) rc = make_map(&md, dy_hi, 4, ddims, box, sw);
-    if (!rc && x_lo) rc = make_map(&mxlo, x_lo, 4, xdims, box, sw);
-    if (!rc && dy_lo) rc = make_map(&mdlo, dy_lo, 4, ddims, box, sw);
+    int rc = make_map(&mx, x, 4, xdims, xbox, sw, stride);
+    if (!rc) rc = make_map(&md, dy, 4, ddims, box, sw);
     if (rc) return rc;
-    if (!x_lo) { mxlo = mx; mdlo = md; }
     cudaStream_t st = (cudaStream_t)stream;
-    if (x_lo) return bn_tile == 128 ? launch_wg<128, true>(mx, mxlo, md, mdlo, p, st) : launch_wg<64, true>(mx, mxlo, md, mdlo, p, st);
-    return bn_tile == 128 ? launch_wg<128, false>(mx, mxlo, md, mdlo, p, st) : launch_wg<64, false>(mx, mxlo, md, mdlo, p, st);
+    if (precise) return bn_tile == 128 ? launch_wg<128, true>(mx, md, p, st) : launch_wg<64, true>(mx, md, p, st);
+    return bn_tile == 128 ? launch_wg<128, false>(mx, md, p, st) : launch_wg<64, false>(mx, md, p, st);
 }
 
 extern "C" int ttdg_tf32_split(const float *x, float *hi, float *lo, int64_t numel, void *stream) {
@@ -622,19 +653,27 @@ extern "C" int ttdg_conv_tc_supported(int Cin, int Cout, int stride) {
     return (Cin % 32 == 0 && Cout % 64 == 0 && stride == 1) ? 1 : 0;
 }
 
-// x_hi / x_lo: N x H x W x Cin (x_lo NULL = single-pass TF32 on x_hi as is); wk_hi / wk_lo: weights K-major
-// [taps][n][k] - for the forward conv [R*S][Cout][Cin] (ttdg_weight_transpose_split), for the data gradient (flip = 1)
-// the conv's own [R*S][Cin_fwd][Cout_fwd] array with n = Cin_fwd, k = Cout_fwd.  (Cin, Cout) here are the GEMM's k and n.
-extern "C" int ttdg_conv_tc(const float *x_hi, const float *x_lo, const float *wk_hi, const float *wk_lo, const float *scale,
-                            const float *bias, const float *residual, int res_mode, int relu, int flip, int N, int H, int W,
-                            int Cin, int Cout, int R, int S, int pad, float *y, void *stream) {
-    TTDG_CHECK_ARG(x_hi && wk_hi && y && N >= 0 && H > 0 && W > 0 && R > 0 && S > 0 && pad >= 0);
-    TTDG_CHECK_ARG((x_lo == nullptr) == (wk_lo == nullptr) && (res_mode == 0 || residual));
+// x: N x H x W x Cin fp32; wk_hi / wk_lo: weights K-major [taps][n][k], split into tf32 hi / lo - for the forward conv
+// [R*S][Cout][Cin] (ttdg_weight_transpose_split), for the data gradient (flip = 1) the conv's own [R*S][Cin_fwd][Cout_fwd]
+// array with n = Cin_fwd, k = Cout_fwd (ttdg_tf32_split).  (Cin, Cout) here are the GEMM's k and n.  wk_lo == NULL ->
+// single-pass TF32; otherwise 3xTF32 with the activations split inside the pipeline.
+// in_stride = 2 (1x1 convs, pad 0): y[n, ho, wo] = W x[n, 2 ho, 2 wo] (forward of a strided 1x1 conv).  out_stride = 2: the
+// result for (ho, wo) is stored at (2 ho, 2 wo) of an outH x outW map the caller zero-filled (its data gradient).
+extern "C" int ttdg_conv_tc(const float *x, const float *wk_hi, const float *wk_lo, const float *scale, const float *bias,
+                            const float *residual, int res_mode, int relu, int flip, int N, int H, int W, int Cin, int Cout, int R,
+                            int S, int pad, int in_stride, int out_stride, int outH, int outW, float *y, void *stream) {
+    TTDG_CHECK_ARG(x && wk_hi && y && N >= 0 && H > 0 && W > 0 && R > 0 && S > 0 && pad >= 0);
+    TTDG_CHECK_ARG(res_mode == 0 || residual);
+    TTDG_CHECK_ARG((in_stride == 1 || in_stride == 2) && (out_stride == 1 || out_stride == 2));
+    if ((in_stride == 2 || out_stride == 2) && (R != 1 || S != 1 || pad != 0)) return TTDG_E_LIMIT;
     if (!ttdg_conv_tc_supported(Cin, Cout, 1)) return TTDG_E_LIMIT;
     if (N == 0) return 0;
     TcParams p = {};
     p.y = y; p.scale = scale; p.bias = bias; p.residual = residual; p.res_mode = res_mode; p.relu = relu;
-    p.N = N; p.Ho = H + 2 * pad - R + 1; p.Wo = W + 2 * pad - S + 1; p.Cout = Cout;
+    p.N = N; p.Ho = (H + 2 * pad - R) / in_stride + 1; p.Wo = (W + 2 * pad - S) / in_stride + 1; p.Cout = Cout;
+    p.in_stride = in_stride; p.out_stride = out_stride;
+    p.outH = out_stride == 1 ? p.Ho : outH; p.outW = out_stride == 1 ? p.Wo : outW;
+    if (out_stride == 2 && ((p.Ho - 1) * 2 >= outH || (p.Wo - 1) * 2 >= outW)) return TTDG_E_ARG;
     p.R = R; p.S = S; p.pad = pad; p.flip = flip; p.kslabs = Cin / TC_BK;
     if (p.Ho < 1 || p.Wo < 1) return TTDG_E_ARG;
     if (res_mode == 2 && ((p.Ho | p.Wo) & 1)) return TTDG_E_ARG;
@@ -642,19 +681,18 @@ extern "C" int ttdg_conv_tc(const float *x_hi, const float *x_lo, const float *w
     p.BH = pow2_ge(p.Ho) < TC_BM / p.BW ? pow2_ge(p.Ho) : TC_BM / p.BW;
     p.BI = TC_BM / (p.BW * p.BH);
     p.tilesW = ceil_div(p.Wo, p.BW); p.tilesH = ceil_div(p.Ho, p.BH); p.tilesI = ceil_div(N, p.BI);
-    CUtensorMap ma, malo, mb, mblo;
+    CUtensorMap ma, mb, mblo;
     const cuuint64_t adims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    const cuuint32_t abox[4] = {TC_BK, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BI};
+    const cuuint32_t abox[4] = {TC_BK, (cuuint32_t)(p.BW * in_stride), (cuuint32_t)(p.BH * in_stride), (cuuint32_t)p.BI};
     const cuuint64_t bdims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(R * S)};
     const int bn_tile = Cout % 128 == 0 ? 128 : 64;
     const cuuint32_t bbox[3] = {TC_BK, (cuuint32_t)bn_tile, 1};
-    int rc = make_map(&ma, x_hi, 4, adims, abox);
+    int rc = make_map(&ma, x, 4, adims, abox, CU_TENSOR_MAP_SWIZZLE_128B, in_stride);
     if (!rc) rc = make_map(&mb, wk_hi, 3, bdims, bbox);
-    if (!rc && x_lo) rc = make_map(&malo, x_lo, 4, adims, abox);
     if (!rc && wk_lo) rc = make_map(&mblo, wk_lo, 3, bdims, bbox);
     if (rc) return rc;
-    if (!x_lo) { malo = ma; mblo = mb; }
+    if (!wk_lo) mblo = mb;
     cudaStream_t st = (cudaStream_t)stream;
-    if (x_lo) return bn_tile == 128 ? launch_tc<128, true>(ma, malo, mb, mblo, p, st) : launch_tc<64, true>(ma, malo, mb, mblo, p, st);
-    return bn_tile == 128 ? launch_tc<128, false>(ma, malo, mb, mblo, p, st) : launch_tc<64, false>(ma, malo, mb, mblo, p, st);
+    if (wk_lo) return bn_tile == 128 ? launch_tc<128, true>(ma, mb, mblo, p, st) : launch_tc<64, true>(ma, mb, mblo, p, st);
+    return bn_tile == 128 ? launch_tc<128, false>(ma, mb, mblo, p, st) : launch_tc<64, false>(ma, mb, mblo, p, st);
 }

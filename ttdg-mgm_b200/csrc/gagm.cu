@@ -15,6 +15,13 @@
 //   phase 2: T, Q_g = U_g T, V_g = (2 qw A_gg Q_g + W[g,:] U) / G, projector, U_new_g, partial norms | cluster barrier
 // All arithmetic is fp64 (A, W, U0 are fp32 inputs widened exactly): the iteration is a discrete dynamical
 // system that amplifies rounding noise, fp64 makes it independent of summation order.
+//
+// Hungarian stage (200 of the ~213 iterations): U_t is a 0/1 partial permutation, described by node_of[g][u] (the node
+// of graph g sitting in universe slot u, or -1).  Then X_g = A_gg U_g, T and W U are gathers:
+//     T[u1][u2] = sum_h A_hh[node_h(u1)][node_h(u2)]         (every CTA builds the whole T itself: no phase-1 barrier)
+//     Q_g[r][:] = T[slot_g(r)][:],   (W U)[r][u] = sum_h W[r][node_h(u)]
+// and only V1 = A_gg Q_g stays dense: one cluster barrier per iteration, ~1/8 of the FMAs.  Zero terms are skipped in
+// the same order the dense loops add them, so both paths produce the same bits (for G <= 8).
 #include "lap.cuh"
 #include "sinkhorn_small.cuh"
 #include <cooperative_groups.h>
@@ -39,6 +46,7 @@ struct GagmParams {
     double *normpart;    // C x 2
     double *trace;       // optional: (trace_cap + 1) x M x NU, U_t of every iteration (tests)
     double *trace_meta;  // optional: trace_cap x 2 = {projector, tau}
+    int32_t *nodeof;     // 2 x GAGM_MAX_G x NU: node_of of U_t for Hungarian-stage iterations, double-buffered by iteration parity
     int trace_cap;
     int G, M, C;
     double init_tau, min_tau, sk_gamma, tol, quad_weight;
@@ -92,6 +100,8 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
     double *padv = T + NU * NU;                            // GAGM_MAX_N
     double *red = padv + GAGM_MAX_N;                       // 2 * GAGM_WARPS
     LapWork *lapw = reinterpret_cast<LapWork *>(red + 2 * GAGM_WARPS);
+    int *nodeof_s = reinterpret_cast<int *>(lapw + 1);      // G x NU: node_of of every graph (Hungarian stage)
+    int *slot_s = nodeof_s + GAGM_MAX_G * NU;               // GAGM_MAX_N: universe slot of each node of the current graph
 
     const int c = blockIdx.x, C = p.C, G = p.G, M = p.M;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -113,6 +123,7 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
     double tau = p.init_tau;
     int projector = (p.mode == 1) ? p.step_projector : 0;   // 0 sinkhorn, 1 hungarian
     int it_total = 0, it_sk = 0, it_hg = 0, n_lap = 0, n_stage = 0;
+    bool binU = false;                                      // U_t came from a Hungarian projection: node_of[it_total & 1] is valid
 
     while (true) {
         bool stop_all = false;
@@ -122,9 +133,27 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
             const double *Ul2 = p.Ubuf + (size_t)last2 * UB;    // U_{t-1}
             double *Un = p.Ubuf + (size_t)cur * UB;             // U_{t+1}
 
+            const int e0 = 2 * tid, u1 = e0 / NU, u2 = e0 % NU;
+            const int32_t *nodeof_cur = p.nodeof + (size_t)(it_total & 1) * GAGM_MAX_G * NU;
+            int32_t *nodeof_nxt = p.nodeof + (size_t)((it_total + 1) & 1) * GAGM_MAX_G * NU;
+            if (binU) {
+                // ================= Hungarian stage: T from the permutation description, no barrier
+                for (int e = tid; e < G * NU; e += GAGM_THREADS) nodeof_s[e] = __ldcg(nodeof_cur + e);
+                __syncthreads();
+                double t0 = 0.0, t1 = 0.0;
+                for (int h = 0; h < G; ++h) {
+                    const int n1 = nodeof_s[h * NU + u1];
+                    if (n1 >= 0) {
+                        const float *arow = p.A + (size_t)(p.node_off[h] + n1) * M + p.node_off[h];
+                        const int n2 = nodeof_s[h * NU + u2], n3 = nodeof_s[h * NU + u2 + 1];
+                        if (n2 >= 0) t0 += (double)__ldg(arow + n2);
+                        if (n3 >= 0) t1 += (double)__ldg(arow + n3);
+                    }
+                }
+                T[e0] = t0; T[e0 + 1] = t1;
+            } else {
             // ================= phase 1: X_g = A_gg U_g, partial T = sum_g U_g^T X_g
             double t0 = 0.0, t1 = 0.0;
-            const int e0 = 2 * tid, u1 = e0 / NU, u2 = e0 % NU;
             for (int g = c; g < G; g += C) {
                 const int o = p.node_off[g], n = p.node_off[g + 1] - o;
                 for (int e = tid; e < n * NU; e += GAGM_THREADS) Ug[e] = __ldcg(Ul + (size_t)o * NU + e);
@@ -157,9 +186,22 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                 }
                 T[e0] = s0; T[e0 + 1] = s1;
             }
+            }
             double d1 = 0.0, d2 = 0.0;
             for (int g = c; g < G; g += C) {
                 const int o = p.node_off[g], n = p.node_off[g + 1] - o;
+                if (binU) {
+                    for (int r = tid; r < n; r += GAGM_THREADS) slot_s[r] = -1;
+                    __syncthreads();                               // also publishes T
+                    if (tid < NU) { const int nd = nodeof_s[g * NU + tid]; if (nd >= 0) slot_s[nd] = tid; }
+                    __syncthreads();
+                    // Q = U_g T = rows of T picked by the node's slot
+#pragma unroll
+                    for (int r = 0; r < RPW; ++r) {
+                        const int row = warp + GAGM_WARPS * r;
+                        if (row < n) { const int sl = slot_s[row]; X[row * NU + lane] = sl >= 0 ? T[sl * NU + lane] : 0.0; }
+                    }
+                } else {
                 for (int e = tid; e < n * NU; e += GAGM_THREADS) Ug[e] = __ldcg(Ul + (size_t)o * NU + e);
                 __syncthreads();                                   // also publishes T
                 // Q = U_g T
@@ -172,13 +214,29 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                         X[row * NU + lane] = q;
                     }
                 }
+                }
                 __syncthreads();
                 // V1 = A_gg Q
                 double v1[RPW], v2[RPW];
 #pragma unroll
                 for (int r = 0; r < RPW; ++r) { v1[r] = 0.0; v2[r] = 0.0; }
                 rows_times_tile(p.A + (size_t)o * M + o, M, n, n, X, v1, warp, lane);
-                // V2 = W[g rows, :] U   (tile by graph h)
+                // V2 = W[g rows, :] U   (Hungarian stage: one entry of W per graph h; else tile by graph h)
+                if (binU) {
+#pragma unroll
+                    for (int r = 0; r < RPW; ++r) {
+                        const int row = warp + GAGM_WARPS * r;
+                        if (row < n) {
+                            const float *wrow = p.W + (size_t)(o + row) * M;
+                            double acc = 0.0;
+                            for (int h = 0; h < G; ++h) {
+                                const int nd = nodeof_s[h * NU + lane];
+                                if (nd >= 0) acc += (double)__ldg(wrow + p.node_off[h] + nd);
+                            }
+                            v2[r] = acc;
+                        }
+                    }
+                } else
                 for (int h = 0; h < G; ++h) {
                     const int oh = p.node_off[h], nh = p.node_off[h + 1] - oh;
                     const double *Us;
@@ -235,6 +293,11 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                     for (int e = tid; e < n * NU; e += GAGM_THREADS) Ug[e] = (e / NU == e % NU) ? 1.0 : 0.0;
                     __syncthreads();
                 }
+                if (projector == 1 && tid < NU) {                  // node_of of U_{t+1} for the next (Hungarian-stage) iteration
+                    int nd = -1;
+                    for (int r = 0; r < n; ++r) if (Ug[r * NU + tid] != 0.0) nd = r;
+                    nodeof_nxt[g * NU + tid] = nd;
+                }
                 for (int e = tid; e < n * NU; e += GAGM_THREADS) {
                     const double un = Ug[e];
                     const double a = un - __ldcg(Ul + (size_t)o * NU + e);
@@ -265,6 +328,7 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                 p.trace_meta[2 * it_total] = (double)projector; p.trace_meta[2 * it_total + 1] = tau;
             }
             ++it_total;
+            binU = (projector == 1);
             if (projector == 0) ++it_sk; else { ++it_hg; n_lap += G; }
             if (p.mode == 1) { stop_all = true; break; }
             if (sqrt(n1) < p.tol || n2 == 0.0) break;              // mgm:361
@@ -290,7 +354,7 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
 
 static size_t gagm_smem_bytes() {
     return (size_t)(3 * GAGM_MAX_N * NU + GAGM_MAX_N * ZP + NU * NU + GAGM_MAX_N + 2 * GAGM_WARPS) * sizeof(double) +
-           sizeof(LapWork) + 16;
+           sizeof(LapWork) + (size_t)(GAGM_MAX_G * NU + GAGM_MAX_N) * sizeof(int) + 16;
 }
 
 }  // namespace ttdg
@@ -299,7 +363,8 @@ using namespace ttdg;
 
 extern "C" int64_t ttdg_gagm_scratch_bytes(int M, int G) {
     (void)G;
-    return (int64_t)(3 * (int64_t)M * NU + GAGM_MAX_C * NU * NU + 2 * GAGM_MAX_C) * (int64_t)sizeof(double);
+    return (int64_t)(3 * (int64_t)M * NU + GAGM_MAX_C * NU * NU + 2 * GAGM_MAX_C) * (int64_t)sizeof(double) +
+           (int64_t)(2 * GAGM_MAX_G * NU) * (int64_t)sizeof(int32_t);
 }
 
 extern "C" int ttdg_gagm_solve(const float *A, const float *W, const float *U0, const int32_t *ms_h, int G, int M,
@@ -327,6 +392,7 @@ extern "C" int ttdg_gagm_solve(const float *A, const float *W, const float *U0, 
     p.Ubuf = reinterpret_cast<double *>(scratch);
     p.Tpart = p.Ubuf + 3 * (size_t)M * NU;
     p.normpart = p.Tpart + GAGM_MAX_C * NU * NU;
+    p.nodeof = reinterpret_cast<int32_t *>(p.normpart + 2 * GAGM_MAX_C);
     p.init_tau = init_tau; p.min_tau = min_tau; p.sk_gamma = sk_gamma; p.tol = converge_tol; p.quad_weight = quad_weight;
     p.max_iter = max_iter; p.sk_iter = sk_iter; p.mode = mode; p.step_projector = step_projector;
     p.trace = trace; p.trace_meta = trace_meta; p.trace_cap = trace ? trace_cap : 0;

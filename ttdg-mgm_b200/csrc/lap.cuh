@@ -41,27 +41,31 @@ __device__ __forceinline__ double lap_unord(unsigned long long k) {
 // On return w.col4row[i] (i < nr) holds the column assigned to row i.  Must be called by a full warp.
 //
 // Per-column state (shortest, v, path, position in SciPy's `remaining` list, row4col) lives in REGISTERS of the lane
-// that owns the column (j = lane + 32 t); one inner iteration is a few FP64 ops per owned column plus three
-// redux.sync reductions (value high word, value low word, tie key) instead of shuffle butterflies over shared memory.
+// that owns the column (j = lane + 32 t, t < SLOTS = ceil(nc / 32)); one inner iteration is a few FP64 ops per owned
+// column plus three redux.sync reductions (value high word, value low word, winner key) instead of shuffle butterflies
+// over shared memory.
 // SciPy's selection rule "strictly lower, or equal and unassigned" over the scan order it = 0 .. num_remaining-1 picks,
 // among the minima, the LAST unassigned position if any, else the FIRST position; with the tie key
 //     unassigned: 256 + it,   assigned: 255 - it      (maximised)
-// the winner of (value ascending, key descending) is exactly that element.  `remaining` is filled in reverse
+// the winner of (value ascending, key descending) is exactly that element.  The tie key is unique among the remaining
+// columns, so the winner's column index and its row4col ride along in the low bits of the same 32-bit key
+// (tie << 16 | column << 8 | row4col + 1) and one redux.max delivers all three.  `remaining` is filled in reverse
 // (position it holds column nc-1-it) and compacted by moving the last element into the freed position - tracked here
 // as a per-column position register.
-template <class Cost>
-__device__ void lap_solve_warp(int nr, int nc, Cost cost, LapWork &w) {
+template <int SLOTS, class Cost>
+__device__ void lap_solve_warp_t(int nr, int nc, Cost cost, LapWork &w) {
     const int lane = threadIdx.x & 31;
     for (int k = lane; k < nr; k += 32) { w.u[k] = 0.0; w.col4row[k] = -1; }
     for (int k = lane; k < nc; k += 32) { w.v[k] = 0.0; w.row4col[k] = -1; }
     __syncwarp();
     for (int cur = 0; cur < nr; ++cur) {
-        double sh[LAP_SLOTS], vj[LAP_SLOTS];
-        int pos[LAP_SLOTS], r4c[LAP_SLOTS], pth[LAP_SLOTS];
+        double sh[SLOTS], vj[SLOTS];
+        unsigned long long ks[SLOTS];                           // lap_ord(sh[t])
+        int pos[SLOTS], r4c[SLOTS], pth[SLOTS];
 #pragma unroll
-        for (int t = 0; t < LAP_SLOTS; ++t) {
+        for (int t = 0; t < SLOTS; ++t) {
             const int j = lane + 32 * t;
-            sh[t] = INFINITY; pth[t] = -1;
+            sh[t] = INFINITY; ks[t] = lap_ord(INFINITY); pth[t] = -1;
             if (j < nc) { vj[t] = w.v[j]; pos[t] = nc - 1 - j; r4c[t] = w.row4col[j]; }
             else { vj[t] = 0.0; pos[t] = -1; r4c[t] = 0; }
         }
@@ -72,36 +76,30 @@ __device__ void lap_solve_warp(int nr, int nc, Cost cost, LapWork &w) {
             ++nvis;
             const double ui = w.u[i];
             unsigned long long bk = 0xFFFFFFFFFFFFFFFFull;      // lane-local best (ordered value)
-            unsigned bkey = 0;                                  // its tie key
-            int bslot = 0;
+            unsigned bkey = 0;                                  // its winner key
 #pragma unroll
-            for (int t = 0; t < LAP_SLOTS; ++t) {
+            for (int t = 0; t < SLOTS; ++t) {
                 if (pos[t] >= 0) {
                     const double r = ((minVal + cost(i, lane + 32 * t)) - ui) - vj[t];
-                    if (r < sh[t]) { sh[t] = r; pth[t] = i; }
-                    const unsigned long long k = lap_ord(sh[t]);
-                    const unsigned key = (r4c[t] == -1) ? 256u + (unsigned)pos[t] : 255u - (unsigned)pos[t];
-                    if (k < bk || (k == bk && key > bkey)) { bk = k; bkey = key; bslot = t; }
+                    if (r < sh[t]) { sh[t] = r; pth[t] = i; ks[t] = lap_ord(r); }
+                    const unsigned tie = (r4c[t] == -1) ? 256u + (unsigned)pos[t] : 255u - (unsigned)pos[t];
+                    const unsigned key = (tie << 16) | ((unsigned)(lane + 32 * t) << 8) | (unsigned)(r4c[t] + 1);
+                    if (ks[t] < bk || (ks[t] == bk && key > bkey)) { bk = ks[t]; bkey = key; }
                 }
             }
             const unsigned hi = (unsigned)(bk >> 32), lo = (unsigned)bk;
             const unsigned mhi = __reduce_min_sync(TTDG_FULL, hi);
             const unsigned mlo = __reduce_min_sync(TTDG_FULL, hi == mhi ? lo : 0xFFFFFFFFu);
-            const bool cand = (hi == mhi) && (lo == mlo) && (bk != 0xFFFFFFFFFFFFFFFFull);
+            const bool cand = (hi == mhi) && (lo == mlo) && (bkey != 0u);
             const unsigned mkey = __reduce_max_sync(TTDG_FULL, cand ? bkey : 0u);
-            const bool win = cand && (bkey == mkey);
-            const int src = __ffs(__ballot_sync(TTDG_FULL, win)) - 1;
             minVal = lap_unord(((unsigned long long)mhi << 32) | mlo);
-            const int psel = mkey >= 256u ? (int)(mkey - 256u) : (int)(255u - mkey);
-            int jsel = lane + 32 * bslot, rsel = 0;
-#pragma unroll
-            for (int t = 0; t < LAP_SLOTS; ++t) if (t == bslot) rsel = r4c[t];
-            jsel = __shfl_sync(TTDG_FULL, jsel, src);
-            rsel = __shfl_sync(TTDG_FULL, rsel, src);
+            const unsigned mtie = mkey >> 16;
+            const int psel = mtie >= 256u ? (int)(mtie - 256u) : (int)(255u - mtie);
+            const int jsel = (int)((mkey >> 8) & 0xFFu), rsel = (int)(mkey & 0xFFu) - 1;
             if (rsel == -1) sink = jsel; else i = rsel;
             const int last = num_remaining - 1;
 #pragma unroll
-            for (int t = 0; t < LAP_SLOTS; ++t) {
+            for (int t = 0; t < SLOTS; ++t) {
                 const int j = lane + 32 * t;
                 if (j == jsel) {                                  // scanned: SC[j] = true, leaves `remaining`
                     w.shortest[j] = sh[t]; w.path[j] = pth[t]; pos[t] = -2;
@@ -117,7 +115,7 @@ __device__ void lap_solve_warp(int nr, int nc, Cost cost, LapWork &w) {
             else w.u[r] += minVal - w.shortest[w.col4row[r]];
         }
 #pragma unroll
-        for (int t = 0; t < LAP_SLOTS; ++t)
+        for (int t = 0; t < SLOTS; ++t)
             if (pos[t] == -2) w.v[lane + 32 * t] = vj[t] - (minVal - sh[t]);
         __syncwarp();
         // augment along the path (sequential, short)
@@ -134,6 +132,13 @@ __device__ void lap_solve_warp(int nr, int nc, Cost cost, LapWork &w) {
         }
         __syncwarp();
     }
+}
+
+template <class Cost>
+__device__ __forceinline__ void lap_solve_warp(int nr, int nc, Cost cost, LapWork &w) {
+    if (nc <= 32) lap_solve_warp_t<1>(nr, nc, cost, w);
+    else if (nc <= 64) lap_solve_warp_t<2>(nr, nc, cost, w);
+    else lap_solve_warp_t<LAP_SLOTS>(nr, nc, cost, w);
 }
 
 // hungarian(s) for one stored n1 x n2 fp32 score matrix (leading dimension ld): perm = 0/1 matrix of the

@@ -50,9 +50,9 @@ SIGNATURES = {
     "ttdg_resample2": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "ttdg_preprocess": (c_int, [P, c_int, c_int, c_int, c_float, c_float, c_float, P, P]),
     "ttdg_conv_tc_supported": (c_int, [c_int, c_int, c_int]),
-    "ttdg_conv_tc": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "ttdg_conv_tc": (c_int, [P, P, P, P, P, P] + [c_int] * 15 + [P, P]),
     "ttdg_wgrad_tc_supported": (c_int, [c_int, c_int, c_int]),
-    "ttdg_wgrad_tc": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "ttdg_wgrad_tc": (c_int, [P, P] + [c_int] * 10 + [P, P]),
     "ttdg_tf32_split": (c_int, [P, P, P, c_int64, P]),
     "ttdg_weight_transpose_split": (c_int, [P, c_int, c_int, c_int, P, P, P]),
     "ttdg_rpn_decode": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_float, c_float, P, P, P]),

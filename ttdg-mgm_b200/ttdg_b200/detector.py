@@ -36,6 +36,7 @@ def _pad4(c):
 CONV_MODE = [os.environ.get("TTDG_CONV", "tf32x3")]
 PARAM_EPOCH = [0]              # bumped by FlatSGD.step: invalidates the K-major weight copies below
 WGRAD_TC = [os.environ.get("TTDG_WGRAD_TC", "1") == "1"]       # weight gradients on tensor cores (MN-major operands)
+TC_STRIDE2 = [os.environ.get("TTDG_TC_STRIDE2", "1") == "1"]   # 1x1 stride-2 convs on tensor cores (TMA element strides)
 
 
 def set_conv_mode(mode):
@@ -74,8 +75,11 @@ def _weights_kmajor(w, transposed, precise, owner=None):
     return hi, lo
 
 
-def _tc_ok(Cin, Cout, stride):
-    return CONV_MODE[0] != "simt" and stride == 1 and Cin % 32 == 0 and Cout % 64 == 0
+def _tc_ok(Cin, Cout, stride, R=1, pad=0):
+    """Tensor-core kernel coverage: stride 1, or the strided 1x1 convs (TMA element strides)."""
+    if CONV_MODE[0] == "simt" or Cin % 32 or Cout % 64:
+        return False
+    return stride == 1 or (stride == 2 and R == 1 and pad == 0 and TC_STRIDE2[0])
 
 
 # ---------------------------------------------------------------------------------------------- raw op wrappers
@@ -85,12 +89,11 @@ def conv_forward(x, w, scale, bias, residual, res_mode, relu, R, S, stride, pad,
     Cout = w.shape[-1]
     Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
     y = torch.empty(N, Ho, Wo, Cout, dtype=torch.float32, device=x.device) if out is None else out
-    if _tc_ok(Cin, Cout, stride):
+    if _tc_ok(Cin, Cout, stride, R, pad):
         precise = CONV_MODE[0] == "tf32x3"
         w_hi, w_lo = _weights_kmajor(w, True, precise, owner)
-        x_hi, x_lo = tf32_split(x) if precise else (x, None)
-        check(_C.lib().ttdg_conv_tc(_p(x_hi), _p(x_lo), _p(w_hi), _p(w_lo), _p(scale), _p(bias), _p(residual), int(res_mode), int(relu),
-                                    0, N, H, W, Cin, Cout, R, S, pad, _p(y), _stream()), "conv_tc")
+        check(_C.lib().ttdg_conv_tc(_p(x), _p(w_hi), _p(w_lo), _p(scale), _p(bias), _p(residual), int(res_mode), int(relu),
+                                    0, N, H, W, Cin, Cout, R, S, pad, stride, 1, 0, 0, _p(y), _stream()), "conv_tc")
         return y
     check(_C.lib().ttdg_conv_fwd(_p(x), _p(w), _p(scale), _p(bias), _p(residual), int(res_mode), int(relu), N, H, W, Cin, Cout, R, S,
                                  stride, pad, _p(y), _stream()), "conv_fwd")
@@ -140,28 +143,21 @@ class _ConvFn(torch.autograd.Function):
             check(L.ttdg_relu_bn_bwd(_p(d_pre), None, _p(scale), Cout, d_pre.numel(), _p(d_conv), s), "bn_bwd")
         else:
             d_conv = d_pre
-        g_x = g_w = d_hi = d_lo = None
+        g_x = g_w = None
         if ctx.needs_input_grad[0]:
             g_x = (torch.zeros if stride == 2 else torch.empty)(N, H, W, Cin, dtype=torch.float32, device=g.device)
-            if _tc_ok(Cout, Cin, stride):                  # GEMM k = Cout, n = Cin; taps mirrored, pad' = R - 1 - pad
-                precise = CONV_MODE[0] == "tf32x3"
+            if _tc_ok(Cout, Cin, stride, R, pad):          # GEMM k = Cout, n = Cin; taps mirrored, pad' = R - 1 - pad
+                precise = CONV_MODE[0] == "tf32x3"         # (stride 2, 1x1: results land on the even pixels of the zeroed g_x)
                 w_hi, w_lo = _weights_kmajor(w, False, precise, ctx.owner)
-                d_hi, d_lo = tf32_split(d_conv) if precise else (d_conv, None)
-                check(L.ttdg_conv_tc(_p(d_hi), _p(d_lo), _p(w_hi), _p(w_lo), None, None, None, 0, 0, 1, N, g.shape[1], g.shape[2], Cout,
-                                     Cin, R, S, R - 1 - pad, _p(g_x), s), "conv_tc_dgrad")
+                check(L.ttdg_conv_tc(_p(d_conv), _p(w_hi), _p(w_lo), None, None, None, 0, 0, 1, N, g.shape[1], g.shape[2], Cout,
+                                     Cin, R, S, R - 1 - pad, 1, stride, H, W, _p(g_x), s), "conv_tc_dgrad")
             else:
                 check(L.ttdg_conv_dgrad(_p(d_conv), _p(w), N, H, W, Cin, Cout, R, S, stride, pad, _p(g_x), s), "conv_dgrad")
         if ctx.needs_input_grad[1]:
             g_w = torch.zeros_like(w)
-            if CONV_MODE[0] != "simt" and WGRAD_TC[0] and stride == 1 and Cin % 128 == 0 and Cout % 64 == 0:
-                precise = CONV_MODE[0] == "tf32x3"
-                if precise:
-                    x_hi, x_lo = tf32_split(x)
-                    if d_hi is None:
-                        d_hi, d_lo = tf32_split(d_conv)
-                else:
-                    x_hi, x_lo, d_hi, d_lo = x, None, d_conv, None
-                check(L.ttdg_wgrad_tc(_p(x_hi), _p(x_lo), _p(d_hi), _p(d_lo), N, H, W, Cin, Cout, R, S, pad, _p(g_w), s), "wgrad_tc")
+            if WGRAD_TC[0] and Cin % 128 == 0 and _tc_ok(Cin, Cout, stride, R, pad):
+                check(L.ttdg_wgrad_tc(_p(x), _p(d_conv), int(CONV_MODE[0] == "tf32x3"), N, H, W, Cin, Cout, R, S, stride, pad, _p(g_w), s),
+                      "wgrad_tc")
             else:
                 check(L.ttdg_conv_wgrad(_p(x), _p(d_conv), N, H, W, Cin, Cout, R, S, stride, pad, _p(g_w), s), "conv_wgrad")
         return g_x, g_w, g_bias, g_res, None, None, None, None, None, None, None, None, None
