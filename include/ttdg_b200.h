@@ -233,9 +233,10 @@ int ttdg_maxpool3x3s2(const float *x, int N, int H, int W, int C, float *y, void
 /* mode 0: y[small] = x[big at even pixels] (p6 = max_pool2d(p5, 1, 2)); 1: y[big even] += x[small] (its backward);
  * 2: y[small] += sum of 2x2 children of x[big] (backward of the FPN nearest upsample).  Hs x Ws = small grid. */
 int ttdg_resample2(const float *x, float *y, int N, int Hs, int Ws, int C, int mode, void *stream);
-/* uint8 N x 3 x H x W planar -> fp32 NHWC with 4 channels (4th = 0), minus PIXEL_MEAN (d2 preprocess_image). */
-int ttdg_preprocess(const unsigned char *img_u8, int N, int H, int W, float mean0, float mean1, float mean2, float *out,
-                    void *stream);
+/* uint8 N x 3 x H x W planar -> fp32 NHWC with 4 channels (4th = 0), minus PIXEL_MEAN (d2 preprocess_image).  Output rows
+ * hold Wp >= left + W pixels: `left` zero pixels, the image, zeros up to Wp (left = 0, Wp = W: plain layout). */
+int ttdg_preprocess(const unsigned char *img_u8, int N, int H, int W, int Wp, int left, float mean0, float mean1, float mean2,
+                    float *out, void *stream);
 
 /* Tensor-core version of ttdg_conv_fwd / stride-1 ttdg_conv_dgrad: tcgen05.mma.kind::tf32 fed by TMA (activations as a 4-D
  * NHWC tensor map - filter taps are coordinate shifts, padding is TMA's out-of-bounds zero fill), fp32 accumulators in
@@ -264,6 +265,12 @@ int ttdg_conv_tc(const float *x, const float *wk_hi, const float *wk_lo, const f
 int ttdg_wgrad_tc_supported(int Cin, int Cout, int stride);
 int ttdg_wgrad_tc(const float *x, const float *dy, int precise, int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
                   int pad, float *dw, void *stream);
+/* d2 BasicStem (7x7 stride 2 pad 3, 3 -> 64, FrozenBN, ReLU) on tensor cores from the padded image of ttdg_preprocess
+ * (left = 3, Wp >= W + 8): the 28 floats of one filter row are a contiguous window, read as overlapping TMA boxes.
+ * wk_hi / wk_lo [7][64][32]: wk[r][co][4 s + c] = w[r][s][c][co], zero for s = 7 (wk_lo NULL = single-pass TF32).
+ * y: N x H/2 x W/2 x 64; H, W even. */
+int ttdg_stem_tc(const float *x_pad, int Wp, const float *wk_hi, const float *wk_lo, const float *scale, const float *bias,
+                 int relu, int N, int H, int W, float *y, void *stream);
 int ttdg_tf32_split(const float *x, float *hi, float *lo, int64_t numel, void *stream);
 /* w [taps][Cin][Cout] -> wt_hi, wt_lo (may be NULL) [taps][Cout][Cin] */
 int ttdg_weight_transpose_split(const float *w, int taps, int Cin, int Cout, float *wt_hi, float *wt_lo, void *stream);

@@ -205,3 +205,32 @@ def test_conv_tc_stride2_1x1(mode, rtol, cin, cout, H, W, N):
     ys = layer(xs)
     (ys * nhwc(up).cuda()).sum().backward()
     assert rel(ys.detach(), yc.detach()) < rtol and rel(xs.grad, xc.grad) < rtol
+
+
+@pytest.mark.parametrize("mode,rtol", [("tf32x3", 1e-5), ("tf32", 6e-3)])
+@pytest.mark.parametrize("N,H,W", [(2, 64, 96), (1, 512, 512), (3, 40, 24)])
+def test_stem_tc(mode, rtol, N, H, W):
+    """d2 BasicStem (7x7 stride 2 pad 3 + FrozenBN + ReLU) on tensor cores from the padded image (overlapping 8-pixel TMA
+    windows) against torch and against the CUDA-core path; H, W not multiples of 32 exercise size_divisibility padding."""
+    det.set_conv_mode(mode)
+    g = torch.Generator().manual_seed(H + W)
+    stem = det.Stem().cuda()
+    w = torch.randn(64, 3, 7, 7, generator=g) / 147 ** 0.5
+    sd = {"conv1.weight": w, "conv1.norm.weight": torch.rand(64, generator=g) + 0.5, "conv1.norm.bias": torch.randn(64, generator=g) * 0.1,
+          "conv1.norm.running_mean": torch.randn(64, generator=g) * 0.1, "conv1.norm.running_var": torch.rand(64, generator=g) + 0.5}
+    stem.load_state_dict(sd)
+    ims = [torch.randint(0, 256, (3, H, W), generator=g, dtype=torch.uint8) for _ in range(N)]
+    xp, width = det.preprocess(ims, torch.device("cuda"), stem_padded=True)
+    H32, W32 = (H + 31) // 32 * 32, (W + 31) // 32 * 32
+    assert width == W32 and tuple(xp.shape) == (N, H32, W32 + 8, 4)
+    y = stem(xp, width)
+    x = torch.stack(ims).float() - torch.tensor(det.PIXEL_MEAN).view(1, 3, 1, 1)
+    x = F.pad(x, (0, W32 - W, 0, H32 - H))
+    scale = sd["conv1.norm.weight"] * (sd["conv1.norm.running_var"] + 1e-5).rsqrt()
+    bias = sd["conv1.norm.bias"] - sd["conv1.norm.running_mean"] * scale
+    ref = F.relu(F.conv2d(x, w, None, 2, 3) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
+    assert tuple(y.shape) == (N, H32 // 2, W32 // 2, 64)
+    assert float((nchw(y.cpu()) - ref).abs().max() / ref.abs().max()) < rtol
+    det.set_conv_mode("simt")
+    y2 = stem(det.preprocess(ims, torch.device("cuda")))
+    assert float((y2 - y).abs().max() / ref.abs().max()) < rtol

@@ -186,11 +186,13 @@ def test_residual_stage_backward_vs_oracle(model_and_sd, conv_mode, stage, block
                 assert rel2(gr, sdg[f"{q}{b}.{name}.weight"].grad) < tol, (b, name)
 
 
-def test_backbone_backward_vs_oracle(model_and_sd):
+def test_backbone_backward_vs_oracle(model_and_sd, conv_mode):
     """Gradients of a random linear functional of the pyramid w.r.t. the adapted parameters (res3-res5, FPN) on real
     synthetic images.  Loose by necessity: with FrozenBN-centred pre-activations a ~1e-5 forward difference flips a few
     ReLU masks, and the ORACLE's own gradients move by up to 30 % (max norm) / 5 % (L2) under a 1e-5 perturbation of
-    res2 (measured); the tight check is test_residual_stage_backward_vs_oracle."""
+    res2 (measured); the tight check is test_residual_stage_backward_vs_oracle.  In the 3xTF32 mode the frozen stem and
+    res2 run on tensor cores too (2e-6 per layer instead of 1e-6), which is that perturbation: the bound is the oracle's
+    own 5 % sensitivity there."""
     m, sd = model_and_sd
     ims = _images(2, 128)
     g = torch.Generator().manual_seed(9)
@@ -213,7 +215,8 @@ def test_backbone_backward_vs_oracle(model_and_sd):
         gr = gr[:, :, :layer.cin, :layer.cout].permute(3, 2, 0, 1) if kind == "weight" else gr[:layer.cout]
         r = sdg[name].grad
         errs.append(float((gr.cpu() - r).norm() / r.norm()))
-    assert len(errs) == 58 and max(errs) < 0.15 and float(np.median(errs)) < 0.03, (max(errs), float(np.median(errs)))
+    assert len(errs) == 58 and max(errs) < 0.15 and float(np.median(errs)) < (0.03 if conv_mode == "simt" else 0.06), \
+        (max(errs), float(np.median(errs)))
     # the FPN parameters sit above every ReLU of the loss graph: tight
     for name in ("backbone.fpn_output2.weight", "backbone.fpn_output5.bias"):
         mod_name, kind = name.rsplit(".", 1)
@@ -250,13 +253,14 @@ def test_inference_vs_oracle(model_and_sd, conv_mode, size, polyp):
         pb, rb = props[n][0].cpu(), rprops[n][0]
         assert abs(len(pb) - len(rb)) <= 5
         _, ok = _match(pb, rb, 0.05)
-        assert ok.float().mean() > 0.97, ok.float().mean()
+        # 3xTF32 objectness logits differ by ~2e-6 from the oracle's: a few more top-k / NMS flips than exact fp32 products
+        assert ok.float().mean() > (0.97 if conv_mode == "simt" else 0.93), ok.float().mean()
         a, b = res[n], ref[n]
         assert len(a["scores"]) == len(b["scores"]) == 100
         idx, ok = _match(a["pred_boxes"].cpu(), b["pred_boxes"], 0.1)
         ok = ok & (a["pred_classes"].cpu() == b["pred_classes"][idx])
         assert ok.float().mean() >= 0.95, ok.float().mean()
-        np.testing.assert_allclose(a["scores"].cpu()[ok].numpy(), b["scores"][idx][ok].numpy(), atol=5e-4)
+        np.testing.assert_allclose(a["scores"].cpu()[ok].numpy(), b["scores"][idx][ok].numpy(), atol=5e-4 if conv_mode == "simt" else 1e-3)
         iou = _iou(a["pred_masks"].cpu()[ok], b["pred_masks"][idx][ok])
         # matched boxes differ by up to ~0.05 px (box deltas come out of a K = 12544 FC), which moves a few boundary pixels
         if conv_mode == "simt":      # exact-fp32 products: the pipeline semantics, tight

@@ -114,3 +114,40 @@ def test_baseline_trainer_test_end_to_end():
     assert opt.steps == 2 and not torch.equal(w0, opt.flat_p)
     for k in ("Dice Coefficient", "Enhanced Alignment Metric", "Structural Similarity Metric"):
         assert 0.0 <= res["REFUGE_test"][k] <= 100.0 and np.isfinite(res["REFUGE_mean"][k])
+
+
+def test_config3_polyp_384_test_batch_5():
+    """BASELINE.json configs[3] on one rank: 8 synthetic 384x384 1-class polyp-like images with TEST.BATCH = 5
+    (drop_last False, data/build.py:146) -> one 5-graph and one 3-graph matching problem per pass over the shard, then the
+    eval pass with the adapted weights.  The matching stage of the 5-graph problem is checked against the oracle port
+    (differentiable half with the CUDA path's U; solver trajectory step by step)."""
+    from adapteacher.config import add_ateacher_config
+    from adapteacher.engine.trainer import BaselineTrainer
+    m = build(num_classes=1)
+    opt = FlatSGD(m.adapted_parameters(), lr=0.005, momentum=0.9, weight_decay=1e-4)
+    size = 384
+    ims = [synth.fundus_like_image(500 + i, size, polyp=True) for i in range(8)]
+    inputs = [{"image": im["image"], "height": size, "width": size, "image_id": i} for i, im in enumerate(ims)]
+    # the 5-graph problem on its own first (same weights as the trainer run will see)
+    m.train()
+    loss, _, _, feats = m(inputs[:5], branch="TTT")
+    assert loss is not None and torch.isfinite(loss)
+    assert [tuple(f.shape[-2:]) for f in feats] == [(size // s, size // s) for s in (4, 8, 16, 32, 64)]
+    aux = m.multi_matching_unsup.last_aux
+    sizes = aux["sizes"]
+    assert len(sizes) == 5 and all(1 <= n <= 95 for n in sizes)
+    U2, info, trace, meta = ops.gagm_solve(aux["A"], aux["Wds"], aux["U0"], sizes, trace_cap=1300)
+    assert torch.equal(U2, aux["U"])
+    verify_trajectory(aux["A"].cpu(), aux["Wds"].cpu(), aux["U0"].cpu(), sizes, trace, meta, info.cpu().tolist())
+    dicts = [{"image_id": i, "annotations": [{"category_id": int(c), "mask": mk.numpy()} for c, mk in zip(im["gt_classes"], im["gt_masks"])]}
+             for i, im in enumerate(ims)]
+    cfg = add_ateacher_config()
+    cfg.DATASETS.TEST = ("Polyp_test",)
+    cfg.TEST.BATCH, cfg.TEST.DICE_THRES = 5, 0.0
+    seen = []
+    hook = m.multi_matching_unsup.register_forward_hook(lambda mod, a, o: seen.append(len(mod.last_aux["sizes"])))
+    res = BaselineTrainer.test(cfg, m, opt, data_loaders={"Polyp_test": [inputs[:5], inputs[5:]]}, dataset_dicts={"Polyp_test": dicts})
+    hook.remove()
+    assert seen == [5, 3] and opt.steps == 2
+    for k in ("Dice Coefficient", "Enhanced Alignment Metric", "Structural Similarity Metric"):
+        assert 0.0 <= res["Polyp_test"][k] <= 100.0

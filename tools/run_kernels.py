@@ -59,8 +59,7 @@ elif what == "timing":
     for it in range(reps + 2):
         m.train()
         t0 = ev()
-        x = __import__("ttdg_b200.detector", fromlist=["preprocess"]).preprocess(images, dev)
-        feats = det.backbone(x); t1 = ev()
+        feats = det.features(images); t1 = ev()
         props = det.proposal_generator(feats, (512, 512), training=True); t2 = ev()
         dets = det.roi_heads.forward_box(feats, props, (512, 512)); t3 = ev()
         insts = [Instances((512, 512), pred_boxes=Boxes(b), scores=s, pred_classes=c) for b, s, c in dets]
@@ -69,13 +68,19 @@ elif what == "timing":
         opt.zero_grad(); loss.backward(); t6 = ev()
         opt.step(1); t7 = ev()
         m.eval()
-        out = m(inputs); t8 = ev()
+        with torch.no_grad():                                    # = m(inputs), stage by stage
+            e_feats = det.features(images); t8 = ev()
+            e_props = det.proposal_generator(e_feats, (512, 512), training=False); t9 = ev()
+            e_dets = det.roi_heads.forward_box(e_feats, e_props, (512, 512)); t10 = ev()
+            out = det.roi_heads.forward_mask(e_feats, e_dets, (512, 512), (512, 512)); t11 = ev()
         torch.cuda.synchronize()
         if it >= 2:
             for k, a, b in (("backbone_fwd", t0, t1), ("rpn", t1, t2), ("box_head", t2, t3), ("sampler", t3, t4), ("mgm_fwd", t4, t5),
-                            ("backward", t5, t6), ("sgd", t6, t7), ("eval_pass", t7, t8), ("TOTAL", t0, t8)):
+                            ("backward", t5, t6), ("sgd", t6, t7), ("eval_backbone", t7, t8), ("eval_rpn", t8, t9), ("eval_box", t9, t10),
+                            ("eval_mask", t10, t11), ("TOTAL", t0, t11)):
                 acc[k] += a.elapsed_time(b) / reps
-    print({k: round(v, 2) for k, v in acc.items()}, "gagm iters", int(m.multi_matching_unsup.last_aux["info"][0]))
+    info = m.multi_matching_unsup.last_aux["info"].tolist()
+    print({k: round(v, 2) for k, v in acc.items()}, "gagm iters", info[0], "graph-0 LAP steps", info[5], "hops", info[6])
 elif what == "busy":
     # hot (not cold-cache) per-kernel device time of the full step and the GPU-busy fraction, from CUPTI via torch.profiler
     sys.path.insert(0, ROOT)

@@ -328,15 +328,22 @@ resample2_kernel(const float *__restrict__ x, float *__restrict__ y, int N, int 
     }
 }
 
-// uint8 N x 3 x H x W (planar, as the dataset mapper delivers) -> fp32 NHWC padded to 4 channels, minus the pixel mean
+// uint8 N x 3 x H x W (planar, as the dataset mapper delivers) -> fp32 NHWC padded to 4 channels, minus the pixel mean.
+// The output rows hold Wp >= left + W pixels: `left` zero pixels, the image, zeros up to Wp (the zero padding of the
+// stem convolution materialised, so that the tensor-core stem can read 8-pixel windows as plain TMA boxes).
 __global__ void __launch_bounds__(256)
-preprocess_kernel(const unsigned char *__restrict__ img, int N, int H, int W, float m0, float m1, float m2, float *__restrict__ out) {
-    const int64_t total = (int64_t)N * H * W;
+preprocess_kernel(const unsigned char *__restrict__ img, int N, int H, int W, int Wp, int left, float m0, float m1, float m2,
+                  float *__restrict__ out) {
+    const int64_t total = (int64_t)N * H * Wp;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-        const int64_t n = i / ((int64_t)H * W), pix = i - n * H * W;
-        const unsigned char *b = img + n * 3 * H * W + pix;
-        float4 v;
-        v.x = (float)b[0] - m0; v.y = (float)b[(int64_t)H * W] - m1; v.z = (float)b[2 * (int64_t)H * W] - m2; v.w = 0.f;
+        const int64_t row = i / Wp;                       // n * H + h
+        const int col = (int)(i - row * Wp) - left;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col >= 0 && col < W) {
+            const int64_t n = row / H, h = row - n * H;
+            const unsigned char *b = img + n * 3 * H * W + h * W + col;
+            v.x = (float)b[0] - m0; v.y = (float)b[(int64_t)H * W] - m1; v.z = (float)b[2 * (int64_t)H * W] - m2;
+        }
         reinterpret_cast<float4 *>(out)[i] = v;
     }
 }
@@ -457,13 +464,13 @@ extern "C" int ttdg_resample2(const float *x, float *y, int N, int Hs, int Ws, i
     TTDG_LAUNCH_RET();
 }
 
-extern "C" int ttdg_preprocess(const unsigned char *img_u8, int N, int H, int W, float mean0, float mean1, float mean2, float *out,
-                               void *stream) {
-    TTDG_CHECK_ARG(img_u8 && out && N >= 0 && H > 0 && W > 0);
+extern "C" int ttdg_preprocess(const unsigned char *img_u8, int N, int H, int W, int Wp, int left, float mean0, float mean1, float mean2,
+                               float *out, void *stream) {
+    TTDG_CHECK_ARG(img_u8 && out && N >= 0 && H > 0 && W > 0 && left >= 0 && Wp >= left + W);
     if (N == 0) return 0;
-    int64_t nb = ((int64_t)N * H * W + 255) / 256;
+    int64_t nb = ((int64_t)N * H * Wp + 255) / 256;
     if (nb > 148 * 8) nb = 148 * 8;
     count_launches(1);
-    preprocess_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(img_u8, N, H, W, mean0, mean1, mean2, out);
+    preprocess_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(img_u8, N, H, W, Wp, left, mean0, mean1, mean2, out);
     TTDG_LAUNCH_RET();
 }

@@ -41,6 +41,7 @@ struct TcParams {
     int kslabs;                      // Cin / 32
     int res_mode, relu;
     int in_stride;                   // 1, or 2 for a strided 1x1 conv: the tensor map has element strides {1, 2, 2, 1}
+    int stem;                        // 7x7 stride-2 stem on the padded image: k-block r = filter row, box = 8-pixel windows
     int out_stride, outH, outW;      // output pixel (ho, wo) is stored at (ho, wo) * out_stride of an outH x outW map
 };
 
@@ -253,7 +254,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&sm.empty[stage], phase ^ 1);
                 unsigned char *st = sm.tiles + stage * Cfg::STAGE_BYTES;
                 mbar_expect_tx(&sm.full[stage], Cfg::TX_BYTES);
-                tma_load_4d(st, &tmA, &sm.full[stage], c0, (w0 + s - p.pad) * p.in_stride, (h0 + r - p.pad) * p.in_stride, i0);
+                if (p.stem) tma_load_4d(st, &tmA, &sm.full[stage], 0, w0, 2 * h0 + r - 3, i0);
+                else tma_load_4d(st, &tmA, &sm.full[stage], c0, (w0 + s - p.pad) * p.in_stride, (h0 + r - p.pad) * p.in_stride, i0);
                 tma_load_3d(st + Cfg::A_BYTES, &tmB, &sm.full[stage], c0, n0, btap);
                 if (PRECISE) tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tmBlo, &sm.full[stage], c0, n0, btap);
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -516,10 +518,11 @@ static EncodeTiledFn get_encode() {
 // caching allocator hands back at the same address with the same geometry: keep a small cache keyed by
 // (base, dims, box).  The descriptor only names the address and the geometry, so a hit is always valid.
 struct MapKey {
-    const void *base; int rank; int swizzle; int estride; cuuint64_t d[4]; cuuint32_t b[4];
+    const void *base; int rank; int swizzle; int estride; cuuint64_t d[4]; cuuint32_t b[4]; cuuint64_t st[3];
     bool operator==(const MapKey &o) const {
         if (base != o.base || rank != o.rank || swizzle != o.swizzle || estride != o.estride) return false;
         for (int i = 0; i < rank; ++i) if (d[i] != o.d[i] || b[i] != o.b[i]) return false;
+        for (int i = 0; i < rank - 1; ++i) if (st[i] != o.st[i]) return false;
         return true;
     }
 };
@@ -534,12 +537,16 @@ struct MapKeyHash {
 // estride: traversal stride of dimensions 1 and 2 (W, H) of a 4-D activation map - 2 for strided 1x1 convolutions (the
 // box then spans 2x the pixels and TMA delivers every other one)
 static int make_map(CUtensorMap *m, const float *base, int rank, const cuuint64_t *dims, const cuuint32_t *box,
-                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, int estride = 1) {
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, int estride = 1, const cuuint64_t *strides_in = nullptr) {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
     MapKey key = {};
+    cuuint64_t strides[4];
+    if (strides_in) for (int i = 0; i < rank - 1; ++i) strides[i] = strides_in[i];
+    else { cuuint64_t sb = sizeof(float); for (int i = 0; i < rank - 1; ++i) { sb *= dims[i]; strides[i] = sb; } }
     key.base = base; key.rank = rank; key.swizzle = (int)swizzle; key.estride = estride;
     for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
+    for (int i = 0; i < rank - 1; ++i) key.st[i] = strides[i];
     {
         std::lock_guard<std::mutex> lock(mu);
         auto it = cache.find(key);
@@ -547,10 +554,8 @@ static int make_map(CUtensorMap *m, const float *base, int rank, const cuuint64_
     }
     EncodeTiledFn enc = get_encode();
     if (!enc) return TTDG_E_LIMIT;
-    cuuint64_t strides[4];
-    cuuint64_t s = sizeof(float);
-    for (int i = 0; i < rank - 1; ++i) { s *= dims[i]; strides[i] = s; }
-    cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+    // estride > 0: W and H strided (1x1 stride-2 convs); estride = -2: H only (stem: W is already a stride-2 window index)
+    cuuint32_t estr[4] = {1, (cuuint32_t)(estride > 0 ? estride : 1), (cuuint32_t)(estride > 0 ? estride : -estride), 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -630,6 +635,42 @@ extern "C" int ttdg_wgrad_tc(const float *x, const float *dy, int precise, int N
     cudaStream_t st = (cudaStream_t)stream;
     if (precise) return bn_tile == 128 ? launch_wg<128, true>(mx, md, p, st) : launch_wg<64, true>(mx, md, p, st);
     return bn_tile == 128 ? launch_wg<128, false>(mx, md, p, st) : launch_wg<64, false>(mx, md, p, st);
+}
+
+// Stem (7x7, stride 2, pad 3, 3 -> 64 channels + FrozenBN + ReLU; d2 BasicStem, configs/Base-RCNN-FPN.yaml:3-8) on tensor
+// cores.  x_pad: N x H x Wp x 4 fp32 with 3 zero pixels left of the image and >= 5 right (ttdg_preprocess with left = 3,
+// Wp >= W + 8).  The 7 taps of one filter row over 4 channels are 28 contiguous floats of that row, so the GEMM k-block
+// of filter row r is a 32-float window (8 pixels, the 8th with zero weights) starting at pixel 2 wo of row 2 ho + r - 3:
+// a tensor map whose dimension 1 is the OUTPUT column with a 32-byte stride (overlapping windows), dimension 2 the input
+// row with element stride 2 (rows outside the image are TMA zero fill).  wk_hi / wk_lo: [7][64][32] with
+// wk[r][co][4 s + c] = w[r][s][c][co] (s < 7), zeros for s = 7, split like the other weights (wk_lo NULL = single pass).
+// y: N x H/2 x W/2 x 64.  H, W even.  Returns TTDG_E_ARG if the driver rejects the overlapping tensor map.
+extern "C" int ttdg_stem_tc(const float *x_pad, int Wp, const float *wk_hi, const float *wk_lo, const float *scale, const float *bias,
+                            int relu, int N, int H, int W, float *y, void *stream) {
+    TTDG_CHECK_ARG(x_pad && wk_hi && y && N >= 0 && H > 0 && W > 0 && Wp >= W + 8 && (H % 2) == 0 && (W % 2) == 0);
+    if (N == 0) return 0;
+    TcParams p = {};
+    p.y = y; p.scale = scale; p.bias = bias; p.relu = relu; p.stem = 1;
+    p.N = N; p.Ho = H / 2; p.Wo = W / 2; p.Cout = 64;
+    p.in_stride = 1; p.out_stride = 1; p.outH = p.Ho; p.outW = p.Wo;
+    p.R = 7; p.S = 1; p.pad = 0; p.flip = 0; p.kslabs = 1;
+    p.BW = pow2_ge(p.Wo) < TC_BM ? pow2_ge(p.Wo) : TC_BM;
+    p.BH = pow2_ge(p.Ho) < TC_BM / p.BW ? pow2_ge(p.Ho) : TC_BM / p.BW;
+    p.BI = TC_BM / (p.BW * p.BH);
+    p.tilesW = ceil_div(p.Wo, p.BW); p.tilesH = ceil_div(p.Ho, p.BH); p.tilesI = ceil_div(N, p.BI);
+    CUtensorMap ma, mb, mblo;
+    const cuuint64_t adims[4] = {32, (cuuint64_t)p.Wo, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t astr[3] = {32, (cuuint64_t)Wp * 16, (cuuint64_t)H * Wp * 16};
+    const cuuint32_t abox[4] = {32, (cuuint32_t)p.BW, (cuuint32_t)(2 * p.BH), (cuuint32_t)p.BI};
+    const cuuint64_t bdims[3] = {32, 64, 7};
+    const cuuint32_t bbox[3] = {32, 64, 1};
+    int rc = make_map(&ma, x_pad, 4, adims, abox, CU_TENSOR_MAP_SWIZZLE_128B, -2, astr);
+    if (!rc) rc = make_map(&mb, wk_hi, 3, bdims, bbox);
+    if (!rc && wk_lo) rc = make_map(&mblo, wk_lo, 3, bdims, bbox);
+    if (rc) return rc;
+    if (!wk_lo) mblo = mb;
+    cudaStream_t st = (cudaStream_t)stream;
+    return wk_lo ? launch_tc<64, true>(ma, mb, mblo, p, st) : launch_tc<64, false>(ma, mb, mblo, p, st);
 }
 
 extern "C" int ttdg_tf32_split(const float *x, float *hi, float *lo, int64_t numel, void *stream) {

@@ -119,6 +119,7 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
     __threadfence();
     cluster_sync_all();
 
+    if (tid == 0) { lapw->stat_steps = 0; lapw->stat_hops = 0; }
     int cur = 0, last = 1, last2 = 2;
     double tau = p.init_tau;
     int projector = (p.mode == 1) ? p.step_projector : 0;   // 0 sinkhorn, 1 hungarian
@@ -348,7 +349,7 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
     }
     if (c == 0 && tid == 0 && p.info) {
         p.info[0] = it_total; p.info[1] = it_sk; p.info[2] = it_hg; p.info[3] = n_lap; p.info[4] = n_stage;
-        p.info[5] = 0; p.info[6] = 0; p.info[7] = 0;
+        p.info[5] = lapw->stat_steps; p.info[6] = lapw->stat_hops; p.info[7] = 0;     // graph 0's LAPs: Dijkstra steps, path hops
     }
 }
 

@@ -15,6 +15,7 @@ lap_kernel(const float *__restrict__ s, float *__restrict__ perm, const int64_t 
     const int64_t *d = items + (size_t)b * 6;
     const int n1 = (int)d[2], n2 = (int)d[3];
     if (n1 > LAP_MAX_DIM || n2 > LAP_MAX_DIM) return;
+    if ((threadIdx.x & 31) == 0) { work[warp].stat_steps = 0; work[warp].stat_hops = 0; }
     hungarian_warp(s + d[0], perm + d[1], n1, n2, (int)d[4], (int)d[5], work[warp]);
 }
 

@@ -25,6 +25,7 @@ struct LapWork {                     // per-warp shared-memory workspace (state 
     int col4row[LAP_MAX_DIM];
     int row4col[LAP_MAX_DIM];
     int visited[LAP_MAX_DIM];        // rows put into SR in the current augmentation, in order
+    int stat_steps, stat_hops;       // running totals (lane 0): Dijkstra steps and augmenting-path hops, for profiling
 };
 
 // order-preserving map double -> uint64 (no NaNs here)
@@ -120,8 +121,10 @@ __device__ void lap_solve_warp_t(int nr, int nc, Cost cost, LapWork &w) {
         __syncwarp();
         // augment along the path (sequential, short)
         if (lane == 0) {
+            w.stat_steps += nvis;
             int j = sink;
             while (true) {
+                ++w.stat_hops;
                 const int r = w.path[j];
                 w.row4col[j] = r;
                 const int t = w.col4row[r];

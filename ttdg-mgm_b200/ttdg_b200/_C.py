@@ -48,7 +48,8 @@ SIGNATURES = {
     "ttdg_bias_grad": (c_int, [P, c_int64, c_int, P, P]),
     "ttdg_maxpool3x3s2": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "ttdg_resample2": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
-    "ttdg_preprocess": (c_int, [P, c_int, c_int, c_int, c_float, c_float, c_float, P, P]),
+    "ttdg_preprocess": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, P, P]),
+    "ttdg_stem_tc": (c_int, [P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
     "ttdg_conv_tc_supported": (c_int, [c_int, c_int, c_int]),
     "ttdg_conv_tc": (c_int, [P, P, P, P, P, P] + [c_int] * 15 + [P, P]),
     "ttdg_wgrad_tc_supported": (c_int, [c_int, c_int, c_int]),

@@ -182,10 +182,12 @@ class Conv2d(nn.Module):
     (C, H, W) order - the box head's fc1; our activations are (H, W, C)), 'deconv' (ConvTranspose2d Cin x Cout x 2 x 2,
     stored as a 1x1 conv with 4 Cout outputs ordered (a, b, c))."""
 
-    def __init__(self, cin, cout, k=1, stride=1, pad=0, bias=True, norm=False, kind="conv", chw=None):
+    def __init__(self, cin, cout, k=1, stride=1, pad=0, bias=True, norm=False, kind="conv", chw=None, cout_pad=4):
         super().__init__()
         self.cin, self.cout, self.k, self.stride, self.pad, self.kind, self.chw = cin, cout, k, stride, pad, kind, chw
-        self.cin_p, self.cout_p = _pad4(cin), _pad4(cout)
+        # cout_pad = 64 puts the narrow prediction heads (15 / 60 / 3 / 8 / 2 outputs) on the tensor-core kernel, whose N
+        # tile is 64: the zero columns cost nothing next to a 128-wide CUDA-core tile that is 90 % padding
+        self.cin_p, self.cout_p = _pad4(cin), (cout + cout_pad - 1) // cout_pad * cout_pad
         if kind == "deconv":
             self.weight = nn.Parameter(torch.zeros(1, 1, self.cin_p, 4 * self.cout_p))
             self.bias = nn.Parameter(torch.zeros(4 * self.cout_p))
@@ -289,10 +291,42 @@ class Bottleneck(nn.Module):
         return self.conv3(out, relu=True, residual=sc, res_mode=1)                   # relu(bn(conv3) + shortcut)
 
 
+STEM_TC = [os.environ.get("TTDG_STEM_TC", "1") == "1"]        # stem on tensor cores (padded image, overlapping TMA windows)
+STEM_LEFT, STEM_EXTRA = 3, 8                                   # padded image rows: 3 zero pixels | image | 5 zero pixels
+
+
 class Stem(nn.Module):
     def __init__(self):
         super().__init__()
         self.conv1 = Conv2d(3, 64, 7, 2, 3, bias=False, norm=True)
+
+    def _weights_tc(self, precise):
+        """[7][64][32] K-major stem weights: wk[r][co][4 s + c] = w[r][s][c][co], zeros for the 8th pixel of the window."""
+        w = self.conv1.weight
+        stamp = (PARAM_EPOCH[0], w._version, w.data_ptr(), precise)
+        hit = self.__dict__.get("_wk_stem")
+        if hit is not None and hit[0] == stamp:
+            return hit[1], hit[2]
+        wk = torch.zeros(7, 64, 32, dtype=torch.float32, device=w.device)
+        wk[:, :, :28] = w.detach().permute(0, 3, 1, 2).reshape(7, 64, 28)
+        hi, lo = tf32_split(wk)
+        if not precise:
+            lo = None
+        self.__dict__["_wk_stem"] = (stamp, hi, lo)
+        return hi, lo
+
+    def forward(self, x, width=None):
+        """x: N x H x W x 4 (plain) or, with ``width``, the padded image N x H x (width + 8) x 4 for the tensor-core stem."""
+        c = self.conv1
+        if width is None:
+            return c(x, relu=True)
+        if c.fold_scale is None:
+            c.fold()
+        N, H, Wp, _ = x.shape
+        hi, lo = self._weights_tc(CONV_MODE[0] == "tf32x3")
+        y = torch.empty(N, H // 2, width // 2, 64, dtype=torch.float32, device=x.device)
+        check(_C.lib().ttdg_stem_tc(_p(x), Wp, _p(hi), _p(lo), _p(c.fold_scale), _p(c.fold_bias), 1, N, H, width, _p(y), _stream()), "stem_tc")
+        return y
 
 
 class ResNet50(nn.Module):
@@ -307,10 +341,10 @@ class ResNet50(nn.Module):
                 cin = cout
             setattr(self, name, nn.Sequential(*layers))
 
-    def forward(self, x):
+    def forward(self, x, width=None):
         L = _C.lib()
         with torch.no_grad():                                   # FREEZE_AT = 2: stem + res2
-            y = self.stem.conv1(x, relu=True)
+            y = self.stem(x, width)
             N, H, W, C = y.shape
             p = torch.empty(N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C, dtype=torch.float32, device=y.device)
             check(L.ttdg_maxpool3x3s2(_p(y), N, H, W, C, _p(p), _stream()), "maxpool")
@@ -351,8 +385,8 @@ class Backbone(nn.Module):
             setattr(self, f"fpn_lateral{lvl}", Conv2d(c, 256, 1, 1, 0, bias=True))
             setattr(self, f"fpn_output{lvl}", Conv2d(256, 256, 3, 1, 1, bias=True))
 
-    def forward(self, x):
-        res = self.bottom_up(x)
+    def forward(self, x, width=None):
+        res = self.bottom_up(x, width)
         outs, prev = {}, None
         for lvl in (5, 4, 3, 2):
             lat = getattr(self, f"fpn_lateral{lvl}")
@@ -365,8 +399,8 @@ class RPNHead(nn.Module):
     def __init__(self, num_anchors=15):
         super().__init__()
         self.conv = Conv2d(256, 256, 3, 1, 1, bias=True)
-        self.objectness_logits = Conv2d(256, num_anchors, 1, 1, 0, bias=True)
-        self.anchor_deltas = Conv2d(256, num_anchors * 4, 1, 1, 0, bias=True)
+        self.objectness_logits = Conv2d(256, num_anchors, 1, 1, 0, bias=True, cout_pad=64)
+        self.anchor_deltas = Conv2d(256, num_anchors * 4, 1, 1, 0, bias=True, cout_pad=64)
 
 
 def cell_anchors():
@@ -468,8 +502,8 @@ class BoxHead(nn.Module):
 class BoxPredictor(nn.Module):
     def __init__(self, num_classes):
         super().__init__()
-        self.cls_score = Conv2d(1024, num_classes + 1, kind="linear")
-        self.bbox_pred = Conv2d(1024, num_classes * 4, kind="linear")
+        self.cls_score = Conv2d(1024, num_classes + 1, kind="linear", cout_pad=64)
+        self.bbox_pred = Conv2d(1024, num_classes * 4, kind="linear", cout_pad=64)
 
 
 class MaskHead(nn.Module):
@@ -478,7 +512,7 @@ class MaskHead(nn.Module):
         for i in range(1, 5):
             setattr(self, f"mask_fcn{i}", Conv2d(256, 256, 3, 1, 1, bias=True))
         self.deconv = Conv2d(256, 256, kind="deconv")
-        self.predictor = Conv2d(256, num_classes, 1, 1, 0, bias=True)
+        self.predictor = Conv2d(256, num_classes, 1, 1, 0, bias=True, cout_pad=64)
 
 
 def roi_align(feats4, rois, pooled):
@@ -591,17 +625,26 @@ class ROIHeads(nn.Module):
         return results
 
 
-def preprocess(images_u8, device):
+def preprocess(images_u8, device, stem_padded=False):
     """d2 preprocess_image: list of uint8 3 x H x W (same size) -> N x H x W x 4 fp32 NHWC, mean-subtracted, padded to
-    a multiple of 32 (size_divisibility)."""
+    a multiple of 32 (size_divisibility).  stem_padded: rows carry the stem's zero padding as well (3 pixels left, 5
+    right), the layout ttdg_stem_tc reads; returns (tensor N x H32 x (W32 + 8) x 4, W32)."""
     x = torch.stack(list(images_u8)).to(device, non_blocking=True).contiguous()
     N, C, H, W = x.shape
     assert C == 3 and x.dtype == torch.uint8
-    out = torch.empty(N, H, W, 4, dtype=torch.float32, device=device)
-    check(_C.lib().ttdg_preprocess(_p(x), N, H, W, *PIXEL_MEAN, _p(out), _stream()), "preprocess")
     ph, pw = (32 - H % 32) % 32, (32 - W % 32) % 32
-    if ph or pw:
-        out = torch.nn.functional.pad(out, (0, 0, 0, pw, 0, ph)).contiguous()
+    left, Wp = (STEM_LEFT, W + pw + STEM_EXTRA) if stem_padded else (0, W)
+    if ph:                                                  # bottom padding: image by image into the taller zeroed buffer
+        out = torch.zeros(N, H + ph, Wp, 4, dtype=torch.float32, device=device)
+        for n in range(N):
+            check(_C.lib().ttdg_preprocess(_p(x[n]), 1, H, W, Wp, left, *PIXEL_MEAN, _p(out[n]), _stream()), "preprocess")
+    else:
+        out = torch.empty(N, H, Wp, 4, dtype=torch.float32, device=device)
+        check(_C.lib().ttdg_preprocess(_p(x), N, H, W, Wp, left, *PIXEL_MEAN, _p(out), _stream()), "preprocess")
+    if stem_padded:
+        return out, W + pw
+    if pw:
+        out = torch.nn.functional.pad(out, (0, 0, 0, pw)).contiguous()
     return out
 
 
@@ -627,8 +670,11 @@ class MaskRCNN(nn.Module):
 
     def features(self, images_u8):
         _need_cuda(*[p for p in [self.backbone.fpn_output2.weight]])
-        x = preprocess(images_u8, self.backbone.fpn_output2.weight.device)
-        return self.backbone(x)
+        dev = self.backbone.fpn_output2.weight.device
+        if STEM_TC[0] and CONV_MODE[0] != "simt":
+            x, width = preprocess(images_u8, dev, stem_padded=True)
+            return self.backbone(x, width)
+        return self.backbone(preprocess(images_u8, dev))
 
     def detect_ttt(self, images_u8):
         """rcnn.py:331-345: features (NHWC, grad-carrying), RPN proposals and box-head detections in TRAIN mode."""
