@@ -215,6 +215,7 @@ def main():
     inputs_dev = [dict(d, image=d["image"].to(device)) for d in inputs_host]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
     stats = {"skipped": 0}
+    host_res = torch.empty(IMAGES_PER_GPU + 1, dtype=torch.float64).pin_memory()
 
     def step(inputs, readback):
         m.train()                                            # pass 1: adaptation (trainer.py:469-482)
@@ -227,9 +228,12 @@ def main():
             opt.step(world)
         m.eval()                                             # pass 2: inference with the adapted weights (trainer.py:484-485)
         out = m(inputs)
-        if readback:
-            chk = sum(int(o["instances"].pred_masks.sum().item()) for o in out)
-            return (float(loss.item()) if loss is not None else None), chk
+        if readback:                                         # one D2H read of the step's result: per-image mask pixel counts + the loss
+            res = torch.stack([o["instances"].pred_masks.sum().to(torch.float64) for o in out] +
+                              [loss.detach().to(torch.float64) if loss is not None else torch.full((), float("nan"), dtype=torch.float64, device=device)])
+            host_res.copy_(res, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return (float(host_res[-1]) if loss is not None else None), int(host_res[:-1].sum())
         return None
 
     def barrier():
@@ -283,7 +287,7 @@ def main():
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 + 8 * IMAGES_PER_GPU,
+                "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * (IMAGES_PER_GPU + 1),
                         "call": "model(batched_inputs, branch='TTT') + backward + FlatSGD.step + model(batched_inputs) from pinned host images",
                         "last_loss": last[0], "mask_pixels": last[1]},
                 "gpu_launches": int(launches), "skipped_steps": stats["skipped"],

@@ -81,6 +81,73 @@ elif what == "timing":
                 acc[k] += a.elapsed_time(b) / reps
     info = m.multi_matching_unsup.last_aux["info"].tolist()
     print({k: round(v, 2) for k, v in acc.items()}, "gagm iters", info[0], "graph-0 LAP steps", info[5], "hops", info[6])
+elif what == "layers":
+    # per-call device time of every library launch inside a real full step (hot caches, CUDA events around each call),
+    # grouped by entry point + geometry; conv rows carry their fp32-equivalent TFLOP/s (2 * pixels * Cin * Cout * taps)
+    sys.path.insert(0, ROOT)
+    import collections
+    import bench
+    from ttdg_b200 import _C
+    m, opt = bench.build_ours(dev)
+    inputs = [dict(d, image=d["image"].to(dev)) for d in bench.make_inputs(0)]
+    L = _C.lib()
+    rec, on = [], [False]
+    class Timed:
+        def __init__(self, name, fn):
+            self.name, self.fn = name, fn
+        def __call__(self, *a):
+            if not on[0]:
+                return self.fn(*a)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); rc = self.fn(*a); e1.record()
+            rec.append((self.name, tuple(int(v) for v in a if isinstance(v, int) and abs(v) < (1 << 20)), e0, e1))
+            return rc
+    proxy = type("LibProxy", (), {})()
+    for name in _C.SIGNATURES:
+        fn = getattr(L, name)
+        setattr(proxy, name, Timed(name, fn) if fn.restype is _C.c_int and name not in ("ttdg_version", "ttdg_limit") and "supported" not in name else fn)
+    _C._lib = proxy
+    def step():
+        m.train()
+        loss, _, _, _ = m(inputs, branch="TTT")
+        opt.zero_grad(); loss.backward(); opt.step(1)
+        m.eval()
+        return m(inputs)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    on[0] = True
+    for _ in range(reps):
+        step()
+    torch.cuda.synchronize()
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for name, ints, e0, e1 in rec:
+        a = agg[(name, ints)]
+        a[0] += 1; a[1] += e0.elapsed_time(e1)
+    def flops(name, a):
+        if name == "ttdg_conv_tc":          # res_mode, relu, flip, N, H, W, Cin, Cout, R, S, pad, stride, out_stride, outH, outW
+            _, _, _, N, H, W, Cin, Cout, R, S, pad, stride = a[:12]
+            Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+            return 2.0 * N * Ho * Wo * Cin * Cout * R * S
+        if name == "ttdg_wgrad_tc":         # precise, N, H, W, Cin, Cout, R, S, stride, pad
+            _, N, H, W, Cin, Cout, R, S, stride, pad = a[:10]
+            Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+            return 2.0 * N * Ho * Wo * Cin * Cout * R * S
+        if name in ("ttdg_conv_wgrad", "ttdg_conv_dgrad"):   # N, H, W, Cin, Cout, R, S, stride, pad
+            N, H, W, Cin, Cout, R, S, stride, pad = a[:9]
+            Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+            return 2.0 * N * Ho * Wo * Cin * Cout * R * S
+        if name == "ttdg_conv_fwd":         # res_mode, relu, N, H, W, Cin, Cout, R, S, stride, pad
+            _, _, N, H, W, Cin, Cout, R, S, stride, pad = a[:11]
+            Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+            return 2.0 * N * Ho * Wo * Cin * Cout * R * S
+        return 0.0
+    tot = sum(v[1] for v in agg.values()) / reps
+    print("sum of timed library calls: %.2f ms / step (%d calls / step)" % (tot, len(rec) // reps))
+    print("entry,geometry,calls_per_step,ms_per_step,us_per_call,tflops_fp32_equiv")
+    for (name, a), (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(sys.argv[3]) if len(sys.argv) > 3 else 70]:
+        f = flops(name, a)
+        print('%s,"%s",%.1f,%.3f,%.1f,%s' % (name, " ".join(map(str, a)), n / reps, ms / reps, 1e3 * ms / n, ("%.1f" % (f * n / (ms * 1e-3) / 1e12 / 1.0) if f else "")))
 elif what == "busy":
     # hot (not cold-cache) per-kernel device time of the full step and the GPU-busy fraction, from CUPTI via torch.profiler
     sys.path.insert(0, ROOT)

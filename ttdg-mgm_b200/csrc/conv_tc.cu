@@ -121,14 +121,66 @@ __device__ __forceinline__ void split_stage(unsigned char *raw, unsigned char *l
     }
 }
 
+// A operand from tensor memory (lane = GEMM row, one 32-bit column per k element), B from a shared-memory descriptor
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+
+// 3xTF32 split of one stage's A tile INTO TENSOR MEMORY.  Thread t of the four split warps owns GEMM row t (= TMEM lane t;
+// warp 8 + q may touch lanes 32 q .. 32 q + 31): it reads its 128-byte row of the 128-byte-swizzled K-major tile (16-byte
+// chunk c sits at chunk position c ^ (row & 7)), and stores hi = tf32(x) into columns [a_col, a_col + 32) and
+// lo = x - hi into [a_col + 32, a_col + 64) of its lane.
+__device__ __forceinline__ void split_stage_tmem(const unsigned char *raw, uint32_t tmem_row, int t) {
+    const unsigned char *rowp = raw + t * 128;
+    const int sw = t & 7;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float4 v = *reinterpret_cast<const float4 *>(rowp + (((half * 4 + c) ^ sw) << 4));
+            const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint32_t u;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x[e]));
+                hi[c * 4 + e] = u;
+                lo[c * 4 + e] = __float_as_uint(x[e] - __uint_as_float(u));
+            }
+        }
+        tmem_st16(tmem_row + half * 16, hi);
+        tmem_st16(tmem_row + TC_BK + half * 16, lo);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 template <int BN_TILE, bool PRECISE>
 struct TcCfg {
     static constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN_TILE * 128;
-    static constexpr int STAGE_BYTES = (PRECISE ? 2 : 1) * (A_BYTES + B_BYTES);      // [A | B | A lo | B lo]
-    static constexpr int TX_BYTES = A_BYTES + (PRECISE ? 2 : 1) * B_BYTES;           // what TMA delivers per stage
-    static constexpr int STAGES = PRECISE ? (BN_TILE == 128 ? 3 : 4) : (BN_TILE == 128 ? 6 : 8);
+    // 3xTF32: the split activations (A hi / lo) live in TENSOR MEMORY, not in shared memory: the stage holds the raw fp32
+    // A tile and the two pre-split weight tiles [A raw | B hi | B lo].  The kernel was shared-memory-bandwidth bound
+    // (ncu: tensor pipe 54 % with TMA writes + split read/write + UMMA reading both operands = ~190 KB of smem traffic per
+    // k-block against 768 MMA cycles); with A in TMEM the MMAs read only B from shared memory and the split warps write
+    // nothing back to it (~110 KB per k-block).
+    static constexpr int STAGE_BYTES = A_BYTES + (PRECISE ? 2 : 1) * B_BYTES;
+    static constexpr int TX_BYTES = STAGE_BYTES;                                     // what TMA delivers per stage
+    static constexpr int STAGES = PRECISE ? (BN_TILE == 128 ? 4 : 6) : (BN_TILE == 128 ? 6 : 8);
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-    static constexpr int TMEM_COLS = 2 * BN_TILE;        // two accumulator buffers (ping-pong between MMA and epilogue)
+    static constexpr int ACC_COLS = 2 * BN_TILE;         // two accumulator buffers (ping-pong between MMA and epilogue)
+    static constexpr int A_COLS = 2 * TC_BK;             // TMEM columns of one stage's A operand: 32 hi + 32 lo
+    static constexpr int TMEM_COLS = PRECISE ? 512 : ACC_COLS;      // power of two >= ACC_COLS + STAGES * A_COLS
+    static_assert(!PRECISE || ACC_COLS + STAGES * A_COLS <= 512, "TMEM budget");
     static constexpr int EPI_COLS = BN_TILE / 2;         // columns per epilogue warp (two warps share a TMEM lane group)
     // The tensor core adds into its fp32 accumulator with truncation, so the error of one long accumulation grows
     // linearly with K (measured 5e-5 relative at K = 12544).  The accumulation is therefore cut into chunks of CHUNK
@@ -197,6 +249,23 @@ __device__ __forceinline__ void tc_split_loop(const TcSmem &sm, int KB) {
     }
 }
 
+// split warps of the conv kernel: every k-block, wait for TMA, split the A tile into this stage's TMEM columns, publish
+template <class Cfg>
+__device__ __forceinline__ void tc_split_loop_tmem(const TcSmem &sm, uint32_t tmem_base, int KB) {
+    const int t = threadIdx.x - TC_WARP_CVT0 * 32;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(t & ~31) << 16) + (uint32_t)Cfg::ACC_COLS;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&sm.full[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        split_stage_tmem(sm.tiles + stage * Cfg::STAGE_BYTES, lane_base + (uint32_t)(stage * Cfg::A_COLS), t);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.conv[stage])) : "memory");
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+    }
+}
+
 // epilogue warps: add the drained TMEM chunks (columns col0 .. col0 + EPI_COLS of lane group q) in registers
 template <class Cfg>
 __device__ __forceinline__ void tc_drain(const TcSmem &sm, uint32_t tmem_base, int KB, int q, int col0, float (&acc)[Cfg::EPI_COLS]) {
@@ -211,7 +280,7 @@ __device__ __forceinline__ void tc_drain(const TcSmem &sm, uint32_t tmem_base, i
 #pragma unroll
         for (int c0 = 0; c0 < Cfg::EPI_COLS; c0 += 32) {
             uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * (Cfg::TMEM_COLS / 2) + col0 + c0), v);   // warp-collective
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * (Cfg::ACC_COLS / 2) + col0 + c0), v);   // warp-collective
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);                      // round-to-nearest fp32
         }
@@ -257,7 +326,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (p.stem) tma_load_4d(st, &tmA, &sm.full[stage], 0, w0, 2 * h0 + r - 3, i0);
                 else tma_load_4d(st, &tmA, &sm.full[stage], c0, (w0 + s - p.pad) * p.in_stride, (h0 + r - p.pad) * p.in_stride, i0);
                 tma_load_3d(st + Cfg::A_BYTES, &tmB, &sm.full[stage], c0, n0, btap);
-                if (PRECISE) tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tmBlo, &sm.full[stage], c0, n0, btap);
+                if (PRECISE) tma_load_3d(st + Cfg::A_BYTES + Cfg::B_BYTES, &tmBlo, &sm.full[stage], c0, n0, btap);
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -279,14 +348,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(PRECISE ? &sm.conv[stage] : &sm.full[stage], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a = smem_u32(sm.tiles + stage * Cfg::STAGE_BYTES), b = a + Cfg::A_BYTES;
-                    const uint32_t alo = b + Cfg::B_BYTES, blo = alo + Cfg::A_BYTES;
+                    const uint32_t blo = b + Cfg::B_BYTES;
+                    const uint32_t ta = tmem_base + (uint32_t)(Cfg::ACC_COLS + stage * Cfg::A_COLS);      // A hi | A lo (3xTF32)
 #pragma unroll
                     for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
                         const uint32_t koff = k * TC_UMMA_K * 4;             // bytes inside the 128-byte swizzled row
-                        umma_tf32(tacc, umma_desc(a + koff), umma_desc(b + koff), idesc, (kb != ch * Cfg::CHUNK) || k != 0);
+                        const uint32_t first = (kb != ch * Cfg::CHUNK) || k != 0;
                         if (PRECISE) {
-                            umma_tf32(tacc, umma_desc(alo + koff), umma_desc(b + koff), idesc, 1);
-                            umma_tf32(tacc, umma_desc(a + koff), umma_desc(blo + koff), idesc, 1);
+                            umma_tf32_ts(tacc, ta + k * TC_UMMA_K, umma_desc(b + koff), idesc, first);
+                            umma_tf32_ts(tacc, ta + TC_BK + k * TC_UMMA_K, umma_desc(b + koff), idesc, 1);
+                            umma_tf32_ts(tacc, ta + k * TC_UMMA_K, umma_desc(blo + koff), idesc, 1);
+                        } else {
+                            umma_tf32(tacc, umma_desc(a + koff), umma_desc(b + koff), idesc, first);
                         }
                     }
                     umma_commit(&sm.empty[stage]);                           // frees the smem slot when these MMAs retire
@@ -296,7 +369,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp >= TC_WARP_CVT0) {
-        if (PRECISE) tc_split_loop<Cfg, Cfg::A_BYTES>(sm, KB);                // activations only: the weight copies are pre-split
+        if (PRECISE) tc_split_loop_tmem<Cfg>(sm, tmem_base, KB);              // activations only: the weight copies are pre-split
     } else {
         // ===================== epilogue: warps 0..7; warp w owns TMEM lanes 32 * (w % 4) .. and column half w / 4
         const int q = warp & 3, col0 = (warp >> 2) * Cfg::EPI_COLS;
@@ -357,6 +430,7 @@ struct WgCfg {
     static constexpr int STAGES = PRECISE ? (BN_TILE == 128 ? 3 : 4) : (BN_TILE == 128 ? 6 : 8);
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
     static constexpr int TMEM_COLS = 2 * BN_TILE;
+    static constexpr int ACC_COLS = 2 * BN_TILE;
     static constexpr int EPI_COLS = BN_TILE / 2;
     static constexpr int CHUNK = 8;
 };

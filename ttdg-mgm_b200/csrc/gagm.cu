@@ -281,10 +281,10 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                     if (warp == 0) {
                         const double *Zc = Z;
                         if (n <= NU) {
-                            lap_solve_warp(n, NU, [=](int i, int j) { return -Zc[i * ZP + j]; }, *lapw);
+                            lap_solve_warp(n, NU, LapSmemNegCost{lap_smem_u32(Zc), ZP, 1}, *lapw);
                             for (int i = lane; i < n; i += 32) Ug[i * NU + lapw->col4row[i]] = 1.0;
                         } else {
-                            lap_solve_warp(NU, n, [=](int i, int j) { return -Zc[j * ZP + i]; }, *lapw);
+                            lap_solve_warp(NU, n, LapSmemNegCost{lap_smem_u32(Zc), 1, ZP}, *lapw);
                             for (int i = lane; i < NU; i += 32) Ug[lapw->col4row[i] * NU + i] = 1.0;
                         }
                     }

@@ -38,61 +38,97 @@ __device__ __forceinline__ double lap_unord(unsigned long long k) {
     return __longlong_as_double((long long)b);
 }
 
+__device__ __forceinline__ uint32_t lap_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// shared-space fp64 load from a 32-bit shared address (no generic->shared window arithmetic on the critical path)
+__device__ __forceinline__ double lap_lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+// cost(i, j) = -Z[i * si + j * sj] for a double matrix in shared memory (the GA-GM projector's V tile)
+struct LapSmemNegCost {
+    uint32_t base; int si, sj;
+    __device__ __forceinline__ double operator()(int i, int j) const { return -lap_lds_f64(base + (uint32_t)((i * si + j * sj) << 3)); }
+};
+
 // Cost: functor double operator()(int i, int j) for the WORKING matrix (nr <= nc).
 // On return w.col4row[i] (i < nr) holds the column assigned to row i.  Must be called by a full warp.
 //
 // Per-column state (shortest, v, path, position in SciPy's `remaining` list, row4col) lives in REGISTERS of the lane
-// that owns the column (j = lane + 32 t, t < SLOTS = ceil(nc / 32)); one inner iteration is a few FP64 ops per owned
-// column plus three redux.sync reductions (value high word, value low word, winner key) instead of shuffle butterflies
-// over shared memory.
+// that owns the column (j = lane + 32 t, t < SLOTS = ceil(nc / 32)); v stays there across augmentations.  One Dijkstra
+// step is a branch-free relaxation of the owned columns (so the slots of a lane overlap in the FP64 pipe) plus ONE
+// redux.sync on the high word of the ordered value: if a single lane holds that minimum (the usual case) its low word and
+// winner key are fetched with two independent shuffles; only on a high-word tie are the low word and the key reduced too.
 // SciPy's selection rule "strictly lower, or equal and unassigned" over the scan order it = 0 .. num_remaining-1 picks,
 // among the minima, the LAST unassigned position if any, else the FIRST position; with the tie key
 //     unassigned: 256 + it,   assigned: 255 - it      (maximised)
 // the winner of (value ascending, key descending) is exactly that element.  The tie key is unique among the remaining
 // columns, so the winner's column index and its row4col ride along in the low bits of the same 32-bit key
-// (tie << 16 | column << 8 | row4col + 1) and one redux.max delivers all three.  `remaining` is filled in reverse
-// (position it holds column nc-1-it) and compacted by moving the last element into the freed position - tracked here
-// as a per-column position register.
+// (tie << 16 | column << 8 | row4col + 1).  `remaining` is filled in reverse (position it holds column nc-1-it) and
+// compacted by moving the last element into the freed position - tracked here as a per-column position register.
+// Dual update: the rows visited in an augmentation are `cur` and row4col[j] of every scanned, assigned column j, so
+// u[row4col[j]] += minVal - shortest[j] is applied by the lane that owns column j (SciPy: u[i] += minVal -
+// shortest[col4row[i]], the same operands).
 template <int SLOTS, class Cost>
 __device__ void lap_solve_warp_t(int nr, int nc, Cost cost, LapWork &w) {
     const int lane = threadIdx.x & 31;
+    const uint32_t u_sa = lap_smem_u32(w.u);
     for (int k = lane; k < nr; k += 32) { w.u[k] = 0.0; w.col4row[k] = -1; }
-    for (int k = lane; k < nc; k += 32) { w.v[k] = 0.0; w.row4col[k] = -1; }
+    for (int k = lane; k < nc; k += 32) { w.row4col[k] = -1; }
+    double vj[SLOTS];
+    int jc[SLOTS];
+#pragma unroll
+    for (int t = 0; t < SLOTS; ++t) { vj[t] = 0.0; jc[t] = min(lane + 32 * t, nc - 1); }
+    int steps = 0, hops = 0;
     __syncwarp();
     for (int cur = 0; cur < nr; ++cur) {
-        double sh[SLOTS], vj[SLOTS];
-        unsigned long long ks[SLOTS];                           // lap_ord(sh[t])
+        double sh[SLOTS];
         int pos[SLOTS], r4c[SLOTS], pth[SLOTS];
 #pragma unroll
         for (int t = 0; t < SLOTS; ++t) {
             const int j = lane + 32 * t;
-            sh[t] = INFINITY; ks[t] = lap_ord(INFINITY); pth[t] = -1;
-            if (j < nc) { vj[t] = w.v[j]; pos[t] = nc - 1 - j; r4c[t] = w.row4col[j]; }
-            else { vj[t] = 0.0; pos[t] = -1; r4c[t] = 0; }
+            sh[t] = INFINITY; pth[t] = -1;
+            if (j < nc) { pos[t] = nc - 1 - j; r4c[t] = w.row4col[j]; }
+            else { pos[t] = -1; r4c[t] = 0; }
         }
         double minVal = 0.0;
-        int num_remaining = nc, sink = -1, i = cur, nvis = 0;
+        int num_remaining = nc, sink = -1, i = cur;
         while (sink == -1) {
-            if (lane == 0) w.visited[nvis] = i;
-            ++nvis;
-            const double ui = w.u[i];
-            unsigned long long bk = 0xFFFFFFFFFFFFFFFFull;      // lane-local best (ordered value)
-            unsigned bkey = 0;                                  // its winner key
+            ++steps;
+            const double ui = lap_lds_f64(u_sa + (uint32_t)(i << 3));
+            double c[SLOTS];
+#pragma unroll
+            for (int t = 0; t < SLOTS; ++t) c[t] = cost(i, jc[t]);
+            double best = INFINITY;                             // lane-local best value
+            unsigned bkey = 0u;                                 // its winner key (0: no live column in this lane)
 #pragma unroll
             for (int t = 0; t < SLOTS; ++t) {
-                if (pos[t] >= 0) {
-                    const double r = ((minVal + cost(i, lane + 32 * t)) - ui) - vj[t];
-                    if (r < sh[t]) { sh[t] = r; pth[t] = i; ks[t] = lap_ord(r); }
-                    const unsigned tie = (r4c[t] == -1) ? 256u + (unsigned)pos[t] : 255u - (unsigned)pos[t];
-                    const unsigned key = (tie << 16) | ((unsigned)(lane + 32 * t) << 8) | (unsigned)(r4c[t] + 1);
-                    if (ks[t] < bk || (ks[t] == bk && key > bkey)) { bk = ks[t]; bkey = key; }
-                }
+                const bool live = pos[t] >= 0;
+                const double r = ((minVal + c[t]) - ui) - vj[t];
+                const bool upd = live && (r < sh[t]);
+                sh[t] = upd ? r : sh[t];
+                pth[t] = upd ? i : pth[t];
+                const unsigned tie = (r4c[t] == -1) ? 256u + (unsigned)pos[t] : 255u - (unsigned)pos[t];
+                const unsigned key = live ? ((tie << 16) | ((unsigned)(lane + 32 * t) << 8) | (unsigned)(r4c[t] + 1)) : 0u;
+                const double cv = live ? sh[t] : INFINITY;
+                const bool better = live && ((cv < best) || (cv == best && key > bkey));
+                best = better ? cv : best;
+                bkey = better ? key : bkey;
             }
+            const unsigned long long bk = lap_ord(best);
             const unsigned hi = (unsigned)(bk >> 32), lo = (unsigned)bk;
-            const unsigned mhi = __reduce_min_sync(TTDG_FULL, hi);
-            const unsigned mlo = __reduce_min_sync(TTDG_FULL, hi == mhi ? lo : 0xFFFFFFFFu);
-            const bool cand = (hi == mhi) && (lo == mlo) && (bkey != 0u);
-            const unsigned mkey = __reduce_max_sync(TTDG_FULL, cand ? bkey : 0u);
+            const unsigned mhi = __reduce_min_sync(TTDG_FULL, bkey != 0u ? hi : 0xFFFFFFFFu);
+            const bool at_min = (hi == mhi) && (bkey != 0u);
+            const unsigned tied = __ballot_sync(TTDG_FULL, at_min);
+            unsigned mlo, mkey;
+            if (__popc(tied) == 1) {
+                const int src = __ffs(tied) - 1;
+                mlo = __shfl_sync(TTDG_FULL, lo, src);
+                mkey = __shfl_sync(TTDG_FULL, bkey, src);
+            } else {
+                mlo = __reduce_min_sync(TTDG_FULL, at_min ? lo : 0xFFFFFFFFu);
+                mkey = __reduce_max_sync(TTDG_FULL, (at_min && lo == mlo) ? bkey : 0u);
+            }
             minVal = lap_unord(((unsigned long long)mhi << 32) | mlo);
             const unsigned mtie = mkey >> 16;
             const int psel = mtie >= 256u ? (int)(mtie - 256u) : (int)(255u - mtie);
@@ -102,29 +138,27 @@ __device__ void lap_solve_warp_t(int nr, int nc, Cost cost, LapWork &w) {
 #pragma unroll
             for (int t = 0; t < SLOTS; ++t) {
                 const int j = lane + 32 * t;
-                if (j == jsel) {                                  // scanned: SC[j] = true, leaves `remaining`
-                    w.shortest[j] = sh[t]; w.path[j] = pth[t]; pos[t] = -2;
-                } else if (pos[t] == last) pos[t] = psel;         // remaining[index] = remaining[--num_remaining]
+                if (j == jsel) pos[t] = -2;                       // scanned: SC[j] = true, leaves `remaining`
+                else if (pos[t] == last) pos[t] = psel;           // remaining[index] = remaining[--num_remaining]
             }
             num_remaining = last;
         }
-        __syncwarp();
-        // dual update
-        for (int k = lane; k < nvis; k += 32) {
-            const int r = w.visited[k];
-            if (r == cur) w.u[r] += minVal;
-            else w.u[r] += minVal - w.shortest[w.col4row[r]];
-        }
+        // dual update (u in shared memory by the owner of the scanned column, v in registers) + path of the scanned columns
+        if (lane == 0) w.u[cur] += minVal;
 #pragma unroll
         for (int t = 0; t < SLOTS; ++t)
-            if (pos[t] == -2) w.v[lane + 32 * t] = vj[t] - (minVal - sh[t]);
+            if (pos[t] == -2) {
+                const double d = minVal - sh[t];
+                if (r4c[t] >= 0) w.u[r4c[t]] += d;
+                vj[t] -= d;
+                w.path[lane + 32 * t] = pth[t];
+            }
         __syncwarp();
         // augment along the path (sequential, short)
         if (lane == 0) {
-            w.stat_steps += nvis;
             int j = sink;
             while (true) {
-                ++w.stat_hops;
+                ++hops;
                 const int r = w.path[j];
                 w.row4col[j] = r;
                 const int t = w.col4row[r];
@@ -135,6 +169,8 @@ __device__ void lap_solve_warp_t(int nr, int nc, Cost cost, LapWork &w) {
         }
         __syncwarp();
     }
+    if (lane == 0) { w.stat_steps += steps; w.stat_hops += hops; }
+    __syncwarp();
 }
 
 template <class Cost>

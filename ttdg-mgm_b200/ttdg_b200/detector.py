@@ -629,7 +629,13 @@ def preprocess(images_u8, device, stem_padded=False):
     """d2 preprocess_image: list of uint8 3 x H x W (same size) -> N x H x W x 4 fp32 NHWC, mean-subtracted, padded to
     a multiple of 32 (size_divisibility).  stem_padded: rows carry the stem's zero padding as well (3 pixels left, 5
     right), the layout ttdg_stem_tc reads; returns (tensor N x H32 x (W32 + 8) x 4, W32)."""
-    x = torch.stack(list(images_u8)).to(device, non_blocking=True).contiguous()
+    images_u8 = list(images_u8)
+    if images_u8[0].device.type == "cpu":                   # host images (pinned by the loader): one async H2D copy each, straight
+        x = torch.empty((len(images_u8),) + tuple(images_u8[0].shape), dtype=images_u8[0].dtype, device=device)     # into the batch
+        for n, im in enumerate(images_u8):
+            x[n].copy_(im, non_blocking=True)
+    else:
+        x = torch.stack(images_u8).contiguous()
     N, C, H, W = x.shape
     assert C == 3 and x.dtype == torch.uint8
     ph, pw = (32 - H % 32) % 32, (32 - W % 32) % 32
