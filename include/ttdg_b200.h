@@ -246,13 +246,17 @@ int ttdg_preprocess(const unsigned char *img_u8, int N, int H, int W, int Wp, in
  *                (ttdg_weight_transpose_split of the [R][S][Cin][Cout] parameter); data gradient (flip = 1,
  *                pad = R-1-pad_fwd, x = dY) = the parameter array itself read as [R*S][n = Cin_fwd][k = Cout_fwd], split
  *                with ttdg_tf32_split.  wk_lo == NULL -> single-pass TF32.  Otherwise "3xTF32": hi*hi + lo*hi + hi*lo
- *                gives fp32-grade products (parity config); the activations are split in shared memory inside the
- *                kernel's pipeline, between the TMA arrival and the MMA.
+ *                gives fp32-grade products (parity config); the activations are split inside the kernel's pipeline,
+ *                between the TMA arrival and the MMA, into TENSOR MEMORY (the A operand of the MMAs comes from TMEM).
  *   (Cin, Cout) are the GEMM's k and n extents.
  *   Strided 1x1 convs (the first block of res3 / res4 / res5, STRIDE_IN_1X1): in_stride = 2 reads x[n, 2 ho, 2 wo] through
  *   TMA element strides (forward); out_stride = 2 stores the result for (ho, wo) at (2 ho, 2 wo) of a zero-filled
  *   outH x outW map (data gradient).  R = S = 1, pad = 0 only; outH / outW are ignored when out_stride == 1. */
 int ttdg_conv_tc_supported(int Cin, int Cout, int stride);
+/* Thread-block-cluster size along the pixel tiles for ttdg_conv_tc: the CTAs of a cluster share the weight tile, each
+ * loads 1/cl of it and TMA multicasts the slice to all of them.  cl = 1 (default; also env TTDG_TC_CLUSTER), 2 or 4.
+ * Results do not depend on it.  Returns the previous value, or TTDG_E_ARG. */
+int ttdg_conv_tc_set_cluster(int cl);
 int ttdg_conv_tc(const float *x, const float *wk_hi, const float *wk_lo, const float *scale, const float *bias,
                  const float *residual, int res_mode, int relu, int flip, int N, int H, int W, int Cin, int Cout, int R,
                  int S, int pad, int in_stride, int out_stride, int outH, int outW, float *y, void *stream);
@@ -302,6 +306,18 @@ int ttdg_pixel_shuffle2(const float *x, int R, int H, int W, int C, float *y, vo
  * over the H x W image (grid_sample semantics, align_corners = False). */
 int ttdg_mask_paste(const float *logits, int ld_logits, int M, const float *boxes, const int64_t *classes, int R, int H,
                     int W, float threshold, unsigned char *out, void *stream);
+
+/* On-device half of DiceEvaluator.process (adapteacher/evaluation/dice_metric.py:25-92): for BINARY masks Dice (:57-58),
+ * the E-measure (:110-143) and the S-measure (:146-240) are functions of pixel counts, so the <= 100 x H x W predicted
+ * masks per image never leave the GPU.
+ *   ttdg_mask_gt_stats  : gt G x H x W (uint8, nonzero = set) -> stats int64[G][5] = {n, sum of rows, sum of columns,
+ *                         split_y, split_x}, split = int(round(centre of mass)) + 1 with round-half-to-even (:227-229)
+ *   ttdg_mask_pair_counts: pairs int32[n_pairs][2] = (prediction index, ground-truth index) ->
+ *                         counts int64[n_pairs][4 quadrants: TL, TR, BL, BR][n11, n10, n01, n00] (prediction first),
+ *                         quadrants split at the ground truth's (split_y, split_x). */
+int ttdg_mask_gt_stats(const unsigned char *gt, int G, int H, int W, int64_t *stats, void *stream);
+int ttdg_mask_pair_counts(const unsigned char *pred, const unsigned char *gt, const int32_t *pairs, int n_pairs,
+                          const int64_t *gt_stats, int H, int W, int64_t *counts, void *stream);
 
 #ifdef __cplusplus
 }

@@ -234,3 +234,30 @@ def test_stem_tc(mode, rtol, N, H, W):
     det.set_conv_mode("simt")
     y2 = stem(det.preprocess(ims, torch.device("cuda")))
     assert float((y2 - y).abs().max() / ref.abs().max()) < rtol
+
+
+@pytest.mark.parametrize("cl", [2, 4])
+@pytest.mark.parametrize("cin,cout,k,pad,H,W,N", [(256, 256, 3, 1, 32, 32, 2), (256, 256, 3, 1, 14, 14, 7), (128, 512, 1, 0, 24, 40, 1),
+                                                 (1024, 64, 1, 0, 16, 16, 3)])
+def test_conv_tc_cluster_multicast(cl, cin, cout, k, pad, H, W, N):
+    """Thread-block clusters along the pixel tiles with the weight tile delivered by TMA multicast (each CTA loads 1 / cl of
+    it): the same MMAs in the same order, so the result must be BIT-IDENTICAL to the cluster-less launch - including grids
+    that are padded to whole clusters (7 x 2 tiles at 14 x 14) and the 64-wide N tile."""
+    from ttdg_b200 import _C
+    det.set_conv_mode("tf32x3")
+    g = torch.Generator().manual_seed(cl + cin + H)
+    layer = det.Conv2d(cin, cout, k, 1, pad, bias=True).cuda()
+    layer.load_state_dict({"weight": torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5, "bias": torch.randn(cout, generator=g)})
+    x = nhwc(torch.randn(N, cin, H, W, generator=g)).cuda()
+    L = _C.lib()
+    prev = L.ttdg_conv_tc_set_cluster(1)
+    try:
+        with torch.no_grad():
+            y1 = layer(x, relu=True)
+            assert L.ttdg_conv_tc_set_cluster(cl) == 1
+            y2 = layer(x, relu=True)
+        torch.cuda.synchronize()
+    finally:
+        L.ttdg_conv_tc_set_cluster(prev)
+    assert torch.equal(y1, y2)
+    assert L.ttdg_conv_tc_set_cluster(3) == -1

@@ -61,3 +61,46 @@ def test_baseline_trainer_test_loop():
     BaselineTrainer.test(cfg, model, opt, data_loaders={"Fundus_a": batches, "Fundus_b": batches},
                          dataset_dicts={"Fundus_a": dicts, "Fundus_b": dicts})
     assert model.ttt_calls == 2
+
+
+def _counts_numpy(pred, gt):
+    """What ttdg_mask_gt_stats / ttdg_mask_pair_counts compute, in numpy (the device kernels are checked against this)."""
+    from scipy import ndimage
+    h, w = gt.shape
+    if gt.sum() > 0:
+        cy, cx = ndimage.center_of_mass(gt)
+        ys, xs = int(round(cy)) + 1, int(round(cx)) + 1
+    else:
+        ys = xs = 0
+    c = np.zeros((4, 4), np.int64)
+    for q, (sy, sx) in enumerate(((slice(0, ys), slice(0, xs)), (slice(0, ys), slice(xs, w)), (slice(ys, h), slice(0, xs)),
+                                  (slice(ys, h), slice(xs, w)))):
+        p, g = pred[sy, sx].astype(bool), gt[sy, sx].astype(bool)
+        c[q] = [(p & g).sum(), (p & ~g).sum(), (~p & g).sum(), (~p & ~g).sum()]
+    return c, (ys, xs)
+
+
+def test_metrics_from_counts_match_reference(golden_dir):
+    """The closed forms the on-device evaluator uses (pixel counts -> Dice / E-measure / S-measure) against the golden
+    values of the reference's own array code, and against the array mirror on extra random shapes."""
+    from adapteacher.evaluation.dice_metric import metrics_from_counts
+    g = np.load(f"{golden_dir}/metrics.npz")
+    for i, (pred, gt) in enumerate(cases()):
+        c, split = _counts_numpy(pred, gt)
+        d, e, s = metrics_from_counts(c, split, gt.shape)
+        np.testing.assert_allclose(d, float(g[f"dice_{i}"]), rtol=1e-12)
+        np.testing.assert_allclose(e, float(g[f"ea_{i}"]), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(s, float(g[f"sm_{i}"]), rtol=2e-6, atol=1e-9)
+    rng = np.random.default_rng(5)
+    for k in range(12):
+        h, w = int(rng.integers(17, 90)), int(rng.integers(17, 90))
+        yy, xx = np.mgrid[0:h, 0:w]
+        gt = ((yy - rng.uniform(0, h)) ** 2 / rng.uniform(9, 400) + (xx - rng.uniform(0, w)) ** 2 / rng.uniform(9, 400)) <= 1
+        pred = np.roll(gt, (int(rng.integers(-4, 5)), int(rng.integers(-4, 5))), (0, 1)) ^ (rng.random((h, w)) < 0.02)
+        if gt.sum() == 0:
+            continue
+        c, split = _counts_numpy(pred, gt)
+        d, e, s = metrics_from_counts(c, split, gt.shape)
+        np.testing.assert_allclose(d, dice(pred, gt), rtol=1e-12)
+        np.testing.assert_allclose(e, enhanced_align(pred, gt), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(s, Structure_measure().get_score(pred, gt), rtol=2e-6, atol=1e-9)

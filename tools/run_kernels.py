@@ -148,6 +148,29 @@ elif what == "layers":
     for (name, a), (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(sys.argv[3]) if len(sys.argv) > 3 else 70]:
         f = flops(name, a)
         print('%s,"%s",%.1f,%.3f,%.1f,%s' % (name, " ".join(map(str, a)), n / reps, ms / reps, 1e3 * ms / n, ("%.1f" % (f * n / (ms * 1e-3) / 1e12 / 1.0) if f else "")))
+elif what == "conv":
+    # isolated timing of conv_tc geometries (random data): python tools/run_kernels.py conv <reps> [N,H,W,Cin,Cout,R ...]
+    from ttdg_b200 import detector
+    geoms = [tuple(int(v) for v in a.split(",")) for a in sys.argv[3:]] or [(8, 128, 128, 256, 256, 3), (8, 32, 32, 256, 256, 3),
+                                                                             (800, 14, 14, 256, 256, 3), (8000, 1, 1, 12544, 1024, 1),
+                                                                             (8, 128, 128, 64, 256, 1), (8, 32, 32, 256, 1024, 1)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for (N, H, W, Cin, Cout, R) in geoms:
+        x = torch.randn(N, H, W, Cin, device=dev)
+        w = torch.randn(R, R, Cin, Cout, device=dev) * 0.05
+        holder = torch.nn.Module()
+        y = detector.conv_forward(x, w, None, None, None, 0, False, R, R, 1, R // 2, owner=holder)
+        torch.cuda.synchronize()
+        ms = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            detector.conv_forward(x, w, None, None, None, 0, False, R, R, 1, R // 2, out=y, owner=holder)
+            e1.record(); torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1) / reps
+        fl = 2.0 * N * H * W * Cin * Cout * R * R
+        print("conv %s: %.1f us, %.1f TFLOP/s fp32-equivalent" % ((N, H, W, Cin, Cout, R), ms * 1e3, fl / (ms * 1e-3) / 1e12))
 elif what == "busy":
     # hot (not cold-cache) per-kernel device time of the full step and the GPU-busy fraction, from CUPTI via torch.profiler
     sys.path.insert(0, ROOT)

@@ -18,15 +18,20 @@
 // warps between the TMA arrival and the MMA (no extra pass over HBM).  Single-pass TF32 (wk_lo == NULL) is the fast mode.
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
 namespace ttdg {
 
-constexpr int TC_THREADS = 448;       // warps 0-7 epilogue, 8-11 operand split (3xTF32 mode), 12 TMA producer, 13 MMA issuer
+// warps 0-7 epilogue; 8-11 operand split (3xTF32 mode); 12 TMA producer; 13 MMA issuer.  TC_SPLIT_GROUPS = 2 (warps 8-15 in
+// two groups that take alternate k-blocks, 576 threads) was measured on B200 and is NOT faster (210 vs 217 TFLOP/s
+// fp32-equivalent on the 3x3 256->256 layer): the split warps do not pace the pipeline.
+constexpr int TC_SPLIT_GROUPS = 1;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_WARP_CVT0 = 8, TC_CVT_THREADS = 128;
-constexpr int TC_WARP_TMA = 12, TC_WARP_MMA = 13;
+constexpr int TC_WARP_TMA = TC_WARP_CVT0 + 4 * TC_SPLIT_GROUPS, TC_WARP_MMA = TC_WARP_TMA + 1;
+constexpr int TC_THREADS = (TC_WARP_MMA + 1) * 32;
 constexpr int TC_BM = 128;           // output pixels per tile (TMEM lanes)
 constexpr int TC_BK = 32;            // fp32 channels per k-block = one 128-byte swizzle row
 constexpr int TC_UMMA_K = 8;         // tf32
@@ -43,6 +48,7 @@ struct TcParams {
     int in_stride;                   // 1, or 2 for a strided 1x1 conv: the tensor map has element strides {1, 2, 2, 1}
     int stem;                        // 7x7 stride-2 stem on the padded image: k-block r = filter row, box = 8-pixel windows
     int out_stride, outH, outW;      // output pixel (ho, wo) is stored at (ho, wo) * out_stride of an outH x outW map
+    int dbg_skip_blo;                // experiment (TTDG_DEBUG_SKIP_BLO=1, wrong results): do not load the lo weight tile
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -73,6 +79,21 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// multicast variants (thread-block cluster along the pixel tiles: the CTAs of a cluster share the weight tile, each loads
+// 1 / CL of it and TMA delivers the slice to every CTA of the cluster at the same shared-memory offset, signalling each
+// CTA's own mbarrier - one L2 read feeds CL SMs)
+__device__ __forceinline__ void tma_load_3d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // K-major, 128-byte swizzle: 8-row atoms of 1024 bytes (SBO = 64 x 16 B), LBO unused (1), descriptor version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
@@ -86,6 +107,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrives on the mbarrier at the same offset in every CTA of `mask` when the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -196,7 +222,7 @@ struct TcSmem {
 };
 
 // carve the dynamic shared memory, initialise the barriers, allocate TMEM; returns the TMEM base address
-template <class Cfg>
+template <class Cfg, int CL = 1>
 __device__ __forceinline__ uint32_t tc_prologue(TcSmem &sm, unsigned char *raw_smem) {
     sm.tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(raw_smem) + 1023) & ~(uintptr_t)1023);
     sm.full = reinterpret_cast<uint64_t *>(sm.tiles + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -207,7 +233,8 @@ __device__ __forceinline__ uint32_t tc_prologue(TcSmem &sm, unsigned char *raw_s
     sm.tmem_slot = reinterpret_cast<uint32_t *>(sm.tmem_empty + 2);
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); mbar_init(&sm.conv[s], TC_CVT_THREADS); }
+        // empty[s]: one arrival per CTA of the cluster (a slot is refilled by multicast only when every CTA has consumed it)
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], CL); mbar_init(&sm.conv[s], TC_CVT_THREADS); }
         mbar_init(&sm.tmem_full[0], 1); mbar_init(&sm.tmem_full[1], 1);
         mbar_init(&sm.tmem_empty[0], TC_EPI_WARPS); mbar_init(&sm.tmem_empty[1], TC_EPI_WARPS);      // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -219,50 +246,35 @@ __device__ __forceinline__ uint32_t tc_prologue(TcSmem &sm, unsigned char *raw_s
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_barrier();                       // every CTA's barriers exist before a peer multicasts / arrives on them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     return *sm.tmem_slot;
 }
 
-template <class Cfg>
+template <class Cfg, int CL = 1>
 __device__ __forceinline__ void tc_epilogue_end(uint32_t tmem_base) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_barrier();                       // no CTA leaves while a peer may still signal its barriers
     if ((threadIdx.x >> 5) == TC_WARP_MMA) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
     }
 }
 
-// split warps: every k-block, wait for TMA, split the first SPLIT_BYTES of the stage, publish to the MMA warp
-template <class Cfg, int SPLIT_BYTES>
-__device__ __forceinline__ void tc_split_loop(const TcSmem &sm, int KB) {
-    const int t = threadIdx.x - TC_WARP_CVT0 * 32;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int kb = 0; kb < KB; ++kb) {
-        mbar_wait(&sm.full[stage], phase);
-        unsigned char *st = sm.tiles + stage * Cfg::STAGE_BYTES;
-        split_stage<SPLIT_BYTES>(st, st + Cfg::A_BYTES + Cfg::B_BYTES, t);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> tensor-core (async proxy) reads
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.conv[stage])) : "memory");
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-    }
-}
-
 // split warps of the conv kernel: every k-block, wait for TMA, split the A tile into this stage's TMEM columns, publish
 template <class Cfg>
 __device__ __forceinline__ void tc_split_loop_tmem(const TcSmem &sm, uint32_t tmem_base, int KB) {
-    const int t = threadIdx.x - TC_WARP_CVT0 * 32;
+    static_assert(Cfg::STAGES % TC_SPLIT_GROUPS == 0, "a stage always belongs to the same split group");
+    const int tt = threadIdx.x - TC_WARP_CVT0 * 32, group = tt / TC_CVT_THREADS, t = tt % TC_CVT_THREADS;
     const uint32_t lane_base = tmem_base + ((uint32_t)(t & ~31) << 16) + (uint32_t)Cfg::ACC_COLS;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int kb = 0; kb < KB; ++kb) {
-        mbar_wait(&sm.full[stage], phase);
+    for (int kb = group; kb < KB; kb += TC_SPLIT_GROUPS) {
+        const int stage = kb % Cfg::STAGES;
+        mbar_wait(&sm.full[stage], (uint32_t)(kb / Cfg::STAGES) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         split_stage_tmem(sm.tiles + stage * Cfg::STAGE_BYTES, lane_base + (uint32_t)(stage * Cfg::A_COLS), t);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.conv[stage])) : "memory");
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
     }
 }
 
@@ -290,14 +302,16 @@ __device__ __forceinline__ void tc_drain(const TcSmem &sm, uint32_t tmem_base, i
     }
 }
 
-template <int BN_TILE, bool PRECISE>
+template <int BN_TILE, bool PRECISE, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
     using Cfg = TcCfg<BN_TILE, PRECISE>;
     extern __shared__ unsigned char tc_smem_raw[];
     TcSmem sm;
-    const uint32_t tmem_base = tc_prologue<Cfg>(sm, tc_smem_raw);
+    const uint32_t tmem_base = tc_prologue<Cfg, CL>(sm, tc_smem_raw);
+    constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
+    constexpr int SLICE_ROWS = BN_TILE / CL, SLICE_BYTES = SLICE_ROWS * 128;       // this CTA's share of the weight tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // tile coordinates
@@ -316,17 +330,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
             int stage = 0;
             uint32_t phase = 0;
+            const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
             for (int kb = 0; kb < KB; ++kb) {
                 const int tap = kb / p.kslabs, c0 = (kb - tap * p.kslabs) * TC_BK;
                 const int r = tap / p.S, s = tap - r * p.S;
                 const int btap = p.flip ? (p.R - 1 - r) * p.S + (p.S - 1 - s) : tap;
                 mbar_wait(&sm.empty[stage], phase ^ 1);
                 unsigned char *st = sm.tiles + stage * Cfg::STAGE_BYTES;
-                mbar_expect_tx(&sm.full[stage], Cfg::TX_BYTES);
+                mbar_expect_tx(&sm.full[stage], (PRECISE && p.dbg_skip_blo) ? Cfg::TX_BYTES - Cfg::B_BYTES : Cfg::TX_BYTES);
                 if (p.stem) tma_load_4d(st, &tmA, &sm.full[stage], 0, w0, 2 * h0 + r - 3, i0);
                 else tma_load_4d(st, &tmA, &sm.full[stage], c0, (w0 + s - p.pad) * p.in_stride, (h0 + r - p.pad) * p.in_stride, i0);
-                tma_load_3d(st + Cfg::A_BYTES, &tmB, &sm.full[stage], c0, n0, btap);
-                if (PRECISE) tma_load_3d(st + Cfg::A_BYTES + Cfg::B_BYTES, &tmBlo, &sm.full[stage], c0, n0, btap);
+                if (CL == 1) {
+                    tma_load_3d(st + Cfg::A_BYTES, &tmB, &sm.full[stage], c0, n0, btap);
+                    if (PRECISE && !p.dbg_skip_blo) tma_load_3d(st + Cfg::A_BYTES + Cfg::B_BYTES, &tmBlo, &sm.full[stage], c0, n0, btap);
+                } else {                                     // rows [crank * SLICE_ROWS, ...) of the weight tile, to every CTA of the cluster
+                    tma_load_3d_mc(st + Cfg::A_BYTES + crank * SLICE_BYTES, &tmB, &sm.full[stage], c0, n0 + crank * SLICE_ROWS, btap, CL_MASK);
+                    if (PRECISE) tma_load_3d_mc(st + Cfg::A_BYTES + Cfg::B_BYTES + crank * SLICE_BYTES, &tmBlo, &sm.full[stage], c0,
+                                                n0 + crank * SLICE_ROWS, btap, CL_MASK);
+                }
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -362,7 +383,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             umma_tf32(tacc, umma_desc(a + koff), umma_desc(b + koff), idesc, first);
                         }
                     }
-                    umma_commit(&sm.empty[stage]);                           // frees the smem slot when these MMAs retire
+                    if (CL == 1) umma_commit(&sm.empty[stage]);              // frees the smem slot when these MMAs retire
+                    else umma_commit_mc(&sm.empty[stage], CL_MASK);          // ... in every CTA of the cluster
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&sm.tmem_full[buf]);                             // this chunk's accumulator is complete
@@ -400,7 +422,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     }
-    tc_epilogue_end<Cfg>(tmem_base);
+    tc_epilogue_end<Cfg, CL>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------- weight gradient
@@ -425,12 +447,16 @@ struct WgParams {
 template <int BN_TILE, bool PRECISE>
 struct WgCfg {
     static constexpr int A_BYTES = 128 * 128, B_BYTES = BN_TILE * 128;      // 32 pixels x (128 | BN) channels x 4 B
-    static constexpr int STAGE_BYTES = (PRECISE ? 2 : 1) * (A_BYTES + B_BYTES);      // [X | dY | X lo | dY lo]
+    // 3xTF32: X (the A operand) is split into TENSOR MEMORY - its smem tile is only a staging buffer, loaded unswizzled -
+    // and dY is split in place: [X raw | dY hi | dY lo].  (Shared-memory traffic per k-block 224 KB -> 144 KB.)
+    static constexpr int STAGE_BYTES = A_BYTES + (PRECISE ? 2 : 1) * B_BYTES;
     static constexpr int TX_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = PRECISE ? (BN_TILE == 128 ? 3 : 4) : (BN_TILE == 128 ? 6 : 8);
+    static constexpr int STAGES = PRECISE ? (BN_TILE == 128 ? 4 : 6) : (BN_TILE == 128 ? 6 : 8);
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
-    static constexpr int TMEM_COLS = 2 * BN_TILE;
     static constexpr int ACC_COLS = 2 * BN_TILE;
+    static constexpr int A_COLS = 64;                    // TMEM columns of one stage's X operand: 32 pixels hi + 32 lo
+    static constexpr int TMEM_COLS = PRECISE ? 512 : ACC_COLS;
+    static_assert(!PRECISE || ACC_COLS + STAGES * A_COLS <= 512, "TMEM budget");
     static constexpr int EPI_COLS = BN_TILE / 2;
     static constexpr int CHUNK = 8;
 };
@@ -442,6 +468,44 @@ __host__ __device__ __forceinline__ uint64_t umma_desc_mn_hi(uint32_t lbo16, uin
     return ((uint64_t)lbo16 << 16) | ((uint64_t)sbo16 << 32) | ((uint64_t)1 << 46) | ((uint64_t)type << 61);
 }
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint64_t hi) { return (uint64_t)((saddr & 0x3FFFF) >> 4) | hi; }
+
+// split warps of the weight-gradient kernel (3xTF32).  Thread t owns input channel t of the 128-channel tile (= GEMM row =
+// TMEM lane): it gathers its channel's 32 pixels from the unswizzled [32 pixels][32 channels] staging blocks (a warp reads
+// 32 consecutive floats per pixel: conflict-free), splits them and stores hi / lo into this stage's TMEM columns; then all
+// four warps split the dY tile in place (hi) / into the stage's lo buffer.
+template <class Cfg>
+__device__ __forceinline__ void wg_split_loop(const TcSmem &sm, uint32_t tmem_base, int KB) {
+    static_assert(Cfg::STAGES % TC_SPLIT_GROUPS == 0, "a stage always belongs to the same split group");
+    const int tt = threadIdx.x - TC_WARP_CVT0 * 32, group = tt / TC_CVT_THREADS, t = tt % TC_CVT_THREADS;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(t & ~31) << 16) + (uint32_t)Cfg::ACC_COLS;
+    for (int kb = group; kb < KB; kb += TC_SPLIT_GROUPS) {
+        const int stage = kb % Cfg::STAGES;
+        mbar_wait(&sm.full[stage], (uint32_t)(kb / Cfg::STAGES) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        unsigned char *st = sm.tiles + stage * Cfg::STAGE_BYTES;
+        const float *xa = reinterpret_cast<const float *>(st + (t >> 5) * 4096) + (t & 31);
+        const uint32_t trow = lane_base + (uint32_t)(stage * Cfg::A_COLS);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const float x = xa[(half * 16 + q) * 32];
+                uint32_t u;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+                hi[q] = u;
+                lo[q] = __float_as_uint(x - __uint_as_float(u));
+            }
+            tmem_st16(trow + half * 16, hi);
+            tmem_st16(trow + 32 + half * 16, lo);
+        }
+        split_stage<Cfg::B_BYTES>(st + Cfg::A_BYTES, st + Cfg::A_BYTES + Cfg::B_BYTES, t);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> tensor-core (async proxy) reads
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.conv[stage])) : "memory");
+    }
+}
 
 template <int BN_TILE, bool PRECISE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -483,8 +547,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     } else if (warp == TC_WARP_MMA) {
         if (lane == 0) {
             // D = F32, A = B = TF32, both MN-major (bits 15, 16), N = BN_TILE, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN_TILE >> 3) << 17) |
-                                   ((uint32_t)(TC_BM >> 4) << 24);
+            // (3xTF32: X comes from tensor memory, which is K-major by construction - only dY is MN-major)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (PRECISE ? 0u : (1u << 15)) | (1u << 16) |
+                                   ((uint32_t)(BN_TILE >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
@@ -498,14 +563,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                     mbar_wait(PRECISE ? &sm.conv[stage] : &sm.full[stage], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a = smem_u32(sm.tiles + stage * Cfg::STAGE_BYTES), b = a + Cfg::A_BYTES;
-                    const uint32_t alo = b + Cfg::B_BYTES, blo = alo + Cfg::A_BYTES;
+                    const uint32_t blo = b + Cfg::B_BYTES;
+                    const uint32_t ta = tmem_base + (uint32_t)(Cfg::ACC_COLS + stage * Cfg::A_COLS);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {                            // 32 pixels = 4 MMAs of K = 8
                         const uint32_t koff = k * 1024;
-                        umma_tf32(tacc, umma_desc_mn(a + koff, p.desc_hi), umma_desc_mn(b + koff, p.desc_hi), idesc, (kb != ch * Cfg::CHUNK) || k != 0);
+                        const uint32_t first = (kb != ch * Cfg::CHUNK) || k != 0;
                         if (PRECISE) {
-                            umma_tf32(tacc, umma_desc_mn(alo + koff, p.desc_hi), umma_desc_mn(b + koff, p.desc_hi), idesc, 1);
-                            umma_tf32(tacc, umma_desc_mn(a + koff, p.desc_hi), umma_desc_mn(blo + koff, p.desc_hi), idesc, 1);
+                            umma_tf32_ts(tacc, ta + k * 8, umma_desc_mn(b + koff, p.desc_hi), idesc, first);
+                            umma_tf32_ts(tacc, ta + 32 + k * 8, umma_desc_mn(b + koff, p.desc_hi), idesc, 1);
+                            umma_tf32_ts(tacc, ta + k * 8, umma_desc_mn(blo + koff, p.desc_hi), idesc, 1);
+                        } else {
+                            umma_tf32(tacc, umma_desc_mn(a + koff, p.desc_hi), umma_desc_mn(b + koff, p.desc_hi), idesc, first);
                         }
                     }
                     umma_commit(&sm.empty[stage]);
@@ -515,7 +584,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             }
         }
     } else if (warp >= TC_WARP_CVT0) {
-        if (PRECISE) tc_split_loop<Cfg, Cfg::A_BYTES + Cfg::B_BYTES>(sm, KB);
+        if (PRECISE) wg_split_loop<Cfg>(sm, tmem_base, KB);
     } else {
         const int q = warp & 3, col0 = (warp >> 2) * Cfg::EPI_COLS;
         const int row = q * 32 + lane;                                       // input channel inside the tile
@@ -642,15 +711,45 @@ static int make_map(CUtensorMap *m, const float *base, int rank, const cuuint64_
 
 static int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-template <int BN_TILE, bool PRECISE>
-static int launch_tc(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &blo, const TcParams &p, cudaStream_t st) {
+// cluster size along the pixel tiles (TMA multicast of the weight tile): TTDG_TC_CLUSTER = 1 (default) | 2 | 4.
+// Measured on B200 (profiles/r01_summary.md): parity-green at 2 and 4 but not faster - the kernel is not bound by L2 reads.
+static int g_tc_cluster = -1;
+static int tc_cluster_size() {
+    if (g_tc_cluster < 0) {
+        const char *e = getenv("TTDG_TC_CLUSTER");
+        const int v = e ? atoi(e) : 1;
+        g_tc_cluster = (v == 1 || v == 2 || v == 4) ? v : 1;
+    }
+    return g_tc_cluster;
+}
+
+template <int BN_TILE, bool PRECISE, int CL>
+static int launch_tc_cl(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &blo, const TcParams &p, cudaStream_t st) {
     using Cfg = TcCfg<BN_TILE, PRECISE>;
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_TILE, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_TILE, PRECISE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return (int)e;
-    dim3 grid(p.tilesW * p.tilesH * p.tilesI, p.Cout / BN_TILE);
+    const int tiles = p.tilesW * p.tilesH * p.tilesI;
+    // the grid is padded to whole clusters: the extra CTAs run the pipeline on out-of-range pixel coordinates (TMA zero
+    // fill, nothing stored) so that their share of the weight multicast still happens
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((tiles + CL - 1) / CL * CL, p.Cout / BN_TILE);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = CL > 1 ? 1 : 0;
     count_launches(1);
-    conv_tc_kernel<BN_TILE, PRECISE><<<grid, TC_THREADS, Cfg::SMEM, st>>>(a, b, blo, p);
-    return (int)cudaGetLastError();
+    return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN_TILE, PRECISE, CL>, a, b, blo, p);
+}
+
+// cl: cluster size the weight tensor maps were built for (their box holds BN_TILE / cl rows)
+template <int BN_TILE, bool PRECISE>
+static int launch_tc(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &blo, const TcParams &p, cudaStream_t st, int cl = 1) {
+    if (cl == 4) return launch_tc_cl<BN_TILE, PRECISE, 4>(a, b, blo, p, st);
+    if (cl == 2) return launch_tc_cl<BN_TILE, PRECISE, 2>(a, b, blo, p, st);
+    return launch_tc_cl<BN_TILE, PRECISE, 1>(a, b, blo, p, st);
 }
 
 }  // namespace ttdg
@@ -703,7 +802,8 @@ extern "C" int ttdg_wgrad_tc(const float *x, const float *dy, int precise, int N
     const cuuint32_t box[4] = {32, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BI};
     const cuuint32_t xbox[4] = {32, (cuuint32_t)(p.BW * stride), (cuuint32_t)(p.BH * stride), (cuuint32_t)p.BI};
     const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    int rc = make_map(&mx, x, 4, xdims, xbox, sw, stride);
+    // 3xTF32: the X tile is a staging buffer for the split into tensor memory - loaded unswizzled
+    int rc = make_map(&mx, x, 4, xdims, xbox, precise ? CU_TENSOR_MAP_SWIZZLE_NONE : sw, stride);
     if (!rc) rc = make_map(&md, dy, 4, ddims, box, sw);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -764,6 +864,13 @@ extern "C" int ttdg_weight_transpose_split(const float *w, int taps, int Cin, in
     TTDG_LAUNCH_RET();
 }
 
+extern "C" int ttdg_conv_tc_set_cluster(int cl) {
+    if (cl != 1 && cl != 2 && cl != 4) return TTDG_E_ARG;
+    const int prev = ttdg::tc_cluster_size();
+    ttdg::g_tc_cluster = cl;
+    return prev;
+}
+
 extern "C" int ttdg_conv_tc_supported(int Cin, int Cout, int stride) {
     return (Cin % 32 == 0 && Cout % 64 == 0 && stride == 1) ? 1 : 0;
 }
@@ -790,6 +897,7 @@ extern "C" int ttdg_conv_tc(const float *x, const float *wk_hi, const float *wk_
     p.outH = out_stride == 1 ? p.Ho : outH; p.outW = out_stride == 1 ? p.Wo : outW;
     if (out_stride == 2 && ((p.Ho - 1) * 2 >= outH || (p.Wo - 1) * 2 >= outW)) return TTDG_E_ARG;
     p.R = R; p.S = S; p.pad = pad; p.flip = flip; p.kslabs = Cin / TC_BK;
+    { static int skip = -1; if (skip < 0) { const char *e = getenv("TTDG_DEBUG_SKIP_BLO"); skip = (e && e[0] == '1') ? 1 : 0; } p.dbg_skip_blo = skip; }
     if (p.Ho < 1 || p.Wo < 1) return TTDG_E_ARG;
     if (res_mode == 2 && ((p.Ho | p.Wo) & 1)) return TTDG_E_ARG;
     p.BW = pow2_ge(p.Wo) < TC_BM ? pow2_ge(p.Wo) : TC_BM;
@@ -801,13 +909,16 @@ extern "C" int ttdg_conv_tc(const float *x, const float *wk_hi, const float *wk_
     const cuuint32_t abox[4] = {TC_BK, (cuuint32_t)(p.BW * in_stride), (cuuint32_t)(p.BH * in_stride), (cuuint32_t)p.BI};
     const cuuint64_t bdims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(R * S)};
     const int bn_tile = Cout % 128 == 0 ? 128 : 64;
-    const cuuint32_t bbox[3] = {TC_BK, (cuuint32_t)bn_tile, 1};
+    const int tiles = p.tilesW * p.tilesH * p.tilesI;
+    int cl = tc_cluster_size();
+    while (cl > 1 && tiles < 2 * cl) cl >>= 1;              // tiny layers: no point padding the grid
+    const cuuint32_t bbox[3] = {TC_BK, (cuuint32_t)(bn_tile / cl), 1};
     int rc = make_map(&ma, x, 4, adims, abox, CU_TENSOR_MAP_SWIZZLE_128B, in_stride);
     if (!rc) rc = make_map(&mb, wk_hi, 3, bdims, bbox);
     if (!rc && wk_lo) rc = make_map(&mblo, wk_lo, 3, bdims, bbox);
     if (rc) return rc;
     if (!wk_lo) mblo = mb;
     cudaStream_t st = (cudaStream_t)stream;
-    if (wk_lo) return bn_tile == 128 ? launch_tc<128, true>(ma, mb, mblo, p, st) : launch_tc<64, true>(ma, mb, mblo, p, st);
-    return bn_tile == 128 ? launch_tc<128, false>(ma, mb, mblo, p, st) : launch_tc<64, false>(ma, mb, mblo, p, st);
+    if (wk_lo) return bn_tile == 128 ? launch_tc<128, true>(ma, mb, mblo, p, st, cl) : launch_tc<64, true>(ma, mb, mblo, p, st, cl);
+    return bn_tile == 128 ? launch_tc<128, false>(ma, mb, mblo, p, st, cl) : launch_tc<64, false>(ma, mb, mblo, p, st, cl);
 }

@@ -51,6 +51,7 @@ SIGNATURES = {
     "ttdg_preprocess": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, P, P]),
     "ttdg_stem_tc": (c_int, [P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
     "ttdg_conv_tc_supported": (c_int, [c_int, c_int, c_int]),
+    "ttdg_conv_tc_set_cluster": (c_int, [c_int]),
     "ttdg_conv_tc": (c_int, [P, P, P, P, P, P] + [c_int] * 15 + [P, P]),
     "ttdg_wgrad_tc_supported": (c_int, [c_int, c_int, c_int]),
     "ttdg_wgrad_tc": (c_int, [P, P] + [c_int] * 10 + [P, P]),
@@ -63,6 +64,8 @@ SIGNATURES = {
     "ttdg_roi_align": (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
     "ttdg_pixel_shuffle2": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "ttdg_mask_paste": (c_int, [P, c_int, c_int, P, P, c_int, c_int, c_int, c_float, P, P]),
+    "ttdg_mask_gt_stats": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "ttdg_mask_pair_counts": (c_int, [P, P, P, c_int, P, c_int, c_int, P, P]),
     "ttdg_sampler_select": (c_int, [P, P, P, c_int, P, c_int, c_int, P, P, P, P]),
     "ttdg_sampler_gather": (c_int, [P, P, P, c_int, c_int, c_int, P, P, c_int, P, P, P, P]),
     "ttdg_sampler_scatter_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, P, c_int, P, P]),

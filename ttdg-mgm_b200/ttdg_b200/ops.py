@@ -477,3 +477,30 @@ def sample_nodes(features, boxes_per_image, classes_per_image, sample_dist=10):
     nodes, labels = _SamplerGather.apply(plan, *features)
     per_img = [sum(cnt[5 * b:5 * b + 5]) for b in range(B)]
     return list(torch.split(nodes, per_img)), list(torch.split(labels, per_img))
+
+
+# ------------------------------------------------------------------------------------------------ evaluator (counts)
+def mask_gt_stats(gt):
+    """gt: G x H x W uint8 / bool (CUDA) -> int64 [G][5] = {n, sum rows, sum cols, split_y, split_x} (dice_metric.py:227-229)."""
+    _need_cuda(gt)
+    gt = gt.to(torch.uint8).contiguous()
+    G, H, W = gt.shape
+    out = torch.zeros(G, 5, dtype=torch.int64, device=gt.device)
+    check(_C.lib().ttdg_mask_gt_stats(_p(gt), G, H, W, _p(out), _stream()), "mask_gt_stats")
+    return out
+
+
+def mask_pair_counts(pred, gt, pairs, gt_stats):
+    """Per (prediction index, ground-truth index) pair the 4 quadrants x (n11, n10, n01, n00) pixel counts: int64 [n][16]."""
+    _need_cuda(pred, gt, gt_stats)
+    pred = (pred.view(torch.uint8) if pred.dtype == torch.bool else pred.to(torch.uint8)).contiguous()
+    gt = gt.to(torch.uint8).contiguous()
+    H, W = pred.shape[-2:]
+    if tuple(gt.shape[-2:]) != (H, W):
+        raise ValueError("prediction and ground-truth masks differ in size")
+    pt = torch.tensor(list(pairs), dtype=torch.int32, device=pred.device).reshape(-1, 2)
+    if len(pt) and (int(pt[:, 0].max()) >= pred.shape[0] or int(pt[:, 1].max()) >= gt.shape[0] or int(pt.min()) < 0):
+        raise ValueError("pair index out of range")
+    out = torch.zeros(len(pt), 16, dtype=torch.int64, device=pred.device)
+    check(_C.lib().ttdg_mask_pair_counts(_p(pred), _p(gt), _p(pt), len(pt), _p(gt_stats), H, W, _p(out), _stream()), "mask_pair_counts")
+    return out
