@@ -32,12 +32,39 @@ def inference_on_dataset(model, data_loader, evaluator, cfg=None):
 
 class BaselineTrainer:
     @classmethod
+    def _ttt_pass_sharded(cls, cfg, model, optimizer, loader, world_size):
+        """The adaptation pass when images are sharded over ranks.  Shards can differ by one batch and a rank's
+        batch can yield no loss (single graph, mgm:489-490), but the gradient all-reduce is collective: all ranks run
+        max-over-ranks steps; a rank without a loss contributes a zero gradient; a step no rank has a loss for is skipped
+        on all of them (decided by a one-element all-reduce)."""
+        import torch.distributed as dist
+        model.train()
+        dev = next(model.parameters()).device
+        n_local = len(loader) if cfg.TEST.MIN_BATCH_NUM is None else min(len(loader), cfg.TEST.MIN_BATCH_NUM)
+        t = torch.tensor([n_local], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        it = iter(loader)
+        for b in range(int(t.item())):
+            inputs = next(it, None) if b < n_local else None
+            loss = model(inputs, branch="TTT")[0] if inputs is not None else None
+            have = torch.tensor([0 if loss is None else 1], dtype=torch.int64, device=dev)
+            dist.all_reduce(have)
+            if int(have.item()) == 0:
+                continue
+            optimizer.zero_grad()
+            if loss is not None:
+                loss.backward()
+            optimizer.step(world_size)
+
+    @classmethod
     def test(cls, cfg, model, optimizer=None, evaluators=None, data_loaders=None, dataset_dicts=None, world_size=1):
         """cfg needs DATASETS.TEST, TEST.TTT, TEST.MIN_BATCH_NUM, TEST.DICE_THRES (adapteacher/config.py:15-17)."""
         results = OrderedDict()
         for idx, name in enumerate(cfg.DATASETS.TEST):
             loader = data_loaders[name]
-            if cfg.TEST.TTT:                               # pass 1: adaptation, model in train mode (:469-482)
+            if cfg.TEST.TTT and world_size > 1:            # pass 1 on image shards: every rank takes part in every all-reduce
+                cls._ttt_pass_sharded(cfg, model, optimizer, loader, world_size)
+            elif cfg.TEST.TTT:                             # pass 1: adaptation, model in train mode (:469-482)
                 model.train()
                 for b, inputs in enumerate(loader):
                     if cfg.TEST.MIN_BATCH_NUM is not None and b >= cfg.TEST.MIN_BATCH_NUM:

@@ -144,10 +144,22 @@ def metrics_from_counts(counts, split, shape):
     return dice_v, ea_v, float(sm_v)
 
 
+def _gt_mask(ann, h, w):
+    """Ground-truth mask of one annotation: a binary 'mask' array (synthetic data) or COCO polygons rasterised like
+    pycocotools (dice_metric.py:94-108 -> adapteacher/data/build.py:polygon_to_mask)."""
+    if "mask" in ann:
+        return np.asarray(ann["mask"]).astype(bool)
+    from adapteacher.data.build import segmentation_to_mask
+    return segmentation_to_mask(ann["segmentation"], h, w)
+
+
 class DiceEvaluator:
     def __init__(self, dataset_name, thres, dataset_dicts=None, on_device=None):
         self.dataset_name = dataset_name
-        self.dataset_dicts = dataset_dicts if dataset_dicts is not None else []
+        if dataset_dicts is None:                               # the reference: DatasetCatalog.get(dataset_name) (:16)
+            from adapteacher.data.build import DatasetCatalog
+            dataset_dicts = DatasetCatalog.get(dataset_name) if dataset_name in DatasetCatalog or str(dataset_name).startswith("synthetic_") else []
+        self.dataset_dicts = dataset_dicts
         self._by_id = {d["image_id"]: d for d in self.dataset_dicts}     # the reference scans linearly (:29-32)
         self.score_threshold = thres
         # on_device: None = automatically when the predicted masks are CUDA tensors; the masks then stay on the GPU and only
@@ -156,14 +168,14 @@ class DiceEvaluator:
         self._gt_cache = {}
         self.reset()
 
-    def _process_on_device(self, image_id, anns, inst):
+    def _process_on_device(self, image_id, anns, inst, hw=None):
         from ttdg_b200 import ops
         import torch
         masks = inst.pred_masks
         dev = masks.device
         if image_id not in self._gt_cache:                    # ground truth: uploaded once per image, with its centroid split
-            gt = np.stack([np.asarray(a.get("mask", a.get("segmentation"))).astype(np.uint8) for a in anns]) if anns else \
-                np.zeros((0,) + tuple(masks.shape[-2:]), np.uint8)
+            h, w = hw if hw is not None else tuple(masks.shape[-2:])
+            gt = np.stack([_gt_mask(a, h, w).astype(np.uint8) for a in anns]) if anns else np.zeros((0, h, w), np.uint8)
             gt_d = torch.from_numpy(gt).to(dev)
             self._gt_cache[image_id] = (gt_d, ops.mask_gt_stats(gt_d), [a["category_id"] for a in anns])
         gt_d, stats_d, gt_cls = self._gt_cache[image_id]
@@ -189,13 +201,14 @@ class DiceEvaluator:
             anns = self._by_id[inp["image_id"]]["annotations"]
             inst = out["instances"]
             if self.on_device or (self.on_device is None and inst.pred_masks.is_cuda):
-                self._process_on_device(inp["image_id"], anns, inst)
+                self._process_on_device(inp["image_id"], anns, inst, (inp["height"], inp["width"]) if "height" in inp else None)
                 continue
             masks = inst.pred_masks.cpu().numpy()                       # device -> host, as in the reference (:34-36)
             classes = inst.pred_classes.cpu().numpy()
             scores = inst.scores.cpu().numpy()
             keep = scores >= self.score_threshold
-            gts = [(a["category_id"], np.asarray(a.get("mask", a.get("segmentation"))).astype(bool)) for a in anns]
+            h, w = (inp["height"], inp["width"]) if "height" in inp else masks.shape[-2:]
+            gts = [(a["category_id"], _gt_mask(a, h, w)) for a in anns]
             for c, m in zip(classes[keep], masks[keep]):
                 best = [0.0, 0.0, 0.0]
                 for gc, gm in gts:
@@ -208,5 +221,10 @@ class DiceEvaluator:
                 self.sm_scores.append(best[2] * 100)
 
     def evaluate(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:      # image shards -> all ranks' scores
+            parts = [None] * dist.get_world_size()
+            dist.all_gather_object(parts, (self.dice_scores, self.ea_scores, self.sm_scores))
+            self.dice_scores, self.ea_scores, self.sm_scores = ([v for p in parts for v in p[k]] for k in range(3))
         return {"Dice Coefficient": np.mean(self.dice_scores), "Enhanced Alignment Metric": np.mean(self.ea_scores),
                 "Structural Similarity Metric": np.mean(self.sm_scores)}

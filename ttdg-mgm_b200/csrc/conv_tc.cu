@@ -394,6 +394,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (PRECISE) tc_split_loop_tmem<Cfg>(sm, tmem_base, KB);              // activations only: the weight copies are pre-split
     } else {
         // ===================== epilogue: warps 0..7; warp w owns TMEM lanes 32 * (w % 4) .. and column half w / 4
+        // (each thread stores its pixel's EPI_COLS channels = 128 / 256 contiguous bytes.  A shared-memory-staged variant
+        // with one warp per pixel - 512-byte coalesced loads and stores - was measured on B200 and is SLOWER here (the
+        // 64 -> 256 1x1 layer with residual: 234 vs 183 us): the extra smem round trip and barrier cost more than the
+        // L2 write-combining of the row stores loses.  The weight-gradient kernel keeps the staged form for its atomics.)
         const int q = warp & 3, col0 = (warp >> 2) * Cfg::EPI_COLS;
         const int row = q * 32 + lane;                                       // GEMM row inside the tile = TMEM lane
         const int bi = row / (p.BH * p.BW), rem = row - bi * p.BH * p.BW;
@@ -590,10 +594,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int row = q * 32 + lane;                                       // input channel inside the tile
         float acc[Cfg::EPI_COLS];
         tc_drain<Cfg>(sm, tmem_base, KB, q, col0, acc);
-        if (KB > 0) {
-            float *dst = p.dw + ((size_t)tap * p.Cin + ci0 + row) * p.Cout + n0 + col0;
+        // staged like the conv epilogue: thread = input-channel row in phase 1, a warp per row in phase 2, so that each
+        // reduction instruction adds 32 consecutive floats of dW (was: 32 rows Cout * 4 bytes apart)
+        constexpr int PITCH = BN_TILE + 4;
+        float *stg = reinterpret_cast<float *>(sm.tiles);
+        {
+            float *srow = stg + row * PITCH + col0;
 #pragma unroll
-            for (int j = 0; j < Cfg::EPI_COLS; ++j) atomicAdd(dst + j, acc[j]);
+            for (int jj = 0; jj < Cfg::EPI_COLS; jj += 4)
+                *reinterpret_cast<float4 *>(srow + jj) = make_float4(acc[jj], acc[jj + 1], acc[jj + 2], acc[jj + 3]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
+        if (KB > 0) {
+            for (int r2 = warp; r2 < TC_BM; r2 += TC_EPI_WARPS) {
+                float *dst = p.dw + ((size_t)tap * p.Cin + ci0 + r2) * p.Cout + n0;
+#pragma unroll
+                for (int c = 0; c < BN_TILE; c += 32) atomicAdd(dst + c + lane, stg[r2 * PITCH + c + lane]);
+            }
         }
     }
     tc_epilogue_end<Cfg>(tmem_base);

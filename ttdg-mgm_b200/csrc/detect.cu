@@ -161,11 +161,12 @@ __device__ __forceinline__ int roi_level(float x0, float y0, float x1, float y1)
     return (int)lv - 2;
 }
 
-// grid: (pooled * pooled, n_rois); block: C / 4 threads (float4 over channels).  rois: [n][5] = {image, x0, y0, x1, y1}
-__global__ void __launch_bounds__(64)
+// grid: n_rois CTAs of 256 threads = 4 bins in flight x 64 channel quads (float4 over channels); every thread walks the
+// bins bin0, bin0 + 4, ...  (One CTA per (roi, bin) - 392 000 CTAs of 64 threads for 8000 rois at 7 x 7 - was bound by the
+// CTA launch rate: 0.83 ms per call.)  rois: [n][5] = {image, x0, y0, x1, y1}
+__global__ void __launch_bounds__(256)
 roi_align_kernel(Pyr4 pyr, const float *__restrict__ rois, int C, int pooled, float *__restrict__ out) {
-    const int bin = blockIdx.x, ridx = blockIdx.y;
-    const int ph = bin / pooled, pw = bin - ph * pooled;
+    const int ridx = blockIdx.x;
     const float *r = rois + (size_t)ridx * 5;
     const int img = (int)r[0];
     const int lvl = roi_level(r[1], r[2], r[3], r[4]);
@@ -177,9 +178,11 @@ roi_align_kernel(Pyr4 pyr, const float *__restrict__ rois, int C, int pooled, fl
     const float bh = rh / (float)pooled, bw = rw / (float)pooled;
     const int gh = (int)ceilf(rh / (float)pooled), gw = (int)ceilf(rw / (float)pooled);
     const float count = fmaxf((float)(gh * gw), 1.f);
-    const int c = threadIdx.x * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < C) {
+    const int c = (threadIdx.x & 63) * 4;
+    if (c < C)
+    for (int bin = threadIdx.x >> 6; bin < pooled * pooled; bin += 4) {
+        const int ph = bin / pooled, pw = bin - ph * pooled;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int iy = 0; iy < gh; ++iy) {
             float y = rsh + ph * bh + ((float)iy + .5f) * bh / (float)gh;
             for (int ix = 0; ix < gw; ++ix) {
@@ -307,7 +310,7 @@ extern "C" int ttdg_roi_align(const float *const *feat_ptrs_h, const int32_t *lv
     Pyr4 pyr;
     for (int l = 0; l < 4; ++l) { pyr.p[l] = feat_ptrs_h[l]; pyr.h[l] = lvl_hw_h[2 * l]; pyr.w[l] = lvl_hw_h[2 * l + 1]; }
     count_launches(1);
-    roi_align_kernel<<<dim3(pooled * pooled, n_rois), 64, 0, (cudaStream_t)stream>>>(pyr, rois, C, pooled, out);
+    roi_align_kernel<<<n_rois, 256, 0, (cudaStream_t)stream>>>(pyr, rois, C, pooled, out);
     TTDG_LAUNCH_RET();
 }
 

@@ -1,0 +1,157 @@
+#!/usr/bin/env python
+"""Entry point; mirrors the ``--eval-only`` path of the reference's train_net.py:24-84:
+
+    python ttdg-mgm_b200/train_net.py --eval-only --config-file <yaml> [--num-gpus N] MODEL.WEIGHTS <pth> [KEY VAL ...]
+
+setup (yaml with ``_BASE_`` inheritance + ``add_ateacher_config`` defaults + command-line overrides) -> build the
+meta-architecture named by ``MODEL.META_ARCHITECTURE`` -> ``DetectionCheckpointer(model).resume_or_load(MODEL.WEIGHTS)``
+-> ``Trainer.test(cfg, model, optimizer)`` (test-time adaptation on every batch, then evaluation with the adapted
+weights) -> results appended to ``OUTPUT_DIR/result_ap.txt``.  Training (no ``--eval-only``) is out of scope.
+With ``--num-gpus N`` it re-launches itself under torch.distributed.run, one process per GPU; images shard over ranks
+and the adaptation gradients are all-reduced (NCCL)."""
+import argparse
+import ast
+import json
+import os
+import sys
+from types import SimpleNamespace
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+if HERE not in sys.path:
+    sys.path.insert(0, HERE)
+
+import torch  # noqa: E402
+import yaml  # noqa: E402
+
+from adapteacher.checkpoint import DetectionCheckpointer  # noqa: E402
+from adapteacher.config import add_ateacher_config  # noqa: E402
+from adapteacher.data import build_detection_test_loader  # noqa: E402
+from adapteacher.engine.trainer import BaselineTrainer  # noqa: E402
+
+META_ARCH_REGISTRY = {}
+
+
+def _registry():
+    if not META_ARCH_REGISTRY:
+        from adapteacher.modeling.meta_arch.rcnn import DAobjTwoStagePseudoLabGeneralizedRCNN
+        META_ARCH_REGISTRY["DAobjTwoStagePseudoLabGeneralizedRCNN"] = DAobjTwoStagePseudoLabGeneralizedRCNN
+    return META_ARCH_REGISTRY
+
+
+def _literal(v):
+    if isinstance(v, str):
+        try:
+            return ast.literal_eval(v)                          # yacs: '("a", "b")' -> tuple, '0.5' -> float
+        except (ValueError, SyntaxError):
+            return v
+    return v
+
+
+def _merge(ns, d):
+    for k, v in d.items():
+        if isinstance(v, dict):
+            sub = getattr(ns, k, None)
+            if not isinstance(sub, SimpleNamespace):
+                sub = SimpleNamespace()
+                setattr(ns, k, sub)
+            _merge(sub, v)
+        else:
+            setattr(ns, k, _literal(v))
+
+
+def _load_yaml(path):
+    with open(path) as f:
+        d = yaml.safe_load(f) or {}
+    base = d.pop("_BASE_", None)
+    out = _load_yaml(os.path.join(os.path.dirname(path), base)) if base else {}
+
+    def deep(a, b):
+        for k, v in b.items():
+            if isinstance(v, dict) and isinstance(a.get(k), dict):
+                deep(a[k], v)
+            else:
+                a[k] = v
+    deep(out, d)
+    return out
+
+
+def setup(args):
+    cfg = add_ateacher_config()
+    cfg.MODEL = SimpleNamespace(WEIGHTS="", META_ARCHITECTURE="DAobjTwoStagePseudoLabGeneralizedRCNN",
+                                ROI_HEADS=SimpleNamespace(NUM_CLASSES=2))
+    cfg.INPUT = SimpleNamespace(FORMAT="BGR", MIN_SIZE_TEST=800, MAX_SIZE_TEST=1333)
+    cfg.OUTPUT_DIR = "./output"
+    if args.config_file:
+        _merge(cfg, _load_yaml(args.config_file))
+    opts = list(args.opts)
+    if len(opts) % 2:
+        raise ValueError("overrides must be KEY VALUE pairs")
+    for k, v in zip(opts[::2], opts[1::2]):
+        node = cfg
+        *path, leaf = k.split(".")
+        for pth in path:
+            if not hasattr(node, pth):
+                setattr(node, pth, SimpleNamespace())
+            node = getattr(node, pth)
+        setattr(node, leaf, _literal(v))
+    return cfg
+
+
+class Trainer(BaselineTrainer):
+    @classmethod
+    def build_model(cls, cfg):
+        arch = _registry()[cfg.MODEL.META_ARCHITECTURE]         # KeyError = unknown META_ARCHITECTURE, like the d2 registry
+        return arch(cfg.MODEL.ROI_HEADS.NUM_CLASSES, getattr(cfg.SEMISUPNET, "DIS_TYPE", "p2")).to("cuda")
+
+    @classmethod
+    def build_optimizer(cls, cfg, model):
+        from ttdg_b200.optim import FlatSGD
+        s = cfg.SOLVER
+        return FlatSGD(model.adapted_parameters(), lr=s.BASE_LR, momentum=getattr(s, "MOMENTUM", 0.9),
+                       weight_decay=getattr(s, "WEIGHT_DECAY", 1e-4))
+
+    @classmethod
+    def build_test_loader(cls, cfg, dataset_name):
+        return build_detection_test_loader(cfg, dataset_name)
+
+
+def main(args):
+    cfg = setup(args)
+    if not args.eval_only:
+        raise NotImplementedError("only --eval-only (test-time adaptation + evaluation) is implemented")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        torch.distributed.init_process_group("nccl")
+    model = Trainer.build_model(cfg)
+    DetectionCheckpointer(model, save_dir=cfg.OUTPUT_DIR).resume_or_load(cfg.MODEL.WEIGHTS, resume=args.resume)
+    loaders = {name: Trainer.build_test_loader(cfg, name) for name in cfg.DATASETS.TEST}
+    res = Trainer.test(cfg, model, Trainer.build_optimizer(cfg, model), data_loaders=loaders, world_size=world)
+    if world == 1 or torch.distributed.get_rank() == 0:
+        print(res)
+        os.makedirs(cfg.OUTPUT_DIR, exist_ok=True)
+        with open(os.path.join(cfg.OUTPUT_DIR, "result_ap.txt"), "a") as f:
+            f.write("loading data from: " + str(cfg.MODEL.WEIGHTS) + "\n")
+            f.write(json.dumps({k: {m: float(v) for m, v in d.items()} for k, d in res.items()}) + "\n")
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return res
+
+
+def default_argument_parser():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config-file", default="", metavar="FILE")
+    ap.add_argument("--config", dest="config_file", help=argparse.SUPPRESS)       # the README's spelling (README.md:93-94)
+    ap.add_argument("--resume", action="store_true")
+    ap.add_argument("--eval-only", action="store_true")
+    ap.add_argument("--num-gpus", type=int, default=1)
+    ap.add_argument("opts", nargs=argparse.REMAINDER, default=[])
+    return ap
+
+
+if __name__ == "__main__":
+    args = default_argument_parser().parse_args()
+    if args.num_gpus > 1 and "WORLD_SIZE" not in os.environ:       # d2 launch(): one process per GPU
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.num_gpus}",
+                                   "--master-addr", "127.0.0.1", "--master-port", "29511"] + sys.argv)
+    main(args)
