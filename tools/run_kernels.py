@@ -171,6 +171,28 @@ elif what == "conv":
             ms += e0.elapsed_time(e1) / reps
         fl = 2.0 * N * H * W * Cin * Cout * R * R
         print("conv %s: %.1f us, %.1f TFLOP/s fp32-equivalent" % ((N, H, W, Cin, Cout, R), ms * 1e3, fl / (ms * 1e-3) / 1e12))
+elif what == "gagm_fixed":
+    # GA-GM solver alone on fixed seeded inputs (init affinity state: ~212 iterations, 200 of them Hungarian), CUDA events
+    from adapteacher.modeling.GModule.multi_graph_matching import MGM3_unsup
+    m = MGM3_unsup(2, 32).to(dev)
+    m.load_state_dict(synth.mgm_unsup_state(0))
+    m.train()
+    for sizes, seed in (((33, 34, 33, 33, 46, 30, 34, 38), 77), ((30, 31, 29, 32, 28, 30, 31, 32), 5), ((40, 44, 46, 41, 39, 45, 43, 42), 9)):
+        nodes, labels, _ = synth.mgm_inputs(sizes, seed)
+        U = synth.universe(0).to(dev)
+        with torch.no_grad():
+            m([n.to(dev) for n in nodes], [l.to(dev) for l in labels], U)
+        aux = m.last_aux
+        ms = 0.0
+        for _ in range(reps):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            U2, info = ops.gagm_solve(aux["A"], aux["Wds"], aux["U0"], list(sizes), return_info=True)
+            e1.record(); torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1) / reps
+        inf = info.tolist()
+        print("gagm_fixed sizes %s: %.3f ms, iterations %d (sinkhorn %d, hungarian %d), %.1f us / hungarian iteration incl. everything, graph-0 LAP steps %d"
+              % (sizes, ms, inf[0], inf[1], inf[2], 1e3 * ms / max(inf[2], 1), inf[5]))
 elif what == "busy":
     # hot (not cold-cache) per-kernel device time of the full step and the GPU-busy fraction, from CUPTI via torch.profiler
     sys.path.insert(0, ROOT)
