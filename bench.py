@@ -144,6 +144,65 @@ def sinkhorn_roofline(device, n=1024, batch=128, iters=50, launches=5, warm=3):
             "note": "matrix stays in distributed shared memory across iterations: DRAM traffic is ~2 passes, not 2*iters"}
 
 
+# ------------------------------------------------------------------------------------------------ tensor roofline of the step
+def conv_roofline(step_fn, steps=2):
+    """The step's dominant kernel family (conv_tc_kernel + wgrad_tc_kernel, ~45 % of the device time): CUDA events around
+    every launch of `steps` extra, untimed steps.  `achieved` = ALGORITHMIC flops (2 * pixels * Cin * Cout * taps: what an
+    fp32 convolution needs) / summed kernel time; in the 3xTF32 parity mode the tensor pipe executes three
+    TF32 MMAs per product, reported as `mma_tflops`.  `peak` = half of the measured dense bf16 rate (TF32 runs at half the
+    16-bit rate; sustained figure: the kernels run inside a long step)."""
+    from ttdg_b200 import _C
+    lib = _C.lib()
+    rec = []
+
+    class Timed:
+        def __init__(self, name, fn):
+            self.name, self.fn = name, fn
+
+        def __call__(self, *a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = self.fn(*a)
+            e1.record()
+            ints = [int(v) for v in a if isinstance(v, int) and not isinstance(v, bool)]
+            rec.append((self.name, ints, e0, e1))
+            return rc
+
+    proxy = type("LibProxy", (), {})()
+    for name in _C.SIGNATURES:
+        fn = getattr(lib, name)
+        setattr(proxy, name, Timed(name, fn) if name in ("ttdg_conv_tc", "ttdg_wgrad_tc", "ttdg_stem_tc") else fn)
+    _C._lib = proxy
+    try:
+        for _ in range(steps):
+            step_fn()
+        torch.cuda.synchronize()
+    finally:
+        _C._lib = lib
+    flops = ms = 0.0
+    for name, a, e0, e1 in rec:
+        if name == "ttdg_conv_tc":          # res_mode, relu, flip, N, H, W, Cin, Cout, R, S, pad, in_stride, ...
+            N, H, W, Cin, Cout, R, S, pad, stride = a[3:12]
+        elif name == "ttdg_wgrad_tc":       # precise, N, H, W, Cin, Cout, R, S, stride, pad
+            N, H, W, Cin, Cout, R, S, stride, pad = a[1:10]
+        else:                               # stem: Wp, relu, N, H, W  (7 x 7 stride 2, 3 -> 64)
+            N, H, W = a[2:5]
+            Cin, Cout, R, S, pad, stride = 3, 64, 7, 7, 3, 2
+        Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+        flops += 2.0 * N * Ho * Wo * Cin * Cout * R * S
+        ms += e0.elapsed_time(e1)
+    pk, how = peaks()
+    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"]) / 2.0
+    mult = 3 if os.environ.get("TTDG_CONV", "tf32x3") == "tf32x3" else 1
+    achieved = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "conv_tc_kernel + wgrad_tc_kernel (tcgen05 kind::tf32)", "achieved": round(achieved, 1),
+            "mma_tflops": round(achieved * mult, 1), "peak": round(peak, 1), "peak_source": how + " dense bf16 (sustained) / 2 = TF32",
+            "unit": "TFLOP/s", "frac": round(achieved / peak, 3), "frac_mma": round(achieved * mult / peak, 3), "traffic": None,
+            "launches_per_step": len(rec) // steps, "ms_per_step": round(ms / steps, 3),
+            "algorithmic_tflop_per_step": round(flops / steps / 1e12, 3),
+            "note": "3xTF32 parity mode: 3 TF32 MMAs per fp32-grade product; frac = algorithmic, frac_mma = tensor-pipe work"}
+
+
 # ------------------------------------------------------------------------------------------------ CPU leg (oracle port)
 def cpu_baseline(images_u8, steps):
     """The reference's algorithm on the host cores: oracle/ttt_port.Trainer (TTT step + eval pass) on `images_u8`."""
@@ -278,6 +337,7 @@ def main():
     e2e_val = IMAGES_PER_GPU * world * args.steps / (float(t.item()) * 1e-3)
     clk = clocks.stop()
 
+    roof_conv = conv_roofline(lambda: step(inputs_dev, False))           # every rank runs it (the all-reduce inside is collective)
     if rank == 0:
         roof = sinkhorn_roofline(device)
         n_cpu = 2
@@ -292,7 +352,7 @@ def main():
                         "last_loss": last[0], "mask_pixels": last[1]},
                 "gpu_launches": int(launches), "skipped_steps": stats["skipped"],
                 "gagm": {"iterations": info[0], "lap_calls": info[3], "graphs": len(aux["sizes"]), "nodes": int(sum(aux["sizes"]))},
-                "clocks": clk, "roofline": roof,
+                "clocks": clk, "roofline": roof, "roofline_step_dominant": roof_conv,
                 "cpu_baseline": ({"value": round(cpu_val, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                   "sample": f"1 step of {n_cpu} of the 8 images (TTT step + eval pass) with the oracle port on torch "
                                             f"CPU, {cpu_dt:.1f} s"} if world == 1 else None)}

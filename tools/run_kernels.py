@@ -225,6 +225,22 @@ elif what == "busy":
     busy = sum(tot.values())
     print("wall ms/step %.2f (under the profiler), device busy ms/step %.2f (%.0f%%), launches/step %d" %
           (wall, busy, 100 * busy / wall, sum(cnt.values()) // reps))
+    if len(sys.argv) > 3 and sys.argv[3] == "gaps":
+        # idle time of the device between consecutive kernels, attributed to the kernel that FOLLOWS the gap
+        evs = sorted(((e.time_range.start, e.time_range.end, e.name.split("(")[0][:70]) for e in prof.events()
+                      if str(e.device_type).endswith("CUDA")), key=lambda t: t[0])
+        gap_after, gap_n = collections.defaultdict(float), collections.Counter()
+        end = evs[0][1]
+        for (st, en, name), prev in zip(evs[1:], evs[:-1]):
+            g = st - end
+            if g > 2.0:
+                key = "%s  <-after-  %s" % (name, prev[2])
+                gap_after[key] += g / reps / 1e3; gap_n[key] += 1
+            end = max(end, en)
+        print("idle ms/step %.2f in %d gaps > 2 us" % (sum(gap_after.values()), sum(gap_n.values()) // reps))
+        print("gap_ms_per_step,gaps_per_step,kernel_after_gap <-after- kernel_before")
+        for k, v in sorted(gap_after.items(), key=lambda x: -x[1])[:40]:
+            print("%.3f,%.1f,%s" % (v, gap_n[k] / reps, k))
     print("kernel,launches_per_step,ms_per_step,share_pct")
     for k, v in sorted(tot.items(), key=lambda x: -x[1])[:45]:
         print('"%s",%d,%.3f,%.1f' % (k, cnt[k] // reps, v, 100 * v / busy))

@@ -134,10 +134,19 @@ class _ConvFn(torch.autograd.Function):
                 Ho, Wo = g.shape[1], g.shape[2]
                 g_res = torch.zeros(N, Ho // 2, Wo // 2, Cout, dtype=torch.float32, device=g.device)
                 check(L.ttdg_resample2(_p(d_pre), _p(g_res), N, Ho // 2, Wo // 2, Cout, 2, s), "upsample_bwd")
+        # Weight / bias gradients are ACCUMULATED by their kernels (atomics), so when the parameter already owns a gradient
+        # buffer - the views of FlatSGD's flat bucket, zeroed by zero_grad() - they add straight into it and autograd gets
+        # None: no zero-filled temporary and no separate "grad += temporary" pass per parameter (132 launches per step).
+        def _acc(param):
+            gr = getattr(param, "grad", None) if param is not None else None
+            return gr if (gr is not None and gr.is_contiguous() and gr.dtype == torch.float32 and gr.data_ptr() % 16 == 0) else None
+        owner = ctx.owner
         g_bias = None
         if has_bias and ctx.needs_input_grad[2]:
-            g_bias = torch.zeros(Cout, dtype=torch.float32, device=g.device)
-            check(L.ttdg_bias_grad(_p(d_pre), d_pre.numel() // Cout, Cout, _p(g_bias), s), "bias_grad")
+            acc_b = _acc(owner.bias if owner is not None else None)
+            gb = acc_b if acc_b is not None else torch.zeros(Cout, dtype=torch.float32, device=g.device)
+            check(L.ttdg_bias_grad(_p(d_pre), d_pre.numel() // Cout, Cout, _p(gb), s), "bias_grad")
+            g_bias = None if acc_b is not None else gb
         if scale is not None:                              # through the FrozenBN scale
             d_conv = torch.empty_like(d_pre)
             check(L.ttdg_relu_bn_bwd(_p(d_pre), None, _p(scale), Cout, d_pre.numel(), _p(d_conv), s), "bn_bwd")
@@ -154,12 +163,16 @@ class _ConvFn(torch.autograd.Function):
             else:
                 check(L.ttdg_conv_dgrad(_p(d_conv), _p(w), N, H, W, Cin, Cout, R, S, stride, pad, _p(g_x), s), "conv_dgrad")
         if ctx.needs_input_grad[1]:
-            g_w = torch.zeros_like(w)
+            acc_w = _acc(owner.weight if owner is not None else None)
+            if acc_w is not None and acc_w.shape != w.shape:
+                acc_w = None
+            gw = acc_w if acc_w is not None else torch.zeros_like(w)
             if WGRAD_TC[0] and Cin % 128 == 0 and _tc_ok(Cin, Cout, stride, R, pad):
-                check(L.ttdg_wgrad_tc(_p(x), _p(d_conv), int(CONV_MODE[0] == "tf32x3"), N, H, W, Cin, Cout, R, S, stride, pad, _p(g_w), s),
+                check(L.ttdg_wgrad_tc(_p(x), _p(d_conv), int(CONV_MODE[0] == "tf32x3"), N, H, W, Cin, Cout, R, S, stride, pad, _p(gw), s),
                       "wgrad_tc")
             else:
-                check(L.ttdg_conv_wgrad(_p(x), _p(d_conv), N, H, W, Cin, Cout, R, S, stride, pad, _p(g_w), s), "conv_wgrad")
+                check(L.ttdg_conv_wgrad(_p(x), _p(d_conv), N, H, W, Cin, Cout, R, S, stride, pad, _p(gw), s), "conv_wgrad")
+            g_w = None if acc_w is not None else gw
         return g_x, g_w, g_bias, g_res, None, None, None, None, None, None, None, None, None
 
 
@@ -485,11 +498,11 @@ class RPN(nn.Module):
         keep, n_keep = nms_sorted(b_sorted, cats, self.nms_thresh, self.post_topk)          # all images, one launch pair
         ak = torch.arange(self.post_topk, device=dev).unsqueeze(0)
         counts = ((keep < n_valid.unsqueeze(1)) & (ak < n_keep.unsqueeze(1))).sum(1).cpu().tolist()      # one host sync per batch
-        out = []
-        for n in range(N):
-            kk = keep[n, :counts[n]].long()
-            out.append((b_sorted[n][kk], s_sorted[n][kk]))
-        return out
+        # one padded gather for the whole batch (the tail of keep is zero-filled: a valid index), per-image results are views
+        kk = keep[:, :max(counts)].long() if max(counts) > 0 else keep[:, :0].long()
+        b_sel = torch.gather(b_sorted, 1, kk.unsqueeze(-1).expand(-1, -1, 4))
+        s_sel = torch.gather(s_sorted, 1, kk)
+        return [(b_sel[n, :counts[n]], s_sel[n, :counts[n]]) for n in range(N)]
 
 
 class BoxHead(nn.Module):
@@ -529,8 +542,12 @@ def roi_align(feats4, rois, pooled):
 
 def _rois(boxes_per_image):
     dev = boxes_per_image[0].device
-    idx = torch.cat([torch.full((len(b), 1), float(i), device=dev) for i, b in enumerate(boxes_per_image)])
-    return torch.cat([idx, torch.cat(boxes_per_image)], dim=1).contiguous()
+    counts = [len(b) for b in boxes_per_image]
+    if len(set(counts)) == 1:                               # the usual case: same count per image, no host -> device copy
+        idx = torch.arange(len(counts), dtype=torch.float32, device=dev).repeat_interleave(counts[0])
+    else:
+        idx = torch.repeat_interleave(torch.arange(len(counts), dtype=torch.float32), torch.tensor(counts)).to(dev)
+    return torch.cat([idx.unsqueeze(1), torch.cat(boxes_per_image)], dim=1).contiguous()
 
 
 class ROIHeads(nn.Module):
@@ -567,13 +584,16 @@ class ROIHeads(nn.Module):
         # pad every image to the same candidate count (invalid candidates: score -1, unique negative category)
         B = len(props)
         nmax = max(len(p) for p in props) * K
-        cs = torch.full((B, nmax), -1.0, dtype=torch.float32, device=dev)
-        cb = torch.zeros(B, nmax, 4, dtype=torch.float32, device=dev)
-        o = 0
-        for i, p in enumerate(props):
-            n = len(p) * K
-            cs[i, :n], cb[i, :n] = cand_s[o:o + n], cand_b[o:o + n]
-            o += n
+        if all(len(p) * K == nmax for p in props):          # same proposal count everywhere: the padded layout is a view
+            cs, cb = cand_s.view(B, nmax), cand_b.view(B, nmax, 4)
+        else:
+            cs = torch.full((B, nmax), -1.0, dtype=torch.float32, device=dev)
+            cb = torch.zeros(B, nmax, 4, dtype=torch.float32, device=dev)
+            o = 0
+            for i, p in enumerate(props):
+                n = len(p) * K
+                cs[i, :n], cb[i, :n] = cand_s[o:o + n], cand_b[o:o + n]
+                o += n
         order = torch.argsort(cs, dim=1, descending=True, stable=True)
         ss = torch.gather(cs, 1, order)
         bb = torch.gather(cb, 1, order.unsqueeze(-1).expand(-1, -1, 4))
@@ -584,11 +604,11 @@ class ROIHeads(nn.Module):
         keep, n_keep = nms_sorted(bb, cats, self.nms_thresh, self.topk)
         ak = torch.arange(self.topk, device=dev).unsqueeze(0)
         counts = ((keep < n_valid.unsqueeze(1)) & (ak < n_keep.unsqueeze(1))).sum(1).cpu().tolist()      # one host sync per batch
-        out = []
-        for i in range(B):
-            kk = keep[i, :counts[i]].long()
-            out.append((bb[i][kk], ss[i][kk], cc[i][kk].long()))
-        return out
+        kk = keep[:, :max(counts)].long() if max(counts) > 0 else keep[:, :0].long()
+        b_sel = torch.gather(bb, 1, kk.unsqueeze(-1).expand(-1, -1, 4))
+        s_sel = torch.gather(ss, 1, kk)
+        c_sel = torch.gather(cc, 1, kk).long()
+        return [(b_sel[i, :counts[i]], s_sel[i, :counts[i]], c_sel[i, :counts[i]]) for i in range(B)]
 
     @torch.no_grad()
     def forward_mask(self, feats, dets, out_size, image_size):
@@ -610,18 +630,30 @@ class ROIHeads(nn.Module):
             y = torch.empty(R, 28, 28, 256, dtype=torch.float32, device=dev)
             check(L.ttdg_pixel_shuffle2(_p(y4), R, 14, 14, 256, _p(y), _stream()), "pixel_shuffle")
             logits = self.mask_head.predictor(y)                         # R x 28 x 28 x 4 (K used)
-        o = 0
-        for b, s, c in dets:
-            n = len(b)
-            bs = b * torch.tensor([sx, sy, sx, sy], device=dev)
-            bs = torch.stack((bs[:, 0].clamp(0, W), bs[:, 1].clamp(0, H), bs[:, 2].clamp(0, W), bs[:, 3].clamp(0, H)), dim=1).contiguous()
-            masks = torch.zeros(n, H, W, dtype=torch.uint8, device=dev)
-            if n:
-                lg = logits[o:o + n]
-                check(L.ttdg_mask_paste(_p(lg), lg.shape[-1], 28, _p(bs), _p(c.contiguous()), n, H, W, 0.5, _p(masks), _stream()), "mask_paste")
-            o += n
+        # detector_postprocess for the whole batch at once (one paste launch, one host sync); per-image results are views
+        counts = [len(b) for b in boxes]
+        bs = torch.cat(boxes) if R else torch.zeros(0, 4, dtype=torch.float32, device=dev)
+        if sx != 1.0 or sy != 1.0:
+            bs = torch.stack((bs[:, 0] * sx, bs[:, 1] * sy, bs[:, 2] * sx, bs[:, 3] * sy), dim=1)
+        bs = torch.stack((bs[:, 0].clamp(0, W), bs[:, 1].clamp(0, H), bs[:, 2].clamp(0, W), bs[:, 3].clamp(0, H)), dim=1).contiguous()
+        scores = torch.cat([d[1] for d in dets]) if R else torch.zeros(0, dtype=torch.float32, device=dev)
+        classes = (torch.cat([d[2] for d in dets]) if R else torch.zeros(0, dtype=torch.int64, device=dev)).contiguous()
+        masks = torch.zeros(R, H, W, dtype=torch.uint8, device=dev)
+        all_kept = True
+        if R:
+            check(L.ttdg_mask_paste(_p(logits), logits.shape[-1], 28, _p(bs), _p(classes), R, H, W, 0.5, _p(masks), _stream()), "mask_paste")
             keep = ((bs[:, 2] - bs[:, 0]) > 0) & ((bs[:, 3] - bs[:, 1]) > 0)        # Boxes.nonempty()
-            results.append({"pred_boxes": bs[keep], "scores": s[keep], "pred_classes": c[keep], "pred_masks": masks[keep].bool()})
+            all_kept = bool(keep.all().item())
+        masks_b = masks.view(torch.bool)                                # the paste kernel writes 0 / 1
+        o = 0
+        for n in counts:
+            sl = slice(o, o + n)
+            if all_kept:
+                results.append({"pred_boxes": bs[sl], "scores": scores[sl], "pred_classes": classes[sl], "pred_masks": masks_b[sl]})
+            else:
+                k = keep[sl]
+                results.append({"pred_boxes": bs[sl][k], "scores": scores[sl][k], "pred_classes": classes[sl][k], "pred_masks": masks_b[sl][k]})
+            o += n
         return results
 
 
