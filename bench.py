@@ -262,8 +262,10 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"                 # keep stdout to the single JSON line
+        # keep stdout to the single JSON line: NCCL prints its version banner to stdout at any debug level >= VERSION
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # an explicit INFO / TRACE request goes to stderr
         torch.distributed.init_process_group("nccl", device_id=device)
     from ttdg_b200 import _C
     lib = _C.lib()

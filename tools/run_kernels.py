@@ -200,13 +200,20 @@ elif what == "busy":
     import bench
     from torch.profiler import profile, ProfilerActivity
     m, opt = bench.build_ours(dev)
-    inputs = [dict(d, image=d["image"].to(dev)) for d in bench.make_inputs(0)]
+    host = "host" in sys.argv[3:]                          # e2e form: pinned host images, result read back every step
+    inputs = [dict(d, image=(d["image"].pin_memory() if host else d["image"].to(dev))) for d in bench.make_inputs(0)]
+    host_res = torch.empty(9, dtype=torch.float64).pin_memory()
     def step():
         m.train()
         loss, _, _, _ = m(inputs, branch="TTT")
         opt.zero_grad(); loss.backward(); opt.step(1)
         m.eval()
-        return m(inputs)
+        out = m(inputs)
+        if host:
+            res = torch.stack([o["instances"].pred_masks.sum().to(torch.float64) for o in out] + [loss.detach().to(torch.float64)])
+            host_res.copy_(res, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return out
     for _ in range(3):
         step()
     torch.cuda.synchronize()
@@ -225,7 +232,7 @@ elif what == "busy":
     busy = sum(tot.values())
     print("wall ms/step %.2f (under the profiler), device busy ms/step %.2f (%.0f%%), launches/step %d" %
           (wall, busy, 100 * busy / wall, sum(cnt.values()) // reps))
-    if len(sys.argv) > 3 and sys.argv[3] == "gaps":
+    if "gaps" in sys.argv[3:]:
         # idle time of the device between consecutive kernels, attributed to the kernel that FOLLOWS the gap
         evs = sorted(((e.time_range.start, e.time_range.end, e.name.split("(")[0][:70]) for e in prof.events()
                       if str(e.device_type).endswith("CUDA")), key=lambda t: t[0])
