@@ -17,9 +17,11 @@
 // optimizer step (ttdg_weight_transpose_split / ttdg_tf32_split); activations land raw in shared memory and the split
 // warps write hi / lo INTO TENSOR MEMORY (tcgen05.st) - the MMAs take their A operand from TMEM and only B from shared
 // memory (no extra pass over HBM, no write-back to shared memory).  Single-pass TF32 (wk_lo == NULL) is the fast mode.
-// Variants: LIGHT (short K loops, two CTAs per SM), clusters with TMA multicast of the weight tile (optional).
+// The kernel is PERSISTENT (one CTA per SM walks its tiles; set-up once, loads / MMAs / epilogue of consecutive tiles
+// overlap); optional thread-block clusters share the weight tile by TMA multicast.
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
@@ -193,12 +195,7 @@ __device__ __forceinline__ void split_stage_tmem(const unsigned char *raw, uint3
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// LIGHT: the variant for short K loops (<= CHUNK k-blocks: the 1x1 convolutions with Cin <= 256, the stem).  Such a CTA
-// is a chain of latencies - barrier / TMEM set-up, one TMA round trip, a handful of MMAs, the epilogue's global
-// round trip - and with one CTA per SM nothing overlaps them (measured: 13 us per CTA wave for 160 KB of traffic,
-// 1.65 TB/s).  LIGHT uses 2 stages, ONE accumulator buffer and a streaming epilogue (32 columns at a time, no register
-// accumulator), which fits two CTAs per SM: 97 KB of shared memory, 256 TMEM columns and <= 72 registers each.
-template <int BN_TILE, bool PRECISE, bool LIGHT = false>
+template <int BN_TILE, bool PRECISE>
 struct TcCfg {
     static constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN_TILE * 128;
     // 3xTF32: the split activations (A hi / lo) live in TENSOR MEMORY, not in shared memory: the stage holds the raw fp32
@@ -208,13 +205,12 @@ struct TcCfg {
     // nothing back to it (~110 KB per k-block).
     static constexpr int STAGE_BYTES = A_BYTES + (PRECISE ? 2 : 1) * B_BYTES;
     static constexpr int TX_BYTES = STAGE_BYTES;                                     // what TMA delivers per stage
-    static constexpr int STAGES = LIGHT ? 2 : (PRECISE ? (BN_TILE == 128 ? 4 : 6) : (BN_TILE == 128 ? 6 : 8));
+    static constexpr int STAGES = PRECISE ? (BN_TILE == 128 ? 4 : 6) : (BN_TILE == 128 ? 6 : 8);
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-    static constexpr int ACC_COLS = (LIGHT ? 1 : 2) * BN_TILE;      // accumulator buffers (ping-pong between MMA and epilogue)
+    static constexpr int ACC_COLS = 2 * BN_TILE;         // two accumulator buffers (ping-pong between MMA and epilogue)
     static constexpr int A_COLS = 2 * TC_BK;             // TMEM columns of one stage's A operand: 32 hi + 32 lo
-    static constexpr int TMEM_COLS = PRECISE ? (LIGHT ? 256 : 512) : ACC_COLS;       // power of two >= ACC_COLS + STAGES * A_COLS
+    static constexpr int TMEM_COLS = PRECISE ? 512 : ACC_COLS;      // power of two >= ACC_COLS + STAGES * A_COLS
     static_assert(!PRECISE || ACC_COLS + STAGES * A_COLS <= TMEM_COLS, "TMEM budget");
-    static constexpr int MIN_CTAS = LIGHT ? 2 : 1;
     static constexpr int EPI_COLS = BN_TILE / 2;         // columns per epilogue warp (two warps share a TMEM lane group)
     // The tensor core adds into its fp32 accumulator with truncation, so the error of one long accumulation grows
     // linearly with K (measured 5e-5 relative at K = 12544).  The accumulation is therefore cut into chunks of CHUNK
@@ -287,15 +283,17 @@ __device__ __forceinline__ void tc_split_loop_tmem(const TcSmem &sm, uint32_t tm
 }
 
 // epilogue warps: add the drained TMEM chunks (columns col0 .. col0 + EPI_COLS of lane group q) in registers
+// gc0: chunks this CTA has already drained (persistent conv kernel: the ping-pong continues across tiles)
 template <class Cfg>
-__device__ __forceinline__ void tc_drain(const TcSmem &sm, uint32_t tmem_base, int KB, int q, int col0, float (&acc)[Cfg::EPI_COLS]) {
+__device__ __forceinline__ void tc_drain(const TcSmem &sm, uint32_t tmem_base, int KB, int q, int col0, float (&acc)[Cfg::EPI_COLS],
+                                         uint32_t gc0 = 0) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int j = 0; j < Cfg::EPI_COLS; ++j) acc[j] = 0.f;
     const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
     for (int ch = 0; ch < nchunks; ++ch) {
-        const int buf = ch & 1;
-        mbar_wait(&sm.tmem_full[buf], (ch >> 1) & 1);
+        const int buf = (int)((gc0 + ch) & 1u);
+        mbar_wait(&sm.tmem_full[buf], ((gc0 + ch) >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int c0 = 0; c0 < Cfg::EPI_COLS; c0 += 32) {
@@ -310,11 +308,17 @@ __device__ __forceinline__ void tc_drain(const TcSmem &sm, uint32_t tmem_base, i
     }
 }
 
-template <int BN_TILE, bool PRECISE, int CL, bool LIGHT>
-__global__ void __launch_bounds__(TC_THREADS, LIGHT ? 2 : 1)
+// PERSISTENT: the grid is one CTA per SM (a cluster of CL CTAs per CL SMs) and every CTA walks the work items
+// item = (group of CL consecutive pixel tiles, N tile), item = cluster id, + number of clusters, ...  All four roles keep
+// their ring / ping-pong counters running across items, so the TMEM set-up is paid once per SM, the TMA loads of the next
+// tile are in flight while the current one computes, and - the accumulator being double buffered - the epilogue of tile t
+// (TMEM drain, residual read, global stores) overlaps the MMAs of tile t + 1.  (One tile per CTA serialised set-up, TMA
+// round trip, MMAs and epilogue: 13 us per CTA wave on the short-K 1x1 layers.)
+template <int BN_TILE, bool PRECISE, int CL>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
-    using Cfg = TcCfg<BN_TILE, PRECISE, LIGHT>;
+    using Cfg = TcCfg<BN_TILE, PRECISE>;
     extern __shared__ unsigned char tc_smem_raw[];
     TcSmem sm;
     const uint32_t tmem_base = tc_prologue<Cfg, CL>(sm, tc_smem_raw);
@@ -322,41 +326,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int SLICE_ROWS = BN_TILE / CL, SLICE_BYTES = SLICE_ROWS * 128;       // this CTA's share of the weight tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // tile coordinates
-    int t = blockIdx.x;
-    const int tw = t % p.tilesW; t /= p.tilesW;
-    const int th = t % p.tilesH; t /= p.tilesH;
-    const int ti = t;
-    const int w0 = tw * p.BW, h0 = th * p.BH, i0 = ti * p.BI;
-    const int n0 = blockIdx.y * BN_TILE;
     const int KB = p.R * p.S * p.kslabs;
+    const int ntm = p.tilesW * p.tilesH * p.tilesI, ntn = p.Cout / BN_TILE;
+    const int nitems = ((ntm + CL - 1) / CL) * ntn;                               // (pixel-tile group, N tile), N fastest
+    const int clus = blockIdx.x / CL, nclus = gridDim.x / CL, crank = blockIdx.x % CL;   // 1-D clusters along x: crank = %cluster_ctarank
+    // pixel tiles past the end (a group is padded to CL tiles) decode to out-of-range coordinates: TMA zero fill, no stores
+    auto decode = [&](int item, int &w0, int &h0, int &i0, int &n0) {
+        const int mg = item / ntn;
+        n0 = (item - mg * ntn) * BN_TILE;
+        int t = mg * CL + crank;
+        const int tw = t % p.tilesW; t /= p.tilesW;
+        const int th = t % p.tilesH; t /= p.tilesH;
+        w0 = tw * p.BW; h0 = th * p.BH; i0 = t * p.BI;
+    };
 
     if (warp == TC_WARP_TMA) {
         // ===================== TMA producer
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-            int stage = 0;
-            uint32_t phase = 0;
-            const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
-            for (int kb = 0; kb < KB; ++kb) {
-                const int tap = kb / p.kslabs, c0 = (kb - tap * p.kslabs) * TC_BK;
-                const int r = tap / p.S, s = tap - r * p.S;
-                const int btap = p.flip ? (p.R - 1 - r) * p.S + (p.S - 1 - s) : tap;
-                mbar_wait(&sm.empty[stage], phase ^ 1);
-                unsigned char *st = sm.tiles + stage * Cfg::STAGE_BYTES;
-                mbar_expect_tx(&sm.full[stage], (PRECISE && p.dbg_skip_blo) ? Cfg::TX_BYTES - Cfg::B_BYTES : Cfg::TX_BYTES);
-                if (p.stem) tma_load_4d(st, &tmA, &sm.full[stage], 0, w0, 2 * h0 + r - 3, i0);
-                else tma_load_4d(st, &tmA, &sm.full[stage], c0, (w0 + s - p.pad) * p.in_stride, (h0 + r - p.pad) * p.in_stride, i0);
-                if (CL == 1) {
-                    tma_load_3d(st + Cfg::A_BYTES, &tmB, &sm.full[stage], c0, n0, btap);
-                    if (PRECISE && !p.dbg_skip_blo) tma_load_3d(st + Cfg::A_BYTES + Cfg::B_BYTES, &tmBlo, &sm.full[stage], c0, n0, btap);
-                } else {                                     // rows [crank * SLICE_ROWS, ...) of the weight tile, to every CTA of the cluster
-                    tma_load_3d_mc(st + Cfg::A_BYTES + crank * SLICE_BYTES, &tmB, &sm.full[stage], c0, n0 + crank * SLICE_ROWS, btap, CL_MASK);
-                    if (PRECISE) tma_load_3d_mc(st + Cfg::A_BYTES + Cfg::B_BYTES + crank * SLICE_BYTES, &tmBlo, &sm.full[stage], c0,
-                                                n0 + crank * SLICE_ROWS, btap, CL_MASK);
+            uint32_t it = 0;                                                     // k-blocks issued so far (ring position)
+            for (int item = clus; item < nitems; item += nclus) {
+                int w0, h0, i0, n0;
+                decode(item, w0, h0, i0, n0);
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int stage = (int)(it % Cfg::STAGES);
+                    const uint32_t phase = (it / Cfg::STAGES) & 1u;
+                    const int tap = kb / p.kslabs, c0 = (kb - tap * p.kslabs) * TC_BK;
+                    const int r = tap / p.S, s = tap - r * p.S;
+                    const int btap = p.flip ? (p.R - 1 - r) * p.S + (p.S - 1 - s) : tap;
+                    mbar_wait(&sm.empty[stage], phase ^ 1);
+                    unsigned char *st = sm.tiles + stage * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(&sm.full[stage], (PRECISE && p.dbg_skip_blo) ? Cfg::TX_BYTES - Cfg::B_BYTES : Cfg::TX_BYTES);
+                    if (p.stem) tma_load_4d(st, &tmA, &sm.full[stage], 0, w0, 2 * h0 + r - 3, i0);
+                    else tma_load_4d(st, &tmA, &sm.full[stage], c0, (w0 + s - p.pad) * p.in_stride, (h0 + r - p.pad) * p.in_stride, i0);
+                    if (CL == 1) {
+                        tma_load_3d(st + Cfg::A_BYTES, &tmB, &sm.full[stage], c0, n0, btap);
+                        if (PRECISE && !p.dbg_skip_blo) tma_load_3d(st + Cfg::A_BYTES + Cfg::B_BYTES, &tmBlo, &sm.full[stage], c0, n0, btap);
+                    } else {                                 // rows [crank * SLICE_ROWS, ...) of the weight tile, to every CTA of the cluster
+                        tma_load_3d_mc(st + Cfg::A_BYTES + crank * SLICE_BYTES, &tmB, &sm.full[stage], c0, n0 + crank * SLICE_ROWS, btap, CL_MASK);
+                        if (PRECISE) tma_load_3d_mc(st + Cfg::A_BYTES + Cfg::B_BYTES + crank * SLICE_BYTES, &tmBlo, &sm.full[stage], c0,
+                                                    n0 + crank * SLICE_ROWS, btap, CL_MASK);
+                    }
                 }
-                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == TC_WARP_MMA) {
@@ -364,42 +376,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             // instruction descriptor: D = F32, A = B = TF32, both K-major, N = BN_TILE, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN_TILE >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            int stage = 0;
-            uint32_t phase = 0;
+            uint32_t it = 0, gc = 0;                                             // k-blocks consumed, accumulation chunks issued
             const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
-            for (int ch = 0; ch < nchunks; ++ch) {
-                const int buf = ch & 1;
-                mbar_wait(&sm.tmem_empty[buf], ((ch >> 1) & 1) ^ 1);         // epilogue has drained this buffer
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tacc = tmem_base + (uint32_t)(buf * BN_TILE);
-                const int kb_end = min(KB, (ch + 1) * Cfg::CHUNK);
-                for (int kb = ch * Cfg::CHUNK; kb < kb_end; ++kb) {
-                    mbar_wait(PRECISE ? &sm.conv[stage] : &sm.full[stage], phase);
+            for (int item = clus; item < nitems; item += nclus) {
+                for (int ch = 0; ch < nchunks; ++ch, ++gc) {
+                    const int buf = (int)(gc & 1u);
+                    mbar_wait(&sm.tmem_empty[buf], ((gc >> 1) & 1u) ^ 1u);       // epilogue has drained this buffer
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a = smem_u32(sm.tiles + stage * Cfg::STAGE_BYTES), b = a + Cfg::A_BYTES;
-                    const uint32_t blo = b + Cfg::B_BYTES;
-                    const uint32_t ta = tmem_base + (uint32_t)(Cfg::ACC_COLS + stage * Cfg::A_COLS);      // A hi | A lo (3xTF32)
+                    const uint32_t tacc = tmem_base + (uint32_t)(buf * BN_TILE);
+                    const int kb_end = min(KB, (ch + 1) * Cfg::CHUNK);
+                    for (int kb = ch * Cfg::CHUNK; kb < kb_end; ++kb, ++it) {
+                        const int stage = (int)(it % Cfg::STAGES);
+                        const uint32_t phase = (it / Cfg::STAGES) & 1u;
+                        mbar_wait(PRECISE ? &sm.conv[stage] : &sm.full[stage], phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a = smem_u32(sm.tiles + stage * Cfg::STAGE_BYTES), b = a + Cfg::A_BYTES;
+                        const uint32_t blo = b + Cfg::B_BYTES;
+                        const uint32_t ta = tmem_base + (uint32_t)(Cfg::ACC_COLS + stage * Cfg::A_COLS);  // A hi | A lo (3xTF32)
 #pragma unroll
-                    for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-                        const uint32_t koff = k * TC_UMMA_K * 4;             // bytes inside the 128-byte swizzled row
-                        const uint32_t first = (kb != ch * Cfg::CHUNK) || k != 0;
-                        if (PRECISE) {
-                            umma_tf32_ts(tacc, ta + k * TC_UMMA_K, umma_desc(b + koff), idesc, first);
-                            umma_tf32_ts(tacc, ta + TC_BK + k * TC_UMMA_K, umma_desc(b + koff), idesc, 1);
-                            umma_tf32_ts(tacc, ta + k * TC_UMMA_K, umma_desc(blo + koff), idesc, 1);
-                        } else {
-                            umma_tf32(tacc, umma_desc(a + koff), umma_desc(b + koff), idesc, first);
+                        for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                            const uint32_t koff = k * TC_UMMA_K * 4;         // bytes inside the 128-byte swizzled row
+                            const uint32_t first = (kb != ch * Cfg::CHUNK) || k != 0;
+                            if (PRECISE) {
+                                umma_tf32_ts(tacc, ta + k * TC_UMMA_K, umma_desc(b + koff), idesc, first);
+                                umma_tf32_ts(tacc, ta + TC_BK + k * TC_UMMA_K, umma_desc(b + koff), idesc, 1);
+                                umma_tf32_ts(tacc, ta + k * TC_UMMA_K, umma_desc(blo + koff), idesc, 1);
+                            } else {
+                                umma_tf32(tacc, umma_desc(a + koff), umma_desc(b + koff), idesc, first);
+                            }
                         }
+                        if (CL == 1) umma_commit(&sm.empty[stage]);          // frees the smem slot when these MMAs retire
+                        else umma_commit_mc(&sm.empty[stage], CL_MASK);      // ... in every CTA of the cluster
                     }
-                    if (CL == 1) umma_commit(&sm.empty[stage]);              // frees the smem slot when these MMAs retire
-                    else umma_commit_mc(&sm.empty[stage], CL_MASK);          // ... in every CTA of the cluster
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(&sm.tmem_full[buf]);                         // this chunk's accumulator is complete
                 }
-                umma_commit(&sm.tmem_full[buf]);                             // this chunk's accumulator is complete
             }
         }
     } else if (warp >= TC_WARP_CVT0) {
-        if (PRECISE) tc_split_loop_tmem<Cfg>(sm, tmem_base, KB);              // activations only: the weight copies are pre-split
+        // activations only (the weight copies are pre-split); the split does not depend on tile coordinates
+        if (PRECISE) tc_split_loop_tmem<Cfg>(sm, tmem_base, KB * ((nitems - clus + nclus - 1) / nclus));
     } else {
         // ===================== epilogue: warps 0..7; warp w owns TMEM lanes 32 * (w % 4) .. and column half w / 4
         // (each thread stores its pixel's EPI_COLS channels = 128 / 256 contiguous bytes.  A shared-memory-staged variant
@@ -410,54 +425,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int row = q * 32 + lane;                                       // GEMM row inside the tile = TMEM lane
         const int bi = row / (p.BH * p.BW), rem = row - bi * p.BH * p.BW;
         const int bh = rem / p.BW, bw = rem - bh * p.BW;
-        const int img = i0 + bi, ho = h0 + bh, wo = w0 + bw;
-        const bool ok = img < p.N && ho < p.Ho && wo < p.Wo;
-        const size_t pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
-        const size_t opix = ((size_t)img * p.outH + ho * p.out_stride) * p.outW + wo * p.out_stride;
-        const int nb = n0 + col0;
-        float *yrow = p.y + opix * p.Cout + nb;
-        const float *rrow = nullptr;
-        if (ok) {
-            if (p.res_mode == 1) rrow = p.residual + pix * p.Cout + nb;
-            else if (p.res_mode == 2) rrow = p.residual + (((size_t)img * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * p.Cout + nb;
-        }
-        if (LIGHT) {
-            // single chunk (KB <= CHUNK): stream the accumulator 32 columns at a time straight through the epilogue
-            mbar_wait(&sm.tmem_full[0], 0);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int c0 = 0; c0 < Cfg::EPI_COLS; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + c0), v);       // warp-collective
-                if (ok) {
+        const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
+        uint32_t gc = 0;
+        for (int item = clus; item < nitems; item += nclus, gc += nchunks) {
+            int w0, h0, i0, n0;
+            decode(item, w0, h0, i0, n0);
+            const int img = i0 + bi, ho = h0 + bh, wo = w0 + bw;
+            const bool ok = img < p.N && ho < p.Ho && wo < p.Wo;
+            float acc[Cfg::EPI_COLS];
+            tc_drain<Cfg>(sm, tmem_base, KB, q, col0, acc, gc);
+            if (ok) {
+                const size_t pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
+                const size_t opix = ((size_t)img * p.outH + ho * p.out_stride) * p.outW + wo * p.out_stride;
+                const int nb = n0 + col0;
+                float *yrow = p.y + opix * p.Cout + nb;
+                const float *rrow = nullptr;
+                if (p.res_mode == 1) rrow = p.residual + pix * p.Cout + nb;
+                else if (p.res_mode == 2) rrow = p.residual + (((size_t)img * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * p.Cout + nb;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                        const int n = nb + c0 + j;
-                        if (p.scale) { const float4 s4 = *reinterpret_cast<const float4 *>(p.scale + n); o.x *= s4.x; o.y *= s4.y; o.z *= s4.z; o.w *= s4.w; }
-                        if (p.bias) { const float4 b4 = *reinterpret_cast<const float4 *>(p.bias + n); o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w; }
-                        if (rrow) { const float4 r4 = *reinterpret_cast<const float4 *>(rrow + c0 + j); o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
-                        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        *reinterpret_cast<float4 *>(yrow + c0 + j) = o;
-                    }
+                for (int j = 0; j < Cfg::EPI_COLS; j += 4) {
+                    float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                    const int n = nb + j;
+                    if (p.scale) { const float4 s4 = *reinterpret_cast<const float4 *>(p.scale + n); o.x *= s4.x; o.y *= s4.y; o.z *= s4.z; o.w *= s4.w; }
+                    if (p.bias) { const float4 b4 = *reinterpret_cast<const float4 *>(p.bias + n); o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w; }
+                    if (rrow) { const float4 r4 = *reinterpret_cast<const float4 *>(rrow + j); o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
+                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    *reinterpret_cast<float4 *>(yrow + j) = o;
                 }
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        } else {
-        float acc[Cfg::EPI_COLS];
-        tc_drain<Cfg>(sm, tmem_base, KB, q, col0, acc);
-        if (ok) {
-#pragma unroll
-            for (int j = 0; j < Cfg::EPI_COLS; j += 4) {
-                float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-                const int n = nb + j;
-                if (p.scale) { const float4 s4 = *reinterpret_cast<const float4 *>(p.scale + n); o.x *= s4.x; o.y *= s4.y; o.z *= s4.z; o.w *= s4.w; }
-                if (p.bias) { const float4 b4 = *reinterpret_cast<const float4 *>(p.bias + n); o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w; }
-                if (rrow) { const float4 r4 = *reinterpret_cast<const float4 *>(rrow + j); o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
-                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                *reinterpret_cast<float4 *>(yrow + j) = o;
-            }
-        }
         }
     }
     tc_epilogue_end<Cfg, CL>(tmem_base);
@@ -774,16 +769,31 @@ static int tc_cluster_size() {
     return g_tc_cluster;
 }
 
-template <int BN_TILE, bool PRECISE, int CL, bool LIGHT>
+static int tc_sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    }
+    return n;
+}
+
+template <int BN_TILE, bool PRECISE, int CL>
 static int launch_tc_cl(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &blo, const TcParams &p, cudaStream_t st) {
-    using Cfg = TcCfg<BN_TILE, PRECISE, LIGHT>;
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_TILE, PRECISE, CL, LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    using Cfg = TcCfg<BN_TILE, PRECISE>;
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_TILE, PRECISE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return (int)e;
+    // persistent grid: one CTA per SM (whole clusters), each walking its share of the (pixel-tile group, N tile) items;
+    // a group is padded to CL pixel tiles - the extra ones run on out-of-range coordinates so that their share of the
+    // weight multicast still happens
     const int tiles = p.tilesW * p.tilesH * p.tilesI;
-    // the grid is padded to whole clusters: the extra CTAs run the pipeline on out-of-range pixel coordinates (TMA zero
-    // fill, nothing stored) so that their share of the weight multicast still happens
+    const int items = ((tiles + CL - 1) / CL) * (p.Cout / BN_TILE);
+    int clusters = tc_sm_count() / CL;
+    if (clusters > items) clusters = items;
+    if (clusters < 1) clusters = 1;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((tiles + CL - 1) / CL * CL, p.Cout / BN_TILE);
+    cfg.gridDim = dim3(clusters * CL);
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM;
     cfg.stream = st;
@@ -792,22 +802,15 @@ static int launch_tc_cl(const CUtensorMap &a, const CUtensorMap &b, const CUtens
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = CL > 1 ? 1 : 0;
     count_launches(1);
-    return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN_TILE, PRECISE, CL, LIGHT>, a, b, blo, p);
-}
-
-static int g_tc_light = -1;                                  // TTDG_TC_LIGHT = 0 disables the two-CTAs-per-SM variant
-static bool tc_light_enabled() {
-    if (g_tc_light < 0) { const char *e = getenv("TTDG_TC_LIGHT"); g_tc_light = (e && e[0] == '0') ? 0 : 1; }
-    return g_tc_light != 0;
+    return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN_TILE, PRECISE, CL>, a, b, blo, p);
 }
 
 // cl: cluster size the weight tensor maps were built for (their box holds BN_TILE / cl rows)
 template <int BN_TILE, bool PRECISE>
 static int launch_tc(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &blo, const TcParams &p, cudaStream_t st, int cl = 1) {
-    if (cl == 4) return launch_tc_cl<BN_TILE, PRECISE, 4, false>(a, b, blo, p, st);
-    if (cl == 2) return launch_tc_cl<BN_TILE, PRECISE, 2, false>(a, b, blo, p, st);
-    if (p.R * p.S * p.kslabs <= TcCfg<BN_TILE, PRECISE>::CHUNK && tc_light_enabled()) return launch_tc_cl<BN_TILE, PRECISE, 1, true>(a, b, blo, p, st);
-    return launch_tc_cl<BN_TILE, PRECISE, 1, false>(a, b, blo, p, st);
+    if (cl == 4) return launch_tc_cl<BN_TILE, PRECISE, 4>(a, b, blo, p, st);
+    if (cl == 2) return launch_tc_cl<BN_TILE, PRECISE, 2>(a, b, blo, p, st);
+    return launch_tc_cl<BN_TILE, PRECISE, 1>(a, b, blo, p, st);
 }
 
 }  // namespace ttdg
