@@ -31,6 +31,8 @@ CASES = [
     (64, 256, 1, 0, 8, 24, 1),
     (128, 128, 3, 1, 12, 12, 2),          # 3x3: taps are TMA coordinate shifts, padding = OOB fill
     (256, 256, 3, 1, 14, 14, 5),          # mask-head shape: 14 is not a power of two (partial boxes)
+    (256, 128, 3, 1, 14, 14, 40),         # ... with enough rois that the 14 x 1 x 9-image box (126 of 128 rows) is chosen
+    (64, 64, 3, 1, 6, 10, 23),            # odd everything: 10 x 6 x 2 = 120 rows
     (256, 256, 3, 1, 128, 128, 1),        # BW = 128
     (256, 64, 3, 1, 8, 8, 3),             # several images per tile
     (12544, 1024, 1, 0, 1, 1, 300),       # box-head fc1 as a 1x1 conv on N = rows
@@ -62,7 +64,8 @@ def test_conv_tc_forward(mode, rtol, cin, cout, k, pad, H, W, N):
 
 
 @pytest.mark.parametrize("mode,rtol", [("tf32x3", 3e-5), ("tf32", 6e-3)])
-@pytest.mark.parametrize("cin,cout,k,pad,H,W,N", [(128, 128, 3, 1, 10, 12, 2), (512, 128, 1, 0, 8, 8, 2), (256, 256, 3, 1, 16, 16, 1)])
+@pytest.mark.parametrize("cin,cout,k,pad,H,W,N", [(128, 128, 3, 1, 10, 12, 2), (512, 128, 1, 0, 8, 8, 2), (256, 256, 3, 1, 16, 16, 1),
+                                                 (128, 128, 3, 1, 14, 14, 30)])
 def test_conv_tc_dgrad(mode, rtol, cin, cout, k, pad, H, W, N):
     det.set_conv_mode(mode)
     g = torch.Generator().manual_seed(cin + cout + k)

@@ -53,6 +53,7 @@ struct TcParams {
     int stem;                        // 7x7 stride-2 stem on the padded image: k-block r = filter row, box = 8-pixel windows
     int out_stride, outH, outW;      // output pixel (ho, wo) is stored at (ho, wo) * out_stride of an outH x outW map
     int dbg_skip_blo;                // experiment (TTDG_DEBUG_SKIP_BLO=1, wrong results): do not load the lo weight tile
+    int a_tx;                        // bytes one activation box delivers: BW * BH * BI rows of 128 B (<= A_BYTES)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -357,7 +358,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int btap = p.flip ? (p.R - 1 - r) * p.S + (p.S - 1 - s) : tap;
                     mbar_wait(&sm.empty[stage], phase ^ 1);
                     unsigned char *st = sm.tiles + stage * Cfg::STAGE_BYTES;
-                    mbar_expect_tx(&sm.full[stage], (PRECISE && p.dbg_skip_blo) ? Cfg::TX_BYTES - Cfg::B_BYTES : Cfg::TX_BYTES);
+                    mbar_expect_tx(&sm.full[stage], (uint32_t)(p.a_tx + ((PRECISE && !p.dbg_skip_blo) ? 2 : 1) * Cfg::B_BYTES));
                     if (p.stem) tma_load_4d(st, &tmA, &sm.full[stage], 0, w0, 2 * h0 + r - 3, i0);
                     else tma_load_4d(st, &tmA, &sm.full[stage], c0, (w0 + s - p.pad) * p.in_stride, (h0 + r - p.pad) * p.in_stride, i0);
                     if (CL == 1) {
@@ -431,7 +432,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int w0, h0, i0, n0;
             decode(item, w0, h0, i0, n0);
             const int img = i0 + bi, ho = h0 + bh, wo = w0 + bw;
-            const bool ok = img < p.N && ho < p.Ho && wo < p.Wo;
+            const bool ok = bi < p.BI && img < p.N && ho < p.Ho && wo < p.Wo;       // bi >= BI: rows past a box of < 128 pixels
             float acc[Cfg::EPI_COLS];
             tc_drain<Cfg>(sm, tmem_base, KB, q, col0, acc, gc);
             if (ok) {
@@ -893,6 +894,7 @@ extern "C" int ttdg_stem_tc(const float *x_pad, int Wp, const float *wk_hi, cons
     p.BH = pow2_ge(p.Ho) < TC_BM / p.BW ? pow2_ge(p.Ho) : TC_BM / p.BW;
     p.BI = TC_BM / (p.BW * p.BH);
     p.tilesW = ceil_div(p.Wo, p.BW); p.tilesH = ceil_div(p.Ho, p.BH); p.tilesI = ceil_div(N, p.BI);
+    p.a_tx = p.BW * p.BH * p.BI * 128;
     CUtensorMap ma, mb, mblo;
     const cuuint64_t adims[4] = {32, (cuuint64_t)p.Wo, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t astr[3] = {32, (cuuint64_t)Wp * 16, (cuuint64_t)H * Wp * 16};
@@ -965,12 +967,26 @@ extern "C" int ttdg_conv_tc(const float *x, const float *wk_hi, const float *wk_
     p.BH = pow2_ge(p.Ho) < TC_BM / p.BW ? pow2_ge(p.Ho) : TC_BM / p.BW;
     p.BI = TC_BM / (p.BW * p.BH);
     p.tilesW = ceil_div(p.Wo, p.BW); p.tilesH = ceil_div(p.Ho, p.BH); p.tilesI = ceil_div(N, p.BI);
+    // Maps whose width is not a power of two (the mask head's 14 x 14: 16 x 8 boxes use 77 % of the tile rows): a TMA box
+    // does not have to be a power of two - try box width = map width with every height, as many images as fit in the
+    // 128 rows (14 x 3 x 3 = 126 rows: 92 %), and keep it when it needs at least 3 % fewer tiles.
+    if (p.Wo <= TC_BM && (p.Wo & (p.Wo - 1)) != 0) {
+        long best = (long)p.tilesW * p.tilesH * p.tilesI;
+        for (int bh = 1; bh <= p.Ho && p.Wo * bh <= TC_BM; ++bh) {
+            int bi = TC_BM / (p.Wo * bh);
+            if (bi > N) bi = N;
+            const long t = (long)ceil_div(p.Ho, bh) * ceil_div(N, bi);
+            if (t * 100 < best * 97) { best = t; p.BW = p.Wo; p.BH = bh; p.BI = bi; p.tilesW = 1; p.tilesH = ceil_div(p.Ho, bh); p.tilesI = ceil_div(N, bi); }
+        }
+    }
+    p.a_tx = p.BW * p.BH * p.BI * 128;
     CUtensorMap ma, mb, mblo;
     const cuuint64_t adims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint32_t abox[4] = {TC_BK, (cuuint32_t)(p.BW * in_stride), (cuuint32_t)(p.BH * in_stride), (cuuint32_t)p.BI};
     const cuuint64_t bdims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(R * S)};
-    const int bn_tile = Cout % 128 == 0 ? 128 : 64;
     const int tiles = p.tilesW * p.tilesH * p.tilesI;
+    // (64-wide N tiles for the small res5 maps - 64 items on 148 SMs with 128-wide tiles - measured slower: 114 vs 105 us)
+    const int bn_tile = Cout % 128 == 0 ? 128 : 64;
     int cl = tc_cluster_size();
     while (cl > 1 && tiles < 2 * cl) cl >>= 1;              // tiny layers: no point padding the grid
     const cuuint32_t bbox[3] = {TC_BK, (cuuint32_t)(bn_tile / cl), 1};
