@@ -42,6 +42,17 @@ class DAobjTwoStagePseudoLabGeneralizedRCNN(nn.Module):
     def device(self):
         return self.multi_matching_sup.U.device
 
+    def train(self, mode=True):
+        """nn.Module.train walks ~300 sub-modules; the test-time loop flips the mode twice per batch (trainer.py:469-485) and
+        only two modules read the flag: this one (forward dispatch) and the attention of the matching head (dropout)."""
+        if getattr(self, "_mode_initialised", False):
+            self.training = mode
+            for m in self.multi_matching_unsup.modules():
+                m.training = mode
+            return self
+        self._mode_initialised = True
+        return super().train(mode)
+
     def adapted_parameters(self):
         """Everything that receives a gradient in the TTT step: res3-res5, FPN and the affinity layer."""
         return self._det[0].adapted_parameters() + list(self.multi_matching_unsup.node_affinity.parameters())
