@@ -195,3 +195,26 @@ def test_gagm_many_graphs_and_extreme_sizes():
         U, info, trace, meta = ops.gagm_solve(A.cuda(), W.cuda(), U0.cuda(), ms, max_iter=30, trace_cap=300)
         verify_trajectory(A, W, U0, ms, trace, meta, info.cpu().tolist(), max_iter=30)
         assert np.array_equal(U.cpu().numpy(), trace[int(info[0])].float().cpu().numpy())
+
+
+def test_hippi_matches_reference(golden_dir):
+    """HiPPI (mgm:392-449) through the device operators against the reference's own class (oracle/gen_golden_hippi.py):
+    Hungarian projections bit for bit, Sinkhorn projections (tau = 1/200, 20 iterations, dummy rows) to fp32 noise."""
+    from adapteacher.modeling.GModule.multi_graph_matching import HiPPI
+    g = np.load(f"{golden_dir}/hippi.npz")
+    W, U0 = torch.from_numpy(g["W"]).cuda(), torch.from_numpy(g["U0"]).cuda()
+    ms, d = torch.from_numpy(g["ms"]), int(g["d"])
+    for iters in (1, 3):
+        h = HiPPI(max_iter=iters)
+        U = h(W, U0, ms, d, projector="hungarian").cpu().numpy()
+        assert np.array_equal(U, g[f"U_hungarian_{iters}_f32"]) and np.array_equal(U, g[f"U_hungarian_{iters}_f64"])
+        U = h(W, U0, ms, d, projector="sinkhorn").cpu().numpy()
+        np.testing.assert_allclose(U, g[f"U_sinkhorn_{iters}_f64"], rtol=2e-4, atol=1e-7)
+        np.testing.assert_allclose(U, g[f"U_sinkhorn_{iters}_f32"], rtol=2e-4, atol=1e-7)
+        assert h.last_iterations == iters
+    with pytest.raises(NameError):
+        HiPPI()(W, U0, ms, d, projector="softmax")
+    # runs to convergence (or max_iter) without a host-side projector
+    h = HiPPI(max_iter=50)
+    U = h(W, U0, ms, d, projector="hungarian")
+    assert h.last_iterations <= 50 and float(U.sum()) == float(sum(ms.tolist()))

@@ -47,6 +47,40 @@ class GA_GM(nn.Module):
         return U, torch.zeros(len(ms_l), dtype=torch.int)
 
 
+class HiPPI(nn.Module):
+    """Higher-order projected power iteration (mgm:392-449): U <- proj(W U (U^T (W U))) per graph, until
+    ||U - lastU|| < 1e-5 or ``max_iter``.  Host loop over the device operators (two dense products, then one projector
+    call per graph - per graph, not batched, because pygmtools transposes a whole ragged batch at once); the
+    convergence test is the reference's per-iteration host sync.  Used by the source-time ``U_sup.forward`` only."""
+
+    def __init__(self, max_iter=50, sk_iter=20, sk_tau=1 / 200.):
+        super().__init__()
+        self.max_iter = max_iter
+        self.sinkhorn = Sinkhorn(max_iter=sk_iter, tau=sk_tau)
+        self.hungarian = ops.hungarian
+        self.last_iterations = 0
+
+    def forward(self, W, U0, ms, d, projector='sinkhorn'):
+        if projector not in ('sinkhorn', 'hungarian'):
+            raise NameError('Unknown projector {}.'.format(projector))
+        ms_l = [int(v) for v in (ms.tolist() if torch.is_tensor(ms) else ms)]
+        U = U0
+        for i in range(self.max_iter):
+            lastU = U
+            WU = ops.gemm(W, U)                                                  # mgm:419
+            V = ops.gemm(WU, ops.gemm(U, WU, trans_a=True))                      # chain_matmul(WU, U^T, WU), mgm:420
+            parts, o = [], 0
+            for m in ms_l:
+                Vg = V[o:o + m, :d].contiguous()
+                parts.append(self.sinkhorn(Vg, dummy_row=True) if projector == 'sinkhorn' else self.hungarian(Vg))
+                o += m
+            U = torch.cat(parts, dim=0)
+            self.last_iterations = i + 1
+            if torch.norm(U - lastU) < 1e-5:                                     # mgm:445-447
+                break
+        return U
+
+
 class U_sup(nn.Module):
     """Holder of the learned universe embedding ``U`` (mgm:119-135).  The source-training forward (HiPPI,
     mgm:137-168) is outside the test-time path."""
