@@ -7,14 +7,17 @@
 
 namespace ttdg {
 
-constexpr int GT = 64;      // C tile is GT x GT
 constexpr int GK = 16;      // k-slab
+// C tile is GT x GT, 256 threads, (GT / 16)^2 outputs per thread.  GT = 64 normally; GT = 32 when 64-wide tiles would leave
+// most SMs without a CTA (the matching head's GEMMs are ~280 x 512 x 256: 40 tiles of 64 x 64 on 148 SMs).  Every output
+// is accumulated over k in ascending order whatever the tile: results do not depend on GT.
 
 __device__ __forceinline__ double ld_any(const void *p, int is_f64, size_t idx) {
     return is_f64 ? reinterpret_cast<const double *>(p)[idx] : (double)reinterpret_cast<const float *>(p)[idx];
 }
 
 // C (m x n) = op(A) (m x k) * op(B) (k x n) [+ bias(n)] [+ C];  op(A)(i,kk) = transA ? A[kk*lda+i] : A[i*lda+kk]
+template <int GT>
 __global__ void __launch_bounds__(256)
 gemm_f64acc_kernel(int transA, int transB, int m, int n, int k, const void *__restrict__ A, int a64, int lda,
                    const void *__restrict__ B, int b64, int ldb, void *__restrict__ C, int c64, int ldc,
@@ -23,11 +26,12 @@ gemm_f64acc_kernel(int transA, int transB, int m, int n, int k, const void *__re
     __shared__ double Bs[GK][GT + 1];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int row0 = blockIdx.y * GT, col0 = blockIdx.x * GT;
-    double acc[4][4];
+    constexpr int TM = GT / 16;
+    double acc[TM][TM];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        for (int j = 0; j < TM; ++j) acc[i][j] = 0.0;
     for (int k0 = 0; k0 < k; k0 += GK) {
         for (int e = threadIdx.x; e < GK * GT; e += 256) {
             // pick the index order that walks the contiguous dimension of the operand
@@ -45,24 +49,24 @@ gemm_f64acc_kernel(int transA, int transB, int m, int n, int k, const void *__re
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < GK; ++kk) {
-            double a[4], b[4];
+            double a[TM], b[TM];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 16 * i];
+            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty + 16 * i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+            for (int j = 0; j < TM; ++j) b[j] = Bs[kk][tx + 16 * j];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < TM; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < TM; ++i) {
         const int gi = row0 + ty + 16 * i;
         if (gi >= m) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < TM; ++j) {
             const int gj = col0 + tx + 16 * j;
             if (gj >= n) continue;
             double v = acc[i][j];
@@ -88,10 +92,13 @@ extern "C" int ttdg_gemm_f64acc(int transA, int transB, int m, int n, int k, con
                                 void *stream) {
     TTDG_CHECK_ARG(A && B && C && m >= 0 && n >= 0 && k >= 0);
     if (m == 0 || n == 0) return 0;
-    dim3 grid(ceil_div(n, GT), ceil_div(m, GT));
     ttdg::count_launches(1);
-    gemm_f64acc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(transA, transB, m, n, k, A, a_is_f64, lda, B, b_is_f64, ldb,
-                                                              C, c_is_f64, ldc, nullptr, accumulate);
+    if (ceil_div(n, 64) * ceil_div(m, 64) >= 148)
+        gemm_f64acc_kernel<64><<<dim3(ceil_div(n, 64), ceil_div(m, 64)), 256, 0, (cudaStream_t)stream>>>(
+            transA, transB, m, n, k, A, a_is_f64, lda, B, b_is_f64, ldb, C, c_is_f64, ldc, nullptr, accumulate);
+    else
+        gemm_f64acc_kernel<32><<<dim3(ceil_div(n, 32), ceil_div(m, 32)), 256, 0, (cudaStream_t)stream>>>(
+            transA, transB, m, n, k, A, a_is_f64, lda, B, b_is_f64, ldb, C, c_is_f64, ldc, nullptr, accumulate);
     TTDG_LAUNCH_RET();
 }
 
@@ -99,8 +106,12 @@ extern "C" int ttdg_linear_f64acc(const float *X, int ldx, const float *W, int l
                                   int m, int n, int k, void *stream) {
     TTDG_CHECK_ARG(X && W && Y && m >= 0 && n >= 0 && k >= 0);
     if (m == 0 || n == 0) return 0;
-    dim3 grid(ceil_div(n, GT), ceil_div(m, GT));
     ttdg::count_launches(1);
-    gemm_f64acc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(0, 1, m, n, k, X, 0, ldx, W, 0, ldw, Y, 0, ldy, b, 0);
+    if (ceil_div(n, 64) * ceil_div(m, 64) >= 148)
+        gemm_f64acc_kernel<64><<<dim3(ceil_div(n, 64), ceil_div(m, 64)), 256, 0, (cudaStream_t)stream>>>(0, 1, m, n, k, X, 0, ldx, W, 0, ldw, Y,
+                                                                                                           0, ldy, b, 0);
+    else
+        gemm_f64acc_kernel<32><<<dim3(ceil_div(n, 32), ceil_div(m, 32)), 256, 0, (cudaStream_t)stream>>>(0, 1, m, n, k, X, 0, ldx, W, 0, ldw, Y,
+                                                                                                           0, ldy, b, 0);
     TTDG_LAUNCH_RET();
 }
