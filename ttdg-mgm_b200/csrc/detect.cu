@@ -327,8 +327,7 @@ mask_paste_kernel(const float *__restrict__ logits, int ldl, int M, const float 
     const float x0 = boxes[r * 4], y0 = boxes[r * 4 + 1], x1 = boxes[r * 4 + 2], y1 = boxes[r * 4 + 3];
     const int cls = (int)classes[r];
     const float *lg = logits + (size_t)r * M * M * ldl + cls;
-    for (int pix = blockIdx.x * 256 + threadIdx.x; pix < H * W; pix += gridDim.x * 256) {
-        const int py = pix / W, px = pix - py * W;
+    auto value = [&](int py, int px) -> unsigned char {
         const float gy = ((float)py + 0.5f - y0) / (y1 - y0) * 2.f - 1.f;
         const float gx = ((float)px + 0.5f - x0) / (x1 - x0) * 2.f - 1.f;
         const float iy = ((gy + 1.f) * (float)M - 1.f) * 0.5f, ix = ((gx + 1.f) * (float)M - 1.f) * 0.5f;
@@ -344,7 +343,21 @@ mask_paste_kernel(const float *__restrict__ logits, int ldl, int M, const float 
             };
             v = tap(yl, xl) * wy0 * wx0 + tap(yl, xl + 1) * wy0 * wx1 + tap(yl + 1, xl) * wy1 * wx0 + tap(yl + 1, xl + 1) * wy1 * wx1;
         }
-        out[(size_t)r * H * W + pix] = v >= threshold ? 1 : 0;
+        return v >= threshold ? 1 : 0;
+    };
+    unsigned char *o = out + (size_t)r * H * W;
+    if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {          // 4 pixels of a row per thread, one 32-bit store
+        for (int q = blockIdx.x * 256 + threadIdx.x; q < H * W / 4; q += gridDim.x * 256) {
+            const int pix = q * 4, py = pix / W, px = pix - py * W;
+            uchar4 v4;
+            v4.x = value(py, px); v4.y = value(py, px + 1); v4.z = value(py, px + 2); v4.w = value(py, px + 3);
+            reinterpret_cast<uchar4 *>(o)[q] = v4;
+        }
+    } else {
+        for (int pix = blockIdx.x * 256 + threadIdx.x; pix < H * W; pix += gridDim.x * 256) {
+            const int py = pix / W;
+            o[pix] = value(py, pix - py * W);
+        }
     }
 }
 

@@ -638,7 +638,7 @@ class ROIHeads(nn.Module):
         bs = torch.stack((bs[:, 0].clamp(0, W), bs[:, 1].clamp(0, H), bs[:, 2].clamp(0, W), bs[:, 3].clamp(0, H)), dim=1).contiguous()
         scores = torch.cat([d[1] for d in dets]) if R else torch.zeros(0, dtype=torch.float32, device=dev)
         classes = (torch.cat([d[2] for d in dets]) if R else torch.zeros(0, dtype=torch.int64, device=dev)).contiguous()
-        masks = torch.zeros(R, H, W, dtype=torch.uint8, device=dev)
+        masks = torch.empty(R, H, W, dtype=torch.uint8, device=dev)     # the paste kernel writes every pixel
         all_kept = True
         if R:
             check(L.ttdg_mask_paste(_p(logits), logits.shape[-1], 28, _p(bs), _p(classes), R, H, W, 0.5, _p(masks), _stream()), "mask_paste")
