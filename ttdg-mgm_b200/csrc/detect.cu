@@ -270,6 +270,58 @@ roi_align_kernel(Pyr4 pyr, const float *__restrict__ rois, int C, int pooled, fl
     const int gh = (int)ceilf(rh / (float)pooled), gw = (int)ceilf(rw / (float)pooled);
     const float count = fmaxf((float)(gh * gw), 1.f);
     const int c = (threadIdx.x & 63) * 4;
+    // The sample grid is separable: pooled * gh row positions and pooled * gw column positions per roi.  They are
+    // computed ONCE per CTA into shared memory (low index, high index, interpolation weight, validity) with exactly the
+    // per-sample expressions of the loop below, instead of by each of the 64 channel threads for each of its samples.
+    constexpr int RA_TAB = 256;
+    __shared__ int t_lo[2][RA_TAB], t_hi[2][RA_TAB];
+    __shared__ float t_l[2][RA_TAB];
+    __shared__ unsigned char t_ok[2][RA_TAB];
+    const bool tabled = pooled * gh <= RA_TAB && pooled * gw <= RA_TAB;      // block-uniform
+    if (tabled) {
+        for (int e = threadIdx.x; e < pooled * (gh + gw); e += 256) {
+            const int ax = e >= pooled * gh;                                   // 0: rows, 1: columns
+            const int k = ax ? e - pooled * gh : e, g = ax ? gw : gh, L = ax ? W : H;
+            const int pb = k / g, i = k - pb * g;
+            const float b = ax ? bw : bh, st = ax ? rsw : rsh;
+            float v = st + pb * b + ((float)i + .5f) * b / (float)g;
+            const bool ok = !(v < -1.f || v > (float)L);
+            float vv = fmaxf(v, 0.f);
+            int lo = (int)vv, hi;
+            if (lo >= L - 1) { hi = lo = L - 1; vv = (float)lo; } else hi = lo + 1;
+            t_lo[ax][k] = lo; t_hi[ax][k] = hi; t_l[ax][k] = vv - (float)lo; t_ok[ax][k] = ok ? 1 : 0;
+        }
+        __syncthreads();
+        if (c < C)
+        for (int bin = threadIdx.x >> 6; bin < pooled * pooled; bin += 4) {
+            const int ph = bin / pooled, pw = bin - ph * pooled;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int iy = 0; iy < gh; ++iy) {
+                const int ky = ph * gh + iy;
+                if (!t_ok[0][ky]) continue;
+                const float ly = t_l[0][ky], hy = 1.f - ly;
+                const float *row_l = feat + (size_t)t_lo[0][ky] * W * C + c, *row_h = feat + (size_t)t_hi[0][ky] * W * C + c;
+                for (int ix = 0; ix < gw; ++ix) {
+                    const int kx = pw * gw + ix;
+                    if (!t_ok[1][kx]) continue;
+                    const float lx = t_l[1][kx], hx = 1.f - lx;
+                    const int xl = t_lo[1][kx], xh = t_hi[1][kx];
+                    const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+                    const float4 v1 = *reinterpret_cast<const float4 *>(row_l + (size_t)xl * C);
+                    const float4 v2 = *reinterpret_cast<const float4 *>(row_l + (size_t)xh * C);
+                    const float4 v3 = *reinterpret_cast<const float4 *>(row_h + (size_t)xl * C);
+                    const float4 v4 = *reinterpret_cast<const float4 *>(row_h + (size_t)xh * C);
+                    acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
+                    acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
+                    acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
+                    acc.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+                }
+            }
+            acc.x /= count; acc.y /= count; acc.z /= count; acc.w /= count;
+            *reinterpret_cast<float4 *>(out + ((size_t)ridx * pooled * pooled + bin) * C + c) = acc;
+        }
+        return;
+    }
     if (c < C)
     for (int bin = threadIdx.x >> 6; bin < pooled * pooled; bin += 4) {
         const int ph = bin / pooled, pw = bin - ph * pooled;
