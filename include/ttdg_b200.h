@@ -127,6 +127,11 @@ int ttdg_gemm_f64acc(int transA, int transB, int m, int n, int k, const void *A,
                      const void *B, int b_is_f64, int ldb, void *C, int c_is_f64, int ldc, int accumulate,
                      void *stream);
 
+/* Certified fast LAP inside ttdg_gagm_solve: 0 (default; also env TTDG_LAP_FAST) = every Hungarian projection walks SciPy's
+ * shortest-augmenting-path order; 1 = start from a row reduction, certify that the optimum is unique by a margin (no tight
+ * edge to a free column, tight-edge digraph acyclic) and fall back to the SciPy-order solve otherwise.  Same results by
+ * construction (mgm:324-328 -> utils/hungarian.py:58-65).  Returns the previous setting. */
+int ttdg_gagm_set_lap_fast(int on);
 /* ---------------------------------------------------------------------------------------------
  * GA-GM solver.  Replaces GA_GM.forward + gagm (multi_graph_matching.py:223-244, 300-389) for the
  * configuration the hot path uses (num_clusters = 1, projector0 = 'sinkhorn', hung_iter = True) including

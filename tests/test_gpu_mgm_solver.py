@@ -218,3 +218,30 @@ def test_hippi_matches_reference(golden_dir):
     h = HiPPI(max_iter=50)
     U = h(W, U0, ms, d, projector="hungarian")
     assert h.last_iterations <= 50 and float(U.sum()) == float(sum(ms.tolist()))
+
+
+@pytest.mark.parametrize("sizes,seed", [((33, 34, 33, 33, 46, 30, 34, 38), 77), ((23, 40, 31, 57), 3), ((30, 30, 30, 30, 30), 5), ((12, 20), 9)])
+def test_certified_fast_lap_gives_the_same_solution(sizes, seed):
+    """Opt-in fast path of the Hungarian projections (row-reduction start + uniqueness certificate, SciPy-order solve as
+    the fall-back, lap.cuh): the whole GA-GM solve - every projection of ~200 iterations - must give the same U and the
+    same iteration counts as the SciPy-order solver."""
+    from ttdg_b200 import _C
+    from adapteacher.modeling.GModule.multi_graph_matching import MGM3_unsup
+    m = MGM3_unsup(2, 32).cuda()
+    m.load_state_dict(synth.mgm_unsup_state(0))
+    nodes, labels, masks = synth.mgm_inputs(sizes, seed)
+    m.debug_keep_masks = [k.cuda() for k in masks]
+    with torch.no_grad():
+        m([n.cuda() for n in nodes], [l.cuda() for l in labels], synth.universe(0).cuda())
+    aux = m.last_aux
+    L = _C.lib()
+    prev = L.ttdg_gagm_set_lap_fast(0)
+    try:
+        U0, i0 = ops.gagm_solve(aux["A"], aux["Wds"], aux["U0"], list(sizes), return_info=True)
+        L.ttdg_gagm_set_lap_fast(1)
+        U1, i1 = ops.gagm_solve(aux["A"], aux["Wds"], aux["U0"], list(sizes), return_info=True)
+    finally:
+        L.ttdg_gagm_set_lap_fast(prev)
+    assert torch.equal(U0, U1)
+    a, b = i0.tolist(), i1.tolist()
+    assert a[:5] == b[:5]                                     # same iteration schedule (stages, Sinkhorn / Hungarian counts, LAP calls)

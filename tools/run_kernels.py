@@ -191,8 +191,8 @@ elif what == "gagm_fixed":
             e1.record(); torch.cuda.synchronize()
             ms += e0.elapsed_time(e1) / reps
         inf = info.tolist()
-        print("gagm_fixed sizes %s: %.3f ms, iterations %d (sinkhorn %d, hungarian %d), %.1f us / hungarian iteration incl. everything, graph-0 LAP steps %d"
-              % (sizes, ms, inf[0], inf[1], inf[2], 1e3 * ms / max(inf[2], 1), inf[5]))
+        print("gagm_fixed sizes %s: %.3f ms, iterations %d (sinkhorn %d, hungarian %d), %.1f us / hungarian iteration incl. everything, graph-0 LAP steps %d, fast-path fall-backs %d"
+              % (sizes, ms, inf[0], inf[1], inf[2], 1e3 * ms / max(inf[2], 1), inf[5], inf[7]))
 elif what == "busy":
     # hot (not cold-cache) per-kernel device time of the full step and the GPU-busy fraction, from CUPTI via torch.profiler
     sys.path.insert(0, ROOT)

@@ -22,6 +22,7 @@
 //     Q_g[r][:] = T[slot_g(r)][:],   (W U)[r][u] = sum_h W[r][node_h(u)]
 // and only V1 = A_gg Q_g stays dense: one cluster barrier per iteration, ~1/8 of the FMAs.  Zero terms are skipped in
 // the same order the dense loops add them, so both paths produce the same bits (for G <= 8).
+#include <cstdlib>
 #include "lap.cuh"
 #include "sinkhorn_small.cuh"
 #include <cooperative_groups.h>
@@ -51,6 +52,7 @@ struct GagmParams {
     int G, M, C;
     double init_tau, min_tau, sk_gamma, tol, quad_weight;
     int max_iter, sk_iter, mode, step_projector, sq_transposed;
+    int lap_fast;        // TTDG_LAP_FAST=1: certified row-reduction LAP first, SciPy-order solve as the fall-back (lap.cuh)
     int node_off[GAGM_MAX_G + 1];
 };
 
@@ -119,7 +121,7 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
     __threadfence();
     cluster_sync_all();
 
-    if (tid == 0) { lapw->stat_steps = 0; lapw->stat_hops = 0; }
+    if (tid == 0) { lapw->stat_steps = 0; lapw->stat_hops = 0; lapw->stat_fast_ok = 0; lapw->stat_fast_fallback = 0; }
     int cur = 0, last = 1, last2 = 2;
     double tau = p.init_tau;
     int projector = (p.mode == 1) ? p.step_projector : 0;   // 0 sinkhorn, 1 hungarian
@@ -281,10 +283,10 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                     if (warp == 0) {
                         const double *Zc = Z;
                         if (n <= NU) {
-                            lap_solve_warp(n, NU, LapSmemNegCost{lap_smem_u32(Zc), ZP, 1}, *lapw);
+                            lap_solve_warp(n, NU, LapSmemNegCost{lap_smem_u32(Zc), ZP, 1}, *lapw, p.lap_fast);
                             for (int i = lane; i < n; i += 32) Ug[i * NU + lapw->col4row[i]] = 1.0;
                         } else {
-                            lap_solve_warp(NU, n, LapSmemNegCost{lap_smem_u32(Zc), 1, ZP}, *lapw);
+                            lap_solve_warp(NU, n, LapSmemNegCost{lap_smem_u32(Zc), 1, ZP}, *lapw, p.lap_fast);
                             for (int i = lane; i < NU; i += 32) Ug[lapw->col4row[i] * NU + i] = 1.0;
                         }
                     }
@@ -349,7 +351,7 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
     }
     if (c == 0 && tid == 0 && p.info) {
         p.info[0] = it_total; p.info[1] = it_sk; p.info[2] = it_hg; p.info[3] = n_lap; p.info[4] = n_stage;
-        p.info[5] = lapw->stat_steps; p.info[6] = lapw->stat_hops; p.info[7] = 0;     // graph 0's LAPs: Dijkstra steps, path hops
+        p.info[5] = lapw->stat_steps; p.info[6] = lapw->stat_hops; p.info[7] = lapw->stat_fast_fallback;     // graph 0's LAPs: Dijkstra steps, path hops
     }
 }
 
@@ -361,6 +363,17 @@ static size_t gagm_smem_bytes() {
 }  // namespace ttdg
 
 using namespace ttdg;
+
+static int g_lap_fast = -1;     // -1: read TTDG_LAP_FAST at first use
+
+// Certified fast LAP inside the GA-GM solver (lap.cuh): 0 = SciPy-order solve only (default), 1 = row-reduction start +
+// uniqueness certificate, SciPy-order solve as the fall-back.  Results are identical by construction; info[7] counts the
+// fall-backs of graph 0.  Returns the previous setting.
+extern "C" int ttdg_gagm_set_lap_fast(int on) {
+    const int prev = g_lap_fast < 0 ? 0 : g_lap_fast;
+    g_lap_fast = on ? 1 : 0;
+    return prev;
+}
 
 extern "C" int64_t ttdg_gagm_scratch_bytes(int M, int G) {
     (void)G;
@@ -397,6 +410,8 @@ extern "C" int ttdg_gagm_solve(const float *A, const float *W, const float *U0, 
     p.init_tau = init_tau; p.min_tau = min_tau; p.sk_gamma = sk_gamma; p.tol = converge_tol; p.quad_weight = quad_weight;
     p.max_iter = max_iter; p.sk_iter = sk_iter; p.mode = mode; p.step_projector = step_projector;
     p.trace = trace; p.trace_meta = trace_meta; p.trace_cap = trace ? trace_cap : 0;
+    if (g_lap_fast < 0) { const char *e = getenv("TTDG_LAP_FAST"); g_lap_fast = (e && e[0] == '1') ? 1 : 0; }
+    p.lap_fast = g_lap_fast;
 
     const size_t smem = gagm_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(gagm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

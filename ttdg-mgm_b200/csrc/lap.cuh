@@ -26,6 +26,7 @@ struct LapWork {                     // per-warp shared-memory workspace (state 
     int row4col[LAP_MAX_DIM];
     int visited[LAP_MAX_DIM];        // rows put into SR in the current augmentation, in order
     int stat_steps, stat_hops;       // running totals (lane 0): Dijkstra steps and augmenting-path hops, for profiling
+    int stat_fast_ok, stat_fast_fallback;      // certified fast solves / fall-backs to the SciPy-order solve
 };
 
 // order-preserving map double -> uint64 (no NaNs here)
@@ -69,8 +70,16 @@ struct LapSmemNegCost {
 // Dual update: the rows visited in an augmentation are `cur` and row4col[j] of every scanned, assigned column j, so
 // u[row4col[j]] += minVal - shortest[j] is applied by the lane that owns column j (SciPy: u[i] += minVal -
 // shortest[col4row[i]], the same operands).
-template <int SLOTS, class Cost>
-__device__ void lap_solve_warp_t(int nr, int nc, Cost cost, LapWork &w) {
+//
+// FAST = true (nr <= 32, opt-in): SciPy's order of augmentations and its tie rule only matter when the optimum is not
+// unique, so the solve is (1) started from a row reduction - lane = row: u[i] = min_j c[i][j], the row takes its arg-min
+// column if no lower row wants it (match.any) - which is dual feasible with v = 0 and leaves only the losers of a column
+// conflict to the Dijkstra augmentations below, and (2) CERTIFIED: with c̄ = (c - u) - v the optimum is unique by the
+// margin delta iff no row has a delta-tight edge to a free column and the digraph {i -> i' : c̄[i][col4row[i']] <= delta} is
+// acyclic (Kahn's elimination on 32-bit adjacency masks).  Returns false when the certificate fails (structural ties: universe
+// slots no graph uses) - the caller then runs the SciPy-order solve.
+template <int SLOTS, bool FAST, class Cost>
+__device__ bool lap_solve_warp_t(int nr, int nc, Cost cost, LapWork &w) {
     const int lane = threadIdx.x & 31;
     const uint32_t u_sa = lap_smem_u32(w.u);
     for (int k = lane; k < nr; k += 32) { w.u[k] = 0.0; w.col4row[k] = -1; }
@@ -81,7 +90,18 @@ __device__ void lap_solve_warp_t(int nr, int nc, Cost cost, LapWork &w) {
     for (int t = 0; t < SLOTS; ++t) { vj[t] = 0.0; jc[t] = min(lane + 32 * t, nc - 1); }
     int steps = 0, hops = 0;
     __syncwarp();
+    if (FAST) {
+        double umin = INFINITY;
+        int arg = 0;
+        if (lane < nr)
+            for (int j = 0; j < nc; ++j) { const double cij = cost(lane, j); if (cij < umin) { umin = cij; arg = j; } }
+        const unsigned same = __match_any_sync(TTDG_FULL, lane < nr ? arg : -1 - lane);
+        const bool win = lane < nr && (__ffs(same) - 1 == lane);
+        if (lane < nr) { w.u[lane] = umin; if (win) { w.col4row[lane] = arg; w.row4col[arg] = lane; } }
+        __syncwarp();
+    }
     for (int cur = 0; cur < nr; ++cur) {
+        if (FAST && w.col4row[cur] != -1) continue;             // assigned by the row reduction (warp-uniform)
         double sh[SLOTS];
         int pos[SLOTS], r4c[SLOTS], pth[SLOTS];
 #pragma unroll
@@ -171,13 +191,55 @@ __device__ void lap_solve_warp_t(int nr, int nc, Cost cost, LapWork &w) {
     }
     if (lane == 0) { w.stat_steps += steps; w.stat_hops += hops; }
     __syncwarp();
+    if (!FAST) return true;
+    // ---- uniqueness certificate
+#pragma unroll
+    for (int t = 0; t < SLOTS; ++t) if (lane + 32 * t < nc) w.v[lane + 32 * t] = vj[t];
+    __syncwarp();
+    double scale = 0.0;
+    unsigned adj = 0u;
+    bool free_hit = false;
+    if (lane < nr) scale = fabs(w.u[lane]);
+    for (int o = 16; o > 0; o >>= 1) scale = fmax(scale, __shfl_xor_sync(TTDG_FULL, scale, o));
+    const double delta = 1e-9 * (1.0 + scale);
+    if (lane < nr) {
+        const double ui = w.u[lane];
+        const int mine = w.col4row[lane];
+        for (int j = 0; j < nc; ++j) {
+            if (j == mine) continue;
+            const double cb = (cost(lane, j) - ui) - w.v[j];
+            if (cb <= delta) { const int r = w.row4col[j]; if (r < 0) free_hit = true; else adj |= 1u << r; }
+        }
+    }
+    bool ok = !__any_sync(TTDG_FULL, free_hit);
+    if (ok) {
+        unsigned alive = nr >= 32 ? 0xFFFFFFFFu : ((1u << nr) - 1u);
+        while (alive) {                                         // Kahn: drop the rows no alive row points to
+            const unsigned pointed = __reduce_or_sync(TTDG_FULL, ((alive >> lane) & 1u) ? (adj & alive) : 0u);
+            const unsigned next = alive & pointed;
+            if (next == alive) break;
+            alive = next;
+        }
+        ok = alive == 0u;
+    }
+    if (lane == 0) { if (ok) ++w.stat_fast_ok; else ++w.stat_fast_fallback; }
+    __syncwarp();
+    return ok;
 }
 
+// fast != 0: try the certified row-reduction solve first (rows <= 32 only), fall back to the SciPy-order solve
 template <class Cost>
-__device__ __forceinline__ void lap_solve_warp(int nr, int nc, Cost cost, LapWork &w) {
-    if (nc <= 32) lap_solve_warp_t<1>(nr, nc, cost, w);
-    else if (nc <= 64) lap_solve_warp_t<2>(nr, nc, cost, w);
-    else lap_solve_warp_t<LAP_SLOTS>(nr, nc, cost, w);
+__device__ __forceinline__ void lap_solve_warp(int nr, int nc, Cost cost, LapWork &w, int fast = 0) {
+    if (fast && nr <= 32) {
+        bool ok;
+        if (nc <= 32) ok = lap_solve_warp_t<1, true>(nr, nc, cost, w);
+        else if (nc <= 64) ok = lap_solve_warp_t<2, true>(nr, nc, cost, w);
+        else ok = lap_solve_warp_t<LAP_SLOTS, true>(nr, nc, cost, w);
+        if (ok) return;
+    }
+    if (nc <= 32) lap_solve_warp_t<1, false>(nr, nc, cost, w);
+    else if (nc <= 64) lap_solve_warp_t<2, false>(nr, nc, cost, w);
+    else lap_solve_warp_t<LAP_SLOTS, false>(nr, nc, cost, w);
 }
 
 // hungarian(s) for one stored n1 x n2 fp32 score matrix (leading dimension ld): perm = 0/1 matrix of the
