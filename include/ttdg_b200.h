@@ -128,8 +128,9 @@ int ttdg_gemm_f64acc(int transA, int transB, int m, int n, int k, const void *A,
                      void *stream);
 
 /* Certified fast LAP inside ttdg_gagm_solve: 0 (default; also env TTDG_LAP_FAST) = every Hungarian projection walks SciPy's
- * shortest-augmenting-path order; 1 = start from a row reduction, certify that the optimum is unique by a margin (no tight
- * edge to a free column, tight-edge digraph acyclic) and fall back to the SciPy-order solve otherwise.  Same results by
+ * shortest-augmenting-path order; 1 = start from a row reduction (2 = from a Jacobi auction with epsilon 0), certify that the
+ * optimum is unique by a margin (no tight edge to a free column, tight-edge digraph acyclic) and fall back to the SciPy-order
+ * solve otherwise.  Same results by
  * construction (mgm:324-328 -> utils/hungarian.py:58-65).  Returns the previous setting. */
 int ttdg_gagm_set_lap_fast(int on);
 /* ---------------------------------------------------------------------------------------------

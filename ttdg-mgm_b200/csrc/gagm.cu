@@ -371,7 +371,7 @@ static int g_lap_fast = -1;     // -1: read TTDG_LAP_FAST at first use
 // fall-backs of graph 0.  Returns the previous setting.
 extern "C" int ttdg_gagm_set_lap_fast(int on) {
     const int prev = g_lap_fast < 0 ? 0 : g_lap_fast;
-    g_lap_fast = on ? 1 : 0;
+    g_lap_fast = (on == 1 || on == 2) ? on : 0;              // 2: Jacobi-auction start instead of the row reduction
     return prev;
 }
 
@@ -410,7 +410,7 @@ extern "C" int ttdg_gagm_solve(const float *A, const float *W, const float *U0, 
     p.init_tau = init_tau; p.min_tau = min_tau; p.sk_gamma = sk_gamma; p.tol = converge_tol; p.quad_weight = quad_weight;
     p.max_iter = max_iter; p.sk_iter = sk_iter; p.mode = mode; p.step_projector = step_projector;
     p.trace = trace; p.trace_meta = trace_meta; p.trace_cap = trace ? trace_cap : 0;
-    if (g_lap_fast < 0) { const char *e = getenv("TTDG_LAP_FAST"); g_lap_fast = (e && e[0] == '1') ? 1 : 0; }
+    if (g_lap_fast < 0) { const char *e = getenv("TTDG_LAP_FAST"); g_lap_fast = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
     p.lap_fast = g_lap_fast;
 
     const size_t smem = gagm_smem_bytes();

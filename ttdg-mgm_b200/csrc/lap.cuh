@@ -27,6 +27,8 @@ struct LapWork {                     // per-warp shared-memory workspace (state 
     int visited[LAP_MAX_DIM];        // rows put into SR in the current augmentation, in order
     int stat_steps, stat_hops;       // running totals (lane 0): Dijkstra steps and augmenting-path hops, for profiling
     int stat_fast_ok, stat_fast_fallback;      // certified fast solves / fall-backs to the SciPy-order solve
+    int fast_mode;                   // 1: row-reduction start, 2: Jacobi auction start (set by the caller)
+    unsigned long long bidkey[LAP_MAX_DIM];    // auction: best bid per column of the current round
 };
 
 // order-preserving map double -> uint64 (no NaNs here)
@@ -90,7 +92,54 @@ __device__ bool lap_solve_warp_t(int nr, int nc, Cost cost, LapWork &w) {
     for (int t = 0; t < SLOTS; ++t) { vj[t] = 0.0; jc[t] = min(lane + 32 * t, nc - 1); }
     int steps = 0, hops = 0;
     __syncwarp();
-    if (FAST) {
+    if (FAST && w.fast_mode == 2) {
+        // Jacobi auction with epsilon = 0 (the augmenting row reduction of Jonker-Volgenant, all free rows bidding at once):
+        // lane = row.  A free row finds its best and second-best reduced cost c[i][j] - v[j]; it bids for the best column
+        // with the price cut (second - best); per column the largest cut wins, the previous owner is set free.  Prices
+        // only fall, so the duals stay feasible (u_i = second-best value, tight on the won column) and free columns keep
+        // v = 0.  Ties (cut 0) can ping-pong, hence the round cap: whoever is still free goes to the Dijkstra loop below.
+        for (int k = lane; k < nc; k += 32) { w.v[k] = 0.0; w.bidkey[k] = 0ull; }
+        __syncwarp();
+        int myc = -1, prev_free = 33, stalls = 0;
+        for (int round = 0; round < 16; ++round) {
+            const bool isfree = lane < nr && myc == -1;
+            const int nfree = __popc(__ballot_sync(TTDG_FULL, isfree));
+            if (nfree == 0) break;
+            if (nfree >= prev_free && ++stalls >= 2) break;     // ping-pong on ties: leave the rest to the Dijkstra loop
+            prev_free = nfree;
+            double m1 = INFINITY, m2 = INFINITY;
+            int j1 = 0;
+            unsigned long long mykey = 0ull;
+            if (isfree) {
+                for (int j = 0; j < nc; ++j) {
+                    const double val = cost(lane, j) - w.v[j];
+                    if (val < m1) { m2 = m1; m1 = val; j1 = j; } else if (val < m2) m2 = val;
+                }
+                const double cut = (m2 < INFINITY) ? m2 - m1 : 0.0;
+                mykey = ((lap_ord(cut) & ~31ull) | (unsigned long long)(31 - lane)) | (1ull << 63);
+                atomicMax(&w.bidkey[j1], mykey);
+            }
+            __syncwarp();
+            if (isfree) {
+                if (w.bidkey[j1] == mykey) {                      // winner of column j1
+                    const int old = w.row4col[j1];
+                    if (old >= 0) w.col4row[old] = -1;
+                    w.row4col[j1] = lane; w.col4row[lane] = j1;
+                    w.u[lane] = (m2 < INFINITY) ? m2 : m1;
+                    if (m2 < INFINITY) w.v[j1] -= (m2 - m1);
+                } else {
+                    w.u[lane] = m1;                               // still free: a feasible lower bound for the Dijkstra start
+                }
+            }
+            __syncwarp();
+            if (isfree) w.bidkey[j1] = 0ull;
+            __syncwarp();
+            myc = lane < nr ? w.col4row[lane] : 0;
+        }
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) if (lane + 32 * t < nc) vj[t] = w.v[lane + 32 * t];
+        __syncwarp();
+    } else if (FAST) {
         double umin = INFINITY;
         int arg = 0;
         if (lane < nr)
@@ -231,6 +280,8 @@ __device__ bool lap_solve_warp_t(int nr, int nc, Cost cost, LapWork &w) {
 template <class Cost>
 __device__ __forceinline__ void lap_solve_warp(int nr, int nc, Cost cost, LapWork &w, int fast = 0) {
     if (fast && nr <= 32) {
+        if ((threadIdx.x & 31) == 0) w.fast_mode = fast;
+        __syncwarp();
         bool ok;
         if (nc <= 32) ok = lap_solve_warp_t<1, true>(nr, nc, cost, w);
         else if (nc <= 64) ok = lap_solve_warp_t<2, true>(nr, nc, cost, w);
