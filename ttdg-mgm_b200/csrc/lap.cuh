@@ -77,8 +77,8 @@ struct LapSmemNegCost {
 // unique, so the solve is (1) started from a row reduction - lane = row: u[i] = min_j c[i][j], the row takes its arg-min
 // column if no lower row wants it (match.any) - which is dual feasible with v = 0 and leaves only the losers of a column
 // conflict to the Dijkstra augmentations below, and (2) CERTIFIED: with c̄ = (c - u) - v the optimum is unique by the
-// margin delta iff no row has a delta-tight edge to a free column and the digraph {i -> i' : c̄[i][col4row[i']] <= delta} is
-// acyclic (Kahn's elimination on 32-bit adjacency masks).  Returns false when the certificate fails (structural ties: universe
+// margin delta iff no chain of delta-tight edges leads from a row whose column has a zero price to a free column, and the
+// digraph {i -> i' : c̄[i][col4row[i']] <= delta} is acyclic (Kahn's elimination on 32-bit adjacency masks).  Returns false when the certificate fails (structural ties: universe
 // slots no graph uses) - the caller then runs the SciPy-order solve.
 template <int SLOTS, bool FAST, class Cost>
 __device__ bool lap_solve_warp_t(int nr, int nc, Cost cost, LapWork &w) {
@@ -260,7 +260,18 @@ __device__ bool lap_solve_warp_t(int nr, int nc, Cost cost, LapWork &w) {
             if (cb <= delta) { const int r = w.row4col[j]; if (r < 0) free_hit = true; else adj |= 1u << r; }
         }
     }
-    bool ok = !__any_sync(TTDG_FULL, free_hit);
+    // A switch to a free column costs  sum of c̄ on the new edges + |v| of the ABANDONED column  (free columns have v = 0,
+    // prices are <= 0): it ties only if the chain of tight edges that ends in the free column STARTS at a row whose own column
+    // has a zero price.  reach = rows from which a free column is reachable over tight edges.
+    unsigned reach = __ballot_sync(TTDG_FULL, free_hit);
+    while (true) {
+        const unsigned nxt = __ballot_sync(TTDG_FULL, lane < nr && (free_hit || (adj & reach) != 0u));
+        if (nxt == reach) break;
+        reach = nxt;
+    }
+    bool zero_start = false;
+    if (lane < nr && ((reach >> lane) & 1u)) zero_start = fabs(w.v[w.col4row[lane]]) <= delta;
+    bool ok = !__any_sync(TTDG_FULL, zero_start);
     if (ok) {
         unsigned alive = nr >= 32 ? 0xFFFFFFFFu : ((1u << nr) - 1u);
         while (alive) {                                         // Kahn: drop the rows no alive row points to
