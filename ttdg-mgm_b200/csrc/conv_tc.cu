@@ -52,7 +52,6 @@ struct TcParams {
     int in_stride;                   // 1, or 2 for a strided 1x1 conv: the tensor map has element strides {1, 2, 2, 1}
     int stem;                        // 7x7 stride-2 stem on the padded image: k-block r = filter row, box = 8-pixel windows
     int out_stride, outH, outW;      // output pixel (ho, wo) is stored at (ho, wo) * out_stride of an outH x outW map
-    int dbg_skip_blo;                // experiment (TTDG_DEBUG_SKIP_BLO=1, wrong results): do not load the lo weight tile
     int a_tx;                        // bytes one activation box delivers: BW * BH * BI rows of 128 B (<= A_BYTES)
 };
 
@@ -358,12 +357,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int btap = p.flip ? (p.R - 1 - r) * p.S + (p.S - 1 - s) : tap;
                     mbar_wait(&sm.empty[stage], phase ^ 1);
                     unsigned char *st = sm.tiles + stage * Cfg::STAGE_BYTES;
-                    mbar_expect_tx(&sm.full[stage], (uint32_t)(p.a_tx + ((PRECISE && !p.dbg_skip_blo) ? 2 : 1) * Cfg::B_BYTES));
+                    mbar_expect_tx(&sm.full[stage], (uint32_t)(p.a_tx + (PRECISE ? 2 : 1) * Cfg::B_BYTES));
                     if (p.stem) tma_load_4d(st, &tmA, &sm.full[stage], 0, w0, 2 * h0 + r - 3, i0);
                     else tma_load_4d(st, &tmA, &sm.full[stage], c0, (w0 + s - p.pad) * p.in_stride, (h0 + r - p.pad) * p.in_stride, i0);
                     if (CL == 1) {
                         tma_load_3d(st + Cfg::A_BYTES, &tmB, &sm.full[stage], c0, n0, btap);
-                        if (PRECISE && !p.dbg_skip_blo) tma_load_3d(st + Cfg::A_BYTES + Cfg::B_BYTES, &tmBlo, &sm.full[stage], c0, n0, btap);
+                        if (PRECISE) tma_load_3d(st + Cfg::A_BYTES + Cfg::B_BYTES, &tmBlo, &sm.full[stage], c0, n0, btap);
                     } else {                                 // rows [crank * SLICE_ROWS, ...) of the weight tile, to every CTA of the cluster
                         tma_load_3d_mc(st + Cfg::A_BYTES + crank * SLICE_BYTES, &tmB, &sm.full[stage], c0, n0 + crank * SLICE_ROWS, btap, CL_MASK);
                         if (PRECISE) tma_load_3d_mc(st + Cfg::A_BYTES + Cfg::B_BYTES + crank * SLICE_BYTES, &tmBlo, &sm.full[stage], c0,
@@ -960,7 +959,6 @@ extern "C" int ttdg_conv_tc(const float *x, const float *wk_hi, const float *wk_
     p.outH = out_stride == 1 ? p.Ho : outH; p.outW = out_stride == 1 ? p.Wo : outW;
     if (out_stride == 2 && ((p.Ho - 1) * 2 >= outH || (p.Wo - 1) * 2 >= outW)) return TTDG_E_ARG;
     p.R = R; p.S = S; p.pad = pad; p.flip = flip; p.kslabs = Cin / TC_BK;
-    { static int skip = -1; if (skip < 0) { const char *e = getenv("TTDG_DEBUG_SKIP_BLO"); skip = (e && e[0] == '1') ? 1 : 0; } p.dbg_skip_blo = skip; }
     if (p.Ho < 1 || p.Wo < 1) return TTDG_E_ARG;
     if (res_mode == 2 && ((p.Ho | p.Wo) & 1)) return TTDG_E_ARG;
     p.BW = pow2_ge(p.Wo) < TC_BM ? pow2_ge(p.Wo) : TC_BM;
