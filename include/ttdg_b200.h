@@ -246,7 +246,7 @@ int ttdg_preprocess(const unsigned char *img_u8, int N, int H, int W, int Wp, in
 
 /* Tensor-core version of ttdg_conv_fwd / stride-1 ttdg_conv_dgrad: tcgen05.mma.kind::tf32 fed by TMA (activations as a 4-D
  * NHWC tensor map - filter taps are coordinate shifts, padding is TMA's out-of-bounds zero fill), fp32 accumulators in
- * TMEM, same fused epilogue.  Requires Cin % 32 == 0, Cout % 64 == 0, stride 1 (ttdg_conv_tc_supported).
+ * TMEM, same fused epilogue.  Persistent: one CTA per SM walks its (pixel tile, N tile) items.  Requires Cin % 32 == 0, Cout % 64 == 0, stride 1 (ttdg_conv_tc_supported).
  *   x          : N x H x W x Cin, fp32.
  *   wk_hi, wk_lo: weights K-major [taps][n][k], split into hi = tf32(w) and lo = w - hi: forward = [R*S][Cout][Cin]
  *                (ttdg_weight_transpose_split of the [R][S][Cin][Cout] parameter); data gradient (flip = 1,
@@ -267,10 +267,12 @@ int ttdg_conv_tc(const float *x, const float *wk_hi, const float *wk_lo, const f
                  const float *residual, int res_mode, int relu, int flip, int N, int H, int W, int Cin, int Cout, int R,
                  int S, int pad, int in_stride, int out_stride, int outH, int outW, float *y, void *stream);
 /* Weight gradient on tensor cores (stride-1 convs and 1x1 stride-2 convs, Cin % 128 == 0, Cout % 64 == 0): dw [R][S][Cin][Cout] +=
- * sum_pixels X[pixel + tap][ci] dY[pixel][co].  Both operands are MN-major (pixels = GEMM k = slow memory dimension):
- * TMA boxes of {32 channels, 32 pixels} with the 128-byte / 32-byte-atom swizzle, the only MN-major layout tcgen05
- * takes for 32-bit operands.  Accumulated into dw with fp32 atomics over the pixel splits.  precise != 0 = 3xTF32 (both
- * operands split inside the pipeline), 0 = single-pass TF32.  Replaces the weight half of torch autograd's conv
+ * sum_pixels X[pixel + tap][ci] dY[pixel][co].  Both operands are MN-major in memory (pixels = GEMM k = slow dimension):
+ * TMA boxes of {32 channels, 32 pixels}.  precise != 0 = 3xTF32: X is staged unswizzled and split by the kernel into TENSOR
+ * MEMORY (A operand from TMEM, K-major by construction), dY is split in place in shared memory with the 128-byte / 32-byte-
+ * atom swizzle (the only MN-major layout tcgen05 takes for 32-bit operands); 0 = single-pass TF32 with both operands from
+ * shared memory.  Accumulated into dw with coalesced fp32 reductions over the pixel splits (dw may be the parameter's slice
+ * of the flat gradient bucket).  Replaces the weight half of torch autograd's conv
  * backward behind loss.backward() (engine/trainer.py:481). */
 int ttdg_wgrad_tc_supported(int Cin, int Cout, int stride);
 int ttdg_wgrad_tc(const float *x, const float *dy, int precise, int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
@@ -298,7 +300,8 @@ int ttdg_box_predict(const float *cls, int ld_cls, const float *reg, int ld_reg,
 /* Per-category NMS (torchvision batched_nms semantics) for `batch` images at once: boxes_sorted [batch][n][4] already
  * sorted by descending score, category [batch][n] (boxes of different categories never suppress each other).
  * keep [batch][max_keep] receives indices in order, n_keep [batch] their number.
- * scratch: ttdg_nms_scratch_bytes(batch, n). */
+ * scratch: ttdg_nms_scratch_bytes(batch, n) (used for n > 2560: suppression-mask kernel over the upper triangle + sweep;
+ * smaller problems run in one CTA per image with boxes and state in shared memory). */
 int64_t ttdg_nms_scratch_bytes(int batch, int n);
 int ttdg_nms(const float *boxes_sorted, const int32_t *category, int batch, int n, float iou_thresh, int max_keep,
              int32_t *keep, int32_t *n_keep, void *scratch, void *stream);
