@@ -7,11 +7,28 @@ third-party dependency that is neither vendored under /root/reference nor instal
 are restated from SURVEY.md Appendix A ([recalled]) on top of torch / torchvision.ops (roi_align aligned=True, nms,
 batched_nms).  Functional style over a state dict with d2's parameter names.  NCHW fp32 throughout.
 """
+import contextlib
 import math
 
 import torch
 import torch.nn.functional as F
 import torchvision.ops as tvo
+
+
+@contextlib.contextmanager
+def float64():
+    """Run the restatement in float64 (state dict and images converted by the caller): the noise-free limit of the same
+    algorithm, against which both the fp32 restatement and the CUDA path are measured in the parity tests."""
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        yield
+    finally:
+        torch.set_default_dtype(old)
+
+
+def _dt():
+    return torch.get_default_dtype()
 
 PIXEL_MEAN = (103.530, 116.280, 123.675)      # d2 defaults, applied to whatever channel order arrives (SURVEY App. A)
 STRIDES = (4, 8, 16, 32, 64)
@@ -43,7 +60,7 @@ def bottleneck(x, sd, q, stride, has_shortcut):
 
 def preprocess(images_u8):
     """list of uint8 C x H x W -> N x 3 x H x W float (all the same size here; d2 pads to a multiple of 32)."""
-    x = torch.stack([im.float() for im in images_u8])
+    x = torch.stack([im.to(_dt()) for im in images_u8])
     mean = torch.tensor(PIXEL_MEAN).reshape(1, 3, 1, 1)
     x = x - mean                                                     # std = 1
     H, W = x.shape[-2:]
@@ -86,8 +103,8 @@ def cell_anchors():
 
 
 def grid_anchors(h, w, stride):
-    sx = torch.arange(0, w * stride, step=stride, dtype=torch.float32)
-    sy = torch.arange(0, h * stride, step=stride, dtype=torch.float32)
+    sx = torch.arange(0, w * stride, step=stride, dtype=_dt())
+    sy = torch.arange(0, h * stride, step=stride, dtype=_dt())
     yy, xx = torch.meshgrid(sy, sx, indexing="ij")
     shifts = torch.stack((xx.reshape(-1), yy.reshape(-1), xx.reshape(-1), yy.reshape(-1)), dim=1)
     return (shifts.view(-1, 1, 4) + cell_anchors().view(1, -1, 4)).reshape(-1, 4)
@@ -156,7 +173,7 @@ def assign_levels(boxes, min_level=2, max_level=5, canonical_size=224, canonical
 def roi_pool(feats4, boxes_per_image, out_size):
     """ROIPooler with ROIAlignV2 (aligned, sampling_ratio 0) over p2..p5."""
     boxes = torch.cat(boxes_per_image)
-    bidx = torch.cat([torch.full((len(b),), i, dtype=torch.float32) for i, b in enumerate(boxes_per_image)])
+    bidx = torch.cat([torch.full((len(b),), i, dtype=_dt()) for i, b in enumerate(boxes_per_image)])
     rois = torch.cat([bidx[:, None], boxes], dim=1)
     lv = assign_levels(boxes)
     C = feats4[0].shape[1]
@@ -217,8 +234,8 @@ def paste_masks(probs, boxes, H, W, threshold=0.5):
     if n == 0:
         return torch.zeros(0, H, W, dtype=torch.bool)
     x0, y0, x1, y1 = boxes[:, 0:1], boxes[:, 1:2], boxes[:, 2:3], boxes[:, 3:4]
-    img_y = torch.arange(0, H, dtype=torch.float32) + 0.5
-    img_x = torch.arange(0, W, dtype=torch.float32) + 0.5
+    img_y = torch.arange(0, H, dtype=_dt()) + 0.5
+    img_x = torch.arange(0, W, dtype=_dt()) + 0.5
     img_y = (img_y - y0) / (y1 - y0) * 2 - 1
     img_x = (img_x - x0) / (x1 - x0) * 2 - 1
     gx = img_x[:, None, :].expand(n, H, W)

@@ -132,8 +132,11 @@ class MGM3_unsup(nn.Module):
         if max(sizes) > 96:
             raise ValueError("graphs must have at most 96 nodes (the sampler yields at most 95, build_graph.py:189-195)")
         X = torch.cat(list(nodes), dim=0)                                        # M x 256, carries the gradient
+        keep = self.debug_keep_masks
+        if callable(keep):                                                       # parity hook: masks as a function of the sizes
+            keep = [k.to(X.device) for k in keep(sizes)]
         with torch.no_grad():
-            A = self.intra_domain_graph.adjacency(X, sizes, self.debug_keep_masks)          # mgm:496-502
+            A = self.intra_domain_graph.adjacency(X, sizes, keep)                # mgm:496-502
             U0 = ops.linear(X, U)                                                # mgm:531-532 (detached)
         aff = self.node_affinity.forward_pairs(X, sizes, ops.mgm_pairs(len(sizes)))          # mgm:504-525 (learned part)
         loss, Wds, U_b, flags, info = ops.matching_loss(aff, A, U0, sizes, self._cfg(), self.debug_U_override)

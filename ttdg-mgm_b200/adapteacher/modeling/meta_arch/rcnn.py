@@ -65,6 +65,7 @@ class DAobjTwoStagePseudoLabGeneralizedRCNN(nn.Module):
             raise NotImplementedError("only branch='TTT' and eval-mode inference are on the test-time path (SURVEY 8)")
         det = self._det[0]
         feats, props, dets = det.detect_ttt(images)         # rcnn.py:219-226, 333-345
+        self.last_ttt = {"proposals": props, "detections": dets}            # (views; read by the parity tests only)
         size = tuple(images[0].shape[-2:])
         proposals_roih = [Instances(size, pred_boxes=Boxes(b), scores=s, pred_classes=c) for b, s, c in dets]
         features = [f.permute(0, 3, 1, 2) for f in feats]   # NCHW views of the NHWC pyramid (rcnn.py:351)
