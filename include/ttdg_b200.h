@@ -142,8 +142,10 @@ int ttdg_gagm_set_lap_fast(int on);
  * A, W: M x M; U0, U: M x n_univ (n_univ == 32); ms_h: HOST int32[G].
  * mode: 0 = full solve; 1 = exactly one iteration with projector `step_projector` (0 sinkhorn, 1 hungarian)
  * at temperature init_tau (teacher-forced parity tests).
- * info (int32[8], device): {iterations, sinkhorn-stage iterations, hungarian-stage iterations, LAP calls,
- *                           sinkhorn stages, 0, 0, 0}.
+ * info (int32[16], device): {iterations, sinkhorn-stage iterations, hungarian-stage iterations, LAP calls,
+ *                           sinkhorn stages, Dijkstra steps / path hops / certificate fall-backs of graph 0's LAPs,
+ *                           cycle accounting of CTA 0 in units of 1024 cycles: whole kernel, Hungarian-stage iterations,
+ *                           inside the LAP, waiting at cluster barriers, 0, 0, 0, 0}.
  * scratch: ttdg_gagm_scratch_bytes(M, G).
  * trace (optional, may be NULL): fp64[(trace_cap + 1)][M][32] receives U_t of every iteration t <= trace_cap
  * (U_0 = U0) and trace_meta fp64[trace_cap][2] = {projector, tau} - lets a test verify EVERY iteration of the

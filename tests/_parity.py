@@ -142,7 +142,10 @@ def eval_parity(m, sd_det, cfg, with_f64=True, log=print):
     rep["free_running_gpu_vs_fp32"] = free_running(res_g, res_o)
     # ---- teacher-forced, stage by stage (continuous arithmetic only)
     # backbone + FPN
-    rep["pyramid_rel_max"] = max(float((f.permute(0, 3, 1, 2).cpu() - r).abs().max() / r.abs().max()) for f, r in zip(feats_g, feats_o))
+    def pyr(fa, fb):
+        return max(float((a.double() - b.double()).abs().max() / b.double().abs().max()) for a, b in zip(fa, fb))
+    feats_g_nchw = [f.permute(0, 3, 1, 2).cpu() for f in feats_g]
+    rep["pyramid_rel_max"] = pyr(feats_g_nchw, feats_o)
     # box head on the ORACLE's proposals
     props_forced = [(b.cuda(), s.cuda()) for b, s in props_o]
     dets_f = m.roi_heads.forward_box(feats_g, props_forced, (S, S))
@@ -171,8 +174,10 @@ def eval_parity(m, sd_det, cfg, with_f64=True, log=print):
     if with_f64:
         t1 = time.time()
         with dp.float64():
-            res_64 = dp.inference({k: v.double() for k, v in sd_det.items()}, images)[0]
+            res_64, feats_64 = dp.inference({k: v.double() for k, v in sd_det.items()}, images)[:2]
         log("  eval: oracle float64 %.1f s" % (time.time() - t1))
+        rep["pyramid_rel_max_gpu_vs_f64"] = pyr(feats_g_nchw, feats_64)
+        rep["pyramid_rel_max_fp32_vs_f64"] = pyr(feats_o, feats_64)
         rep["free_running_fp32_vs_f64"] = free_running(res_o, res_64)
         rep["free_running_gpu_vs_f64"] = free_running(res_g, res_64)
     return rep
@@ -248,13 +253,14 @@ def ttt_parity(m, sd_det, sd_mgm, U, cfg, with_f64=True, log=print):
         row["weight_max_abs_gpu"] = float((p1[k].double() - p.detach().double()).abs().max())
         rows.append(row)
     rep["per_tensor"] = rows
+    tot_ref = np.sqrt(sum(r["norm"] ** 2 for r in rows))
+    all_rows, rows = rows, [r for r in rows if r["norm"] > 1e-9 * tot_ref]     # e.g. fc_M.2.bias: Sinkhorn is shift invariant
     e = np.array([r["gpu"] for r in rows])
     rep["grad_rel_l2_gpu_vs_%s" % ref_name] = {"max": float(e.max()), "median": float(np.median(e)), "tensors": len(rows)}
-    tot_ref = np.sqrt(sum(r["norm"] ** 2 for r in rows))
     rep["grad_bucket_rel_l2_gpu"] = float(np.sqrt(sum((r["gpu"] * r["norm"]) ** 2 for r in rows)) / tot_ref)
     u = np.array([r["update_gpu"] for r in rows])
     rep["update_rel_l2_gpu"] = {"max": float(u.max()), "median": float(np.median(u))}
-    rep["weight_max_abs_gpu"] = float(max(r["weight_max_abs_gpu"] for r in rows))
+    rep["weight_max_abs_gpu"] = float(max(r["weight_max_abs_gpu"] for r in all_rows))
     if with_f64:
         e32 = np.array([r["fp32"] for r in rows])
         rep["grad_rel_l2_fp32_vs_f64"] = {"max": float(e32.max()), "median": float(np.median(e32))}

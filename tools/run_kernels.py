@@ -183,16 +183,21 @@ elif what == "gagm_fixed":
         with torch.no_grad():
             m([n.to(dev) for n in nodes], [l.to(dev) for l in labels], U)
         aux = m.last_aux
-        ms = 0.0
-        for _ in range(reps):
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            U2, info = ops.gagm_solve(aux["A"], aux["Wds"], aux["U0"], list(sizes), return_info=True)
-            e1.record(); torch.cuda.synchronize()
-            ms += e0.elapsed_time(e1) / reps
-        inf = info.tolist()
-        print("gagm_fixed sizes %s: %.3f ms, iterations %d (sinkhorn %d, hungarian %d), %.1f us / hungarian iteration incl. everything, graph-0 LAP steps %d, fast-path fall-backs %d"
-              % (sizes, ms, inf[0], inf[1], inf[2], 1e3 * ms / max(inf[2], 1), inf[5], inf[7]))
+        from ttdg_b200 import _C
+        for mode in (0, 2, 3):
+            prev = _C.lib().ttdg_gagm_set_lap_fast(mode)
+            ms = 0.0
+            for _ in range(reps + 1):
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                U2, info = ops.gagm_solve(aux["A"], aux["Wds"], aux["U0"], list(sizes), return_info=True)
+                e1.record(); torch.cuda.synchronize()
+                if _ > 0:
+                    ms += e0.elapsed_time(e1) / reps
+            _C.lib().ttdg_gagm_set_lap_fast(prev)
+            inf = info.tolist()
+            print("gagm_fixed lap_fast %d sizes %s: %.3f ms, iterations %d (sinkhorn %d, hungarian %d), %.1f us / hungarian iteration incl. everything, graph-0 LAP steps %d, fast-path fall-backs %d; CTA-0 kcycles: kernel %d, hungarian stage %d, in LAP %d, barrier wait %d"
+                  % (mode, sizes, ms, inf[0], inf[1], inf[2], 1e3 * ms / max(inf[2], 1), inf[5], inf[7], inf[8], inf[9], inf[10], inf[11]))
 elif what == "busy":
     # hot (not cold-cache) per-kernel device time of the full step and the GPU-busy fraction, from CUPTI via torch.profiler
     sys.path.insert(0, ROOT)

@@ -122,6 +122,9 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
     cluster_sync_all();
 
     if (tid == 0) { lapw->stat_steps = 0; lapw->stat_hops = 0; lapw->stat_fast_ok = 0; lapw->stat_fast_fallback = 0; }
+    // cycle accounting of CTA 0 / thread 0 (info[8..12], units of 1024 cycles): whole kernel, Hungarian-stage iterations, LAP, cluster-barrier waits
+    const long long ck_start = clock64();
+    long long ck_hung = 0, ck_lap = 0, ck_bar = 0;
     int cur = 0, last = 1, last2 = 2;
     double tau = p.init_tau;
     int projector = (p.mode == 1) ? p.step_projector : 0;   // 0 sinkhorn, 1 hungarian
@@ -132,6 +135,7 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
         bool stop_all = false;
         for (int i = 0; i < p.max_iter; ++i) {
             { const int nxt = last2; last2 = last; last = cur; cur = nxt; }   // lastU2 = lastU; lastU = U (mgm:313-314)
+            const long long ck_it = clock64();
             const double *Ul = p.Ubuf + (size_t)last * UB;      // U_t
             const double *Ul2 = p.Ubuf + (size_t)last2 * UB;    // U_{t-1}
             double *Un = p.Ubuf + (size_t)cur * UB;             // U_{t+1}
@@ -281,14 +285,19 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                     for (int e = tid; e < n * NU; e += GAGM_THREADS) Ug[e] = 0.0;
                     __syncthreads();
                     if (warp == 0) {
+                        const long long ck_l = clock64();
                         const double *Zc = Z;
+                        const int lf = p.lap_fast == 3 ? 0 : p.lap_fast;
                         if (n <= NU) {
-                            lap_solve_warp(n, NU, LapSmemNegCost{lap_smem_u32(Zc), ZP, 1}, *lapw, p.lap_fast);
+                            if (!(p.lap_fast == 3 && lap_lean_warp(n, NU, LapSmemNegCostP{Zc, ZP, 1}, *lapw)))
+                                lap_solve_warp(n, NU, LapSmemNegCost{lap_smem_u32(Zc), ZP, 1}, *lapw, lf);
                             for (int i = lane; i < n; i += 32) Ug[i * NU + lapw->col4row[i]] = 1.0;
                         } else {
-                            lap_solve_warp(NU, n, LapSmemNegCost{lap_smem_u32(Zc), 1, ZP}, *lapw, p.lap_fast);
+                            if (!(p.lap_fast == 3 && lap_lean_warp(NU, n, LapSmemNegCostP{Zc, 1, ZP}, *lapw)))
+                                lap_solve_warp(NU, n, LapSmemNegCost{lap_smem_u32(Zc), 1, ZP}, *lapw, lf);
                             for (int i = lane; i < NU; i += 32) Ug[lapw->col4row[i] * NU + i] = 1.0;
                         }
+                        ck_lap += clock64() - ck_l;
                     }
                 }
                 __syncthreads();
@@ -324,13 +333,14 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                 p.normpart[2 * c] = a; p.normpart[2 * c + 1] = b;
             }
             __threadfence();
-            cluster_sync_all();
+            { const long long ck_b = clock64(); cluster_sync_all(); ck_bar += clock64() - ck_b; }
             double n1 = 0.0, n2 = 0.0;
             for (int cc = 0; cc < C; ++cc) { n1 += __ldcg(p.normpart + 2 * cc); n2 += __ldcg(p.normpart + 2 * cc + 1); }
             if (p.trace_meta && c == 0 && tid == 0 && it_total < p.trace_cap) {
                 p.trace_meta[2 * it_total] = (double)projector; p.trace_meta[2 * it_total + 1] = tau;
             }
             ++it_total;
+            if (projector == 1) ck_hung += clock64() - ck_it;
             binU = (projector == 1);
             if (projector == 0) ++it_sk; else { ++it_hg; n_lap += G; }
             if (p.mode == 1) { stop_all = true; break; }
@@ -352,6 +362,8 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
     if (c == 0 && tid == 0 && p.info) {
         p.info[0] = it_total; p.info[1] = it_sk; p.info[2] = it_hg; p.info[3] = n_lap; p.info[4] = n_stage;
         p.info[5] = lapw->stat_steps; p.info[6] = lapw->stat_hops; p.info[7] = lapw->stat_fast_fallback;     // graph 0's LAPs: Dijkstra steps, path hops
+        p.info[8] = (int)((clock64() - ck_start) >> 10); p.info[9] = (int)(ck_hung >> 10); p.info[10] = (int)(ck_lap >> 10);
+        p.info[11] = (int)(ck_bar >> 10);
     }
 }
 
@@ -370,8 +382,8 @@ static int g_lap_fast = -1;     // -1: read TTDG_LAP_FAST at first use
 // uniqueness certificate, SciPy-order solve as the fall-back.  Results are identical by construction; info[7] counts the
 // fall-backs of graph 0.  Returns the previous setting.
 extern "C" int ttdg_gagm_set_lap_fast(int on) {
-    const int prev = g_lap_fast < 0 ? 0 : g_lap_fast;
-    g_lap_fast = (on == 1 || on == 2) ? on : 0;              // 2: Jacobi-auction start instead of the row reduction
+    const int prev = g_lap_fast < 0 ? 3 : g_lap_fast;
+    g_lap_fast = (on >= 1 && on <= 3) ? on : 0;              // 2: Jacobi-auction start instead of the row reduction; 3: lean certified solve
     return prev;
 }
 
@@ -410,7 +422,7 @@ extern "C" int ttdg_gagm_solve(const float *A, const float *W, const float *U0, 
     p.init_tau = init_tau; p.min_tau = min_tau; p.sk_gamma = sk_gamma; p.tol = converge_tol; p.quad_weight = quad_weight;
     p.max_iter = max_iter; p.sk_iter = sk_iter; p.mode = mode; p.step_projector = step_projector;
     p.trace = trace; p.trace_meta = trace_meta; p.trace_cap = trace ? trace_cap : 0;
-    if (g_lap_fast < 0) { const char *e = getenv("TTDG_LAP_FAST"); g_lap_fast = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
+    if (g_lap_fast < 0) { const char *e = getenv("TTDG_LAP_FAST"); g_lap_fast = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3; }
     p.lap_fast = g_lap_fast;
 
     const size_t smem = gagm_smem_bytes();

@@ -287,10 +287,228 @@ __device__ bool lap_solve_warp_t(int nr, int nc, Cost cost, LapWork &w) {
     return ok;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Lean certified solve (fast mode 3, nr <= 32): the GA-GM solver's default Hungarian projection.
+//
+// The optimum of the projector's LAP is almost always unique by a wide margin (generic fp64 costs); then ANY exact method
+// returns SciPy's assignment and SciPy's scan order / tie rule are irrelevant.  So: (A) a few Jacobi auction rounds with
+// epsilon = 0 (lane = row: best and second-best reduced cost, bid = price cut, largest cut wins the column, feasible duals
+// throughout) settle the uncontested rows; (B) the rows still free are augmented by a Dijkstra whose step carries none of
+// SciPy's bookkeeping (no `remaining` list positions, no tie keys): lane = column, per-column state in registers, one
+// 32-bit redux.min on the high word of the non-negative fp64 distance + one ballot + two shuffles per step (~1/3 of the
+// instructions of the SciPy-order step); (C) lap_certificate() proves from the duals that the assignment is optimal AND the
+// only optimum within a margin delta - otherwise the caller runs the SciPy-order solve.  Measured on the bench workload's
+// cost matrices (oracle trajectory, 1600 LAPs): 3 rounds leave 13 of 32 rows free and 163 instead of 246 Dijkstra steps on
+// the slowest graph of an iteration; a full auction instead of (B) does NOT work here (rows want the same few columns:
+// median 220 rounds of price war).
+struct LapSmemNegCostP {             // cost(i, j) = -z[i * si + j * sj], plain shared-memory loads (the tile is constant during a solve)
+    const double *z; int si, sj;
+    __device__ __forceinline__ double operator()(int i, int j) const { return -z[i * si + j * sj]; }
+};
+
+constexpr int LAP_ARR_ROUNDS = 3;
+
+// Proves optimality and uniqueness of w.col4row from the duals w.u / w.v (fp64).  c̄ = (c - u) - v.
+//   feasibility:  c̄ >= -eps everywhere, |c̄| <= eps on the assignment, v <= eps, v = 0 on free columns  => optimal (weak duality);
+//   uniqueness:   any other assignment costs  sum c̄(new edges) + sum |v|(abandoned columns)  more, so the optimum is unique by
+//   the margin delta iff (a) the digraph {i -> i' : c̄[i][col4row[i']] <= delta} on the rows is acyclic (Kahn's elimination on
+//   32-bit adjacency masks) and (b) no chain of delta-tight edges leads from a row whose own column has |v| <= delta to a free
+//   column (backward reachability by ballots).  lane = row, nr <= 32.
+template <class Cost>
+__device__ bool lap_certificate(int nr, int nc, Cost cost, LapWork &w) {
+    const int lane = threadIdx.x & 31;
+    double scale = 0.0;
+    unsigned adj = 0u;
+    bool free_hit = false, bad = false;
+    if (lane < nr) scale = fabs(w.u[lane]);
+    for (int o = 16; o > 0; o >>= 1) scale = fmax(scale, __shfl_xor_sync(TTDG_FULL, scale, o));
+    const double delta = 1e-9 * (1.0 + scale), eps = 1e-12 * (1.0 + scale);
+    if (lane < nr) {
+        const double ui = w.u[lane];
+        const int mine = w.col4row[lane];
+        bad = mine < 0 || mine >= nc || w.row4col[mine] != lane;
+        for (int j = 0; j < nc; ++j) {
+            const double vj = w.v[j];
+            const double cb = (cost(lane, j) - ui) - vj;
+            const int r = w.row4col[j];
+            if (j == mine) { bad = bad || fabs(cb) > eps; continue; }
+            bad = bad || cb < -eps || vj > eps || (r < 0 && vj != 0.0);
+            if (cb <= delta) { if (r < 0) free_hit = true; else adj |= 1u << r; }
+        }
+    }
+    if (__any_sync(TTDG_FULL, bad)) return false;
+    unsigned reach = __ballot_sync(TTDG_FULL, free_hit);
+    while (true) {
+        const unsigned nxt = __ballot_sync(TTDG_FULL, lane < nr && (free_hit || (adj & reach) != 0u));
+        if (nxt == reach) break;
+        reach = nxt;
+    }
+    bool zero_start = false;
+    if (lane < nr && ((reach >> lane) & 1u)) zero_start = fabs(w.v[w.col4row[lane]]) <= delta;
+    if (__any_sync(TTDG_FULL, zero_start)) return false;
+    unsigned alive = nr >= 32 ? 0xFFFFFFFFu : ((1u << nr) - 1u);
+    while (alive) {                                             // Kahn: drop the rows no alive row points to
+        const unsigned pointed = __reduce_or_sync(TTDG_FULL, ((alive >> lane) & 1u) ? (adj & alive) : 0u);
+        const unsigned next = alive & pointed;
+        if (next == alive) break;
+        alive = next;
+    }
+    return alive == 0u;
+}
+
+template <int SLOTS, class Cost>
+__device__ bool lap_lean_warp_t(int nr, int nc, Cost cost, LapWork &w) {
+    const int lane = threadIdx.x & 31;
+    for (int k = lane; k < nr; k += 32) { w.u[k] = 0.0; w.col4row[k] = -1; }
+    for (int k = lane; k < nc; k += 32) { w.row4col[k] = -1; w.v[k] = 0.0; w.bidkey[k] = 0ull; }
+    __syncwarp();
+    // ---- (A) Jacobi auction rounds, lane = row
+    int steps = 0, hops = 0;
+    {
+        int myc = -1;
+        for (int round = 0; round < LAP_ARR_ROUNDS; ++round) {
+            const bool isfree = lane < nr && myc == -1;
+            if (!__any_sync(TTDG_FULL, isfree)) break;
+            double m1 = INFINITY, m2 = INFINITY;
+            int j1 = 0;
+            unsigned long long mykey = 0ull;
+            if (isfree) {
+                // two independent half scans (even / odd columns) halve the compare-select dependency chain
+                double a1 = INFINITY, a2 = INFINITY, b1 = INFINITY, b2 = INFINITY;
+                int ja = 0, jb = 0;
+                int j = 0;
+                for (; j + 1 < nc; j += 2) {
+                    const double va = cost(lane, j) - w.v[j], vb = cost(lane, j + 1) - w.v[j + 1];
+                    if (va < a1) { a2 = a1; a1 = va; ja = j; } else if (va < a2) a2 = va;
+                    if (vb < b1) { b2 = b1; b1 = vb; jb = j + 1; } else if (vb < b2) b2 = vb;
+                }
+                if (j < nc) { const double va = cost(lane, j) - w.v[j]; if (va < a1) { a2 = a1; a1 = va; ja = j; } else if (va < a2) a2 = va; }
+                if (b1 < a1) { m1 = b1; j1 = jb; m2 = fmin(a1, b2); } else { m1 = a1; j1 = ja; m2 = fmin(b1, a2); }
+                const double cut = (m2 < INFINITY) ? m2 - m1 : 0.0;
+                mykey = ((lap_ord(cut) & ~31ull) | (unsigned long long)(31 - lane)) | (1ull << 63);
+                atomicMax(&w.bidkey[j1], mykey);
+            }
+            __syncwarp();
+            if (isfree) {
+                if (w.bidkey[j1] == mykey) {                      // winner of column j1
+                    const int old = w.row4col[j1];
+                    if (old >= 0) w.col4row[old] = -1;
+                    w.row4col[j1] = lane; w.col4row[lane] = j1;
+                    w.u[lane] = (m2 < INFINITY) ? m2 : m1;
+                    if (m2 < INFINITY) w.v[j1] -= (m2 - m1);
+                } else {
+                    w.u[lane] = m1;                               // still free: a feasible lower bound (prices only fall)
+                }
+            }
+            __syncwarp();
+            if (isfree) w.bidkey[j1] = 0ull;
+            __syncwarp();
+            myc = lane < nr ? w.col4row[lane] : 0;
+        }
+    }
+    // ---- (B) lean Dijkstra augmentations for the rows still free, lane = column
+    double vj[SLOTS];
+    int jc[SLOTS];
+#pragma unroll
+    for (int t = 0; t < SLOTS; ++t) { jc[t] = min(lane + 32 * t, nc - 1); vj[t] = w.v[jc[t]]; }
+    for (int cur = 0; cur < nr; ++cur) {
+        if (w.col4row[cur] != -1) continue;                     // warp-uniform
+        double sh[SLOTS];
+        int pth[SLOTS], r4c[SLOTS];
+        bool live[SLOTS], scanned[SLOTS];
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) {
+            const int j = lane + 32 * t;
+            sh[t] = INFINITY; pth[t] = -1; scanned[t] = false;
+            live[t] = j < nc;
+            r4c[t] = w.row4col[jc[t]];
+        }
+        double minVal = 0.0;
+        int sink = -1, i = cur;
+        while (true) {
+            ++steps;
+            const double tv = minVal - w.u[i];
+            double best = INFINITY;
+            int bpk = 0;                                        // (row4col + 1) << 2 | slot of the lane-local best column
+#pragma unroll
+            for (int t = 0; t < SLOTS; ++t) {
+                const double r = (cost(i, jc[t]) - vj[t]) + tv;
+                const bool upd = live[t] && (r < sh[t]);
+                sh[t] = upd ? r : sh[t];
+                pth[t] = upd ? i : pth[t];
+                const double cand = live[t] ? sh[t] : INFINITY;
+                const bool better = cand < best;
+                best = better ? cand : best;
+                bpk = better ? (((r4c[t] + 1) << 2) | t) : bpk;
+            }
+            // distances are >= 0 up to rounding, so the high word orders them as a signed integer; ties on it are resolved on the low word
+            const int hi = __double2hiint(best);
+            const int mhi = __reduce_min_sync(TTDG_FULL, hi);
+            unsigned tied = __ballot_sync(TTDG_FULL, hi == mhi);
+            if (__popc(tied) != 1) {
+                const unsigned lo = (hi == mhi) ? (unsigned)__double2loint(best) : 0xFFFFFFFFu;
+                const unsigned mlo = __reduce_min_sync(TTDG_FULL, lo);
+                tied = __ballot_sync(TTDG_FULL, hi == mhi && lo == mlo);
+            }
+            const int src = __ffs(tied) - 1;
+            minVal = __shfl_sync(TTDG_FULL, best, src);
+            const int pk = __shfl_sync(TTDG_FULL, bpk, src);
+            const int rsel = (pk >> 2) - 1, ssel = pk & 3;
+            if (!(minVal < INFINITY)) return false;             // cannot happen with finite costs; never loop forever
+#pragma unroll
+            for (int t = 0; t < SLOTS; ++t)
+                if (lane == src && t == ssel) { live[t] = false; scanned[t] = true; }
+            if (rsel < 0) { sink = src + 32 * ssel; break; }
+            i = rsel;
+        }
+        // dual update: u of the visited rows by the owner of their (scanned) column, v in registers; path of the scanned columns
+        if (lane == 0) w.u[cur] += minVal;
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t)
+            if (scanned[t]) {
+                const double d = minVal - sh[t];
+                if (r4c[t] >= 0) w.u[r4c[t]] += d;
+                vj[t] -= d;
+                w.path[lane + 32 * t] = pth[t];
+            }
+        __syncwarp();
+        if (lane == 0) {                                        // augment along the path (sequential, short)
+            int j = sink;
+            while (true) {
+                ++hops;
+                const int r = w.path[j];
+                w.row4col[j] = r;
+                const int t = w.col4row[r];
+                w.col4row[r] = j;
+                j = t;
+                if (r == cur) break;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) { w.stat_steps += steps; w.stat_hops += hops; }
+#pragma unroll
+    for (int t = 0; t < SLOTS; ++t) if (lane + 32 * t < nc) w.v[lane + 32 * t] = vj[t];
+    __syncwarp();
+    const bool ok = lap_certificate(nr, nc, cost, w);
+    if (lane == 0) { if (ok) ++w.stat_fast_ok; else ++w.stat_fast_fallback; }
+    __syncwarp();
+    return ok;
+}
+
+// lean certified solve; false = not certified (the caller runs the SciPy-order solve).  Full warp, nr <= 32.
+template <class Cost>
+__device__ __forceinline__ bool lap_lean_warp(int nr, int nc, Cost cost, LapWork &w) {
+    if (nr > 32 || nc > LAP_MAX_DIM) return false;
+    if (nc <= 32) return lap_lean_warp_t<1>(nr, nc, cost, w);
+    if (nc <= 64) return lap_lean_warp_t<2>(nr, nc, cost, w);
+    return lap_lean_warp_t<LAP_SLOTS>(nr, nc, cost, w);
+}
+
 // fast != 0: try the certified row-reduction solve first (rows <= 32 only), fall back to the SciPy-order solve
 template <class Cost>
 __device__ __forceinline__ void lap_solve_warp(int nr, int nc, Cost cost, LapWork &w, int fast = 0) {
-    if (fast && nr <= 32) {
+    if ((fast == 1 || fast == 2) && nr <= 32) {
         if ((threadIdx.x & 31) == 0) w.fast_mode = fast;
         __syncwarp();
         bool ok;

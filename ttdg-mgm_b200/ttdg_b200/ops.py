@@ -311,7 +311,7 @@ def gagm_solve(A, W, U0, ms, n_univ=NU, init_tau=0.1, min_tau=1e-2, sk_gamma=0.5
     assert A_c.shape == (M, M) and W_c.shape == (M, M) and U0_c.shape == (M, n_univ)
     ms_h = (ctypes.c_int32 * G)(*ms)
     U = torch.empty(M, n_univ, dtype=torch.float32, device=A.device)
-    info = torch.zeros(8, dtype=torch.int32, device=A.device)
+    info = torch.zeros(16, dtype=torch.int32, device=A.device)
     scratch = torch.empty(L.ttdg_gagm_scratch_bytes(M, G), dtype=torch.uint8, device=A.device)
     trace = meta = None
     if trace_cap > 0:                   # test hook: the whole trajectory, fp64
@@ -357,7 +357,7 @@ class _MatchingLoss(torch.autograd.Function):
         # utils/sinkhorn.py via mgm:467-468, 519-522: max_iter 20, tau 0.05, dummy_row
         check(L.ttdg_sinkhorn_small_fwd(_p(aff_c), _p(Wds), _p(items), len(pairs), max(sizes), cfg["sk_tau"], cfg["sk_iter"], 1,
                                         _stream()), "sinkhorn_small_fwd")
-        info = torch.zeros(8, dtype=torch.int32, device=dev)
+        info = torch.zeros(16, dtype=torch.int32, device=dev)
         if U_override is None:
             U, info = gagm_solve(A, Wds, U0, sizes, NU, cfg["ga_tau0"], cfg["ga_min_tau"], cfg["ga_gamma"], cfg["ga_iter"],
                                  cfg["ga_sk_iter"], cfg["ga_tol"], cfg["quad_weight"], return_info=True)

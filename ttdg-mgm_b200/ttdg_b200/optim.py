@@ -41,10 +41,15 @@ class FlatSGD:
     def zero_grad(self, set_to_none=False):
         self.flat_g.zero_()
 
-    def step(self, world_size=1, process_group=None):
-        """All-reduce (sum) the gradient bucket when world_size > 1, then one fused update."""
+    def allreduce(self, world_size=1, process_group=None):
+        """The path's one collective: all-reduce (sum) of the flat gradient bucket over NVLink."""
         if world_size > 1:
             torch.distributed.all_reduce(self.flat_g, group=process_group)
+
+    def step(self, world_size=1, process_group=None, reduce=True):
+        """All-reduce (sum) the gradient bucket when world_size > 1 (unless the caller already did), then one fused update."""
+        if reduce:
+            self.allreduce(world_size, process_group)
         s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         check(_C.lib().ttdg_sgd_step(ctypes.c_void_p(self.flat_p.data_ptr()), ctypes.c_void_p(self.flat_g.data_ptr()),
                                      ctypes.c_void_p(self.flat_m.data_ptr()), self.numel, self.lr, self.momentum,
