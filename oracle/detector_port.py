@@ -59,13 +59,22 @@ def bottleneck(x, sd, q, stride, has_shortcut):
 
 
 def preprocess(images_u8):
-    """list of uint8 C x H x W -> N x 3 x H x W float (all the same size here; d2 pads to a multiple of 32)."""
-    x = torch.stack([im.to(_dt()) for im in images_u8])
-    mean = torch.tensor(PIXEL_MEAN).reshape(1, 3, 1, 1)
-    x = x - mean                                                     # std = 1
-    H, W = x.shape[-2:]
-    ph, pw = (32 - H % 32) % 32, (32 - W % 32) % 32
-    return F.pad(x, (0, pw, 0, ph))
+    """d2 preprocess_image + ImageList.from_tensors: list of uint8 C x H_i x W_i -> N x 3 x Hp x Wp float; every image is
+    normalised first, then placed in the top-left corner of a ZERO canvas of the batch's maximum size rounded up to a
+    multiple of 32 (size_divisibility)."""
+    mean = torch.tensor(PIXEL_MEAN).reshape(3, 1, 1)
+    ims = [im.to(_dt()) - mean for im in images_u8]                  # std = 1
+    H, W = max(im.shape[-2] for im in ims), max(im.shape[-1] for im in ims)
+    Hp, Wp = (H + 31) // 32 * 32, (W + 31) // 32 * 32
+    return torch.stack([F.pad(im, (0, Wp - im.shape[-1], 0, Hp - im.shape[-2])) for im in ims])
+
+
+def _sizes(image_size, n):
+    """(h, w) for all images or one (h, w) per image -> list of n sizes."""
+    if len(image_size) == 2 and not isinstance(image_size[0], (tuple, list)):
+        return [tuple(image_size)] * n
+    assert len(image_size) == n
+    return [tuple(s) for s in image_size]
 
 
 def backbone(sd, x):
@@ -151,11 +160,12 @@ def rpn(sd, feats, image_size, training, nms_thresh=0.7, post_topk=1000):
             lvl_ids.append(torch.full((k,), l, dtype=torch.int64))
         top_boxes, top_scores, lvl_ids = torch.cat(top_boxes, 1), torch.cat(top_scores, 1), torch.cat(lvl_ids)
         out = []
+        sizes = _sizes(image_size, N)
         for n in range(N):
             b, s, lv = top_boxes[n], top_scores[n], lvl_ids
             valid = torch.isfinite(b).all(1) & torch.isfinite(s)
             b, s, lv = b[valid], s[valid], lv[valid]
-            b = clip_boxes(b, image_size[0], image_size[1])
+            b = clip_boxes(b, sizes[n][0], sizes[n][1])
             keep = ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
             b, s, lv = b[keep], s[keep], lv[keep]
             keep = tvo.batched_nms(b, s, lv, nms_thresh)[:post_topk]
@@ -196,7 +206,8 @@ def box_head(sd, feats, proposals, image_size, score_thresh=0.05, nms_thresh=0.5
         scores = F.linear(x, sd[h + "box_predictor.cls_score.weight"], sd[h + "box_predictor.cls_score.bias"])
         deltas = F.linear(x, sd[h + "box_predictor.bbox_pred.weight"], sd[h + "box_predictor.bbox_pred.bias"])
         out, o = [], 0
-        for boxes_p, _ in proposals:
+        sizes = _sizes(image_size, len(proposals))
+        for (boxes_p, _), image_size in zip(proposals, sizes):
             n = len(boxes_p)
             sc = F.softmax(scores[o:o + n], dim=-1)
             bx = apply_deltas(deltas[o:o + n], boxes_p, (10.0, 10.0, 5.0, 5.0))
@@ -247,8 +258,8 @@ def paste_masks(probs, boxes, H, W, threshold=0.5):
 
 def postprocess(dets, probs, image_size, out_size):
     res = []
-    sx, sy = out_size[1] / image_size[1], out_size[0] / image_size[0]
-    for (b, s, c), p in zip(dets, probs):
+    for (b, s, c), p, image_size, out_size in zip(dets, probs, _sizes(image_size, len(dets)), _sizes(out_size, len(dets))):
+        sx, sy = out_size[1] / image_size[1], out_size[0] / image_size[0]
         b = b * torch.tensor([sx, sy, sx, sy])
         b = clip_boxes(b, out_size[0], out_size[1])
         keep = ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
@@ -261,7 +272,7 @@ def postprocess(dets, probs, image_size, out_size):
 def forward_ttt(sd, images_u8):
     """rcnn.py:331-357 up to the node sampler: features (grad-carrying), detections of the box head in TRAIN mode."""
     x = preprocess(images_u8)
-    size = tuple(images_u8[0].shape[-2:])
+    size = [tuple(im.shape[-2:]) for im in images_u8]
     feats = backbone(sd, x)
     props = rpn(sd, [f.detach() for f in feats], size, training=True)
     dets = box_head(sd, [f.detach() for f in feats], props, size)
@@ -272,7 +283,7 @@ def inference(sd, images_u8, out_sizes=None):
     """GeneralizedRCNN.inference (rcnn.py:181-182): eval-mode detections with pasted masks."""
     with torch.no_grad():
         x = preprocess(images_u8)
-        size = tuple(images_u8[0].shape[-2:])
+        size = [tuple(im.shape[-2:]) for im in images_u8]
         feats = backbone(sd, x)
         props = rpn(sd, feats, size, training=False)
         dets = box_head(sd, feats, props, size)

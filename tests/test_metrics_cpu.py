@@ -104,3 +104,25 @@ def test_metrics_from_counts_match_reference(golden_dir):
         np.testing.assert_allclose(d, dice(pred, gt), rtol=1e-12)
         np.testing.assert_allclose(e, enhanced_align(pred, gt), rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(s, Structure_measure().get_score(pred, gt), rtol=2e-6, atol=1e-9)
+
+
+def test_metrics_from_counts_border_centroid_does_not_raise():
+    """Ground truth touching the bottom-right border: the S-measure's quadrant split lands on the last row / column, a quadrant
+    is empty (or one pixel), and the array code divides by zero the numpy way (nan with a warning).  The closed forms must do
+    the same instead of raising ZeroDivisionError and aborting the evaluation."""
+    import warnings
+    from adapteacher.evaluation.dice_metric import metrics_from_counts
+    h, w = 24, 31
+    for gt_pix in ([(h - 1, w - 1)], [(h - 1, w - 2), (h - 1, w - 1)], [(0, 0)]):
+        gt = np.zeros((h, w), bool)
+        for p in gt_pix:
+            gt[p] = True
+        pred = np.zeros((h, w), bool)
+        pred[h - 3:, w - 4:] = True
+        c, split = _counts_numpy(pred, gt)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            d, e, s = metrics_from_counts(c, split, gt.shape)          # must not raise
+            ref = Structure_measure().get_score(pred, gt)
+        np.testing.assert_allclose(d, dice(pred, gt), rtol=1e-12)
+        assert (np.isnan(s) and np.isnan(ref)) or abs(s - ref) <= 2e-6 * max(1.0, abs(ref)), (s, ref)

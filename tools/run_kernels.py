@@ -60,7 +60,7 @@ elif what == "timing":
         m.train()
         t0 = ev()
         feats = det.features(images); t1 = ev()
-        props = det.proposal_generator(feats, (512, 512), training=True); t2 = ev()
+        props = det.proposal_generator.predict(feats, (512, 512), training=True); t2 = ev()
         dets = det.roi_heads.forward_box(feats, props, (512, 512)); t3 = ev()
         insts = [Instances((512, 512), pred_boxes=Boxes(b), scores=s, pred_classes=c) for b, s, c in dets]
         nodes, labels = m.graph_generator([f.permute(0, 3, 1, 2) for f in feats], insts); t4 = ev()
@@ -70,7 +70,7 @@ elif what == "timing":
         m.eval()
         with torch.no_grad():                                    # = m(inputs), stage by stage
             e_feats = det.features(images); t8 = ev()
-            e_props = det.proposal_generator(e_feats, (512, 512), training=False); t9 = ev()
+            e_props = det.proposal_generator.predict(e_feats, (512, 512), training=False); t9 = ev()
             e_dets = det.roi_heads.forward_box(e_feats, e_props, (512, 512)); t10 = ev()
             out = det.roi_heads.forward_mask(e_feats, e_dets, (512, 512), (512, 512)); t11 = ev()
         torch.cuda.synchronize()

@@ -8,10 +8,19 @@ differs from the model's are dropped and reported (:80-87); ``pixel_mean`` / ``p
 mean-teacher trainers) loaded into a single detector takes the TEACHER weights - the model train_net.py:45-57 tests.
 Caffe2 / ``.pkl`` model-zoo files need Detectron2's name-matching heuristics and are refused.  New relative to the
 reference (which never saves after test-time adaptation): ``save`` writes the adapted weights back in the same format."""
+import logging
 import os
+import pickle
 from collections import namedtuple
 
 import torch
+
+logger = logging.getLogger("adapteacher.checkpoint")
+
+# keys a test-time checkpoint may legitimately lack or carry in excess (SURVEY 8b): the training-only discriminator and
+# universe-learning network, d2's anchor / pixel buffers
+OPTIONAL_PREFIXES = ("D_img.", "multi_matching_sup.Net_U.", "multi_matching_sup.node_affinity.", "pixel_mean", "pixel_std",
+                     "proposal_generator.anchor_generator.")
 
 _IncompatibleKeys = namedtuple("_IncompatibleKeys", ["missing_keys", "unexpected_keys", "incorrect_shapes"])
 
@@ -44,7 +53,14 @@ class DetectionCheckpointer:
         if path.endswith(".pkl"):
             raise NotImplementedError("Caffe2 / model-zoo .pkl checkpoints need Detectron2's name-matching heuristics; "
                                       "convert them to a .pth state dict first")
-        loaded = torch.load(path, map_location="cpu", weights_only=False)
+        try:                                                  # tensors only: a checkpoint must not be able to run code
+            loaded = torch.load(path, map_location="cpu", weights_only=True)
+        except (pickle.UnpicklingError, RuntimeError) as e:
+            if os.environ.get("TTDG_TRUST_CHECKPOINT", "0") != "1":
+                raise RuntimeError(f"{path} holds pickled Python objects besides tensors ({e}); set TTDG_TRUST_CHECKPOINT=1 to "
+                                   "load it anyway (this EXECUTES code from the file)") from e
+            logger.warning("loading %s with full unpickling (TTDG_TRUST_CHECKPOINT=1)", path)
+            loaded = torch.load(path, map_location="cpu", weights_only=False)
         if "model" not in loaded:
             loaded = {"model": loaded}
         return loaded
@@ -67,26 +83,47 @@ class DetectionCheckpointer:
             if k in model_sd and tuple(model_sd[k].shape) != tuple(sd[k].shape):
                 incorrect.append((k, tuple(sd[k].shape), tuple(model_sd[k].shape)))
                 sd.pop(k)
+        # (Conv2d._load_from_state_dict consumes its keys itself, so unexpected keys are computed here, not by torch)
+        unexpected = [k for k in sd if k not in model_sd]
         inc = self.model.load_state_dict(sd, strict=False)
         missing = [k for k in inc.missing_keys if k not in ("pixel_mean", "pixel_std")]
-        return _IncompatibleKeys(missing, list(inc.unexpected_keys), incorrect)
+        return _IncompatibleKeys(missing, sorted(set(unexpected) | set(inc.unexpected_keys)), incorrect)
 
-    def load(self, path, checkpointables=None):
+    def _report(self, inc, path, strict):
+        """Detectron2 logs missing / unexpected / wrong-shape keys; here a REQUIRED key that did not load is also an error when
+        ``strict`` (the entry point): otherwise a renamed key, a wrong NUM_CLASSES or a wrong file would leave zero-initialised
+        convolutions or a random matching head in place and test-time adaptation would run on them without a word."""
+        def required(k):
+            return not k.startswith(OPTIONAL_PREFIXES)
+        if inc.incorrect_shapes:
+            logger.warning("%s: skipped (shape in checkpoint vs model): %s", path,
+                           "; ".join(f"{k} {a} vs {b}" for k, a, b in inc.incorrect_shapes))
+        if inc.missing_keys:
+            logger.warning("%s: keys of the model NOT found in the checkpoint: %s", path, ", ".join(inc.missing_keys))
+        if inc.unexpected_keys:
+            logger.warning("%s: keys of the checkpoint not used by the model: %s", path, ", ".join(inc.unexpected_keys))
+        bad = [k for k in inc.missing_keys if required(k)] + [k for k, _, _ in inc.incorrect_shapes if required(k)]
+        if strict and bad:
+            raise RuntimeError(f"checkpoint {path} does not provide {len(bad)} required parameter(s): " + ", ".join(bad[:8]) +
+                               (" ..." if len(bad) > 8 else ""))
+
+    def load(self, path, checkpointables=None, strict=False):
         if not path:
             return {}
         if not os.path.isfile(path):
             raise FileNotFoundError(f"Checkpoint {path} not found!")
         checkpoint = self._load_file(path)
         self.last_incompatible = self._load_model(checkpoint)
+        self._report(self.last_incompatible, path, strict)
         for key in self.checkpointables if checkpointables is None else checkpointables:
             if key in checkpoint:
                 self.checkpointables[key].load_state_dict(checkpoint.pop(key))
         return checkpoint
 
-    def resume_or_load(self, path, *, resume=True):
+    def resume_or_load(self, path, *, resume=True, strict=False):
         if resume and self.has_checkpoint():
-            return self.load(self.get_checkpoint_file())
-        return self.load(path, checkpointables=[])
+            return self.load(self.get_checkpoint_file(), strict=strict)
+        return self.load(path, checkpointables=[], strict=strict)
 
     # ---- saving (Detectron2 format: {"model": state_dict, <checkpointables>...} + last_checkpoint)
     def save(self, name, **kwargs):

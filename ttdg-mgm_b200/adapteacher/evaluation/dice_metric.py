@@ -130,16 +130,20 @@ def metrics_from_counts(counts, split, shape):
             q11, q10, q01, q00 = (int(v) for v in c[q])
             nq = q11 + q10 + q01 + q00
             assert nq == sizes[q], "quadrant sizes disagree with the split"
-            x = (q11 + q10) / nq                              # mean of the boolean prediction (float64)
-            y32 = np.float32(q11 + q01) / np.float32(nq)      # mean of the float32 ground truth (float32 division)
-            b1, b0 = np.float32(1) - y32, np.float32(0) - y32
-            sxy = (q11 * ((1 - x) * b1) + q10 * ((1 - x) * b0) + q01 * ((0 - x) * b1) + q00 * ((0 - x) * b0)) / (nq - 1)
-            var_a = ((q11 + q10) * (1 - x) ** 2 + (q01 + q00) * (0 - x) ** 2) / nq
-            var_b = np.float32(((q11 + q01) * float(b1) ** 2 + (q10 + q00) * float(b0) ** 2) / nq)
-            alpha = 4 * x * y32 * sxy
-            beta = (x * x + y32 * y32) * (var_a + var_b)
-            ssim = alpha / (beta + 1e-8) if alpha != 0 else (1 if beta == 0 else 0)
-            reg += sizes[q] / n * ssim
+            # an empty quadrant (ground-truth centroid on the last row / column) or a one-pixel quadrant divides by zero: numpy
+            # semantics (nan / inf with a warning, as in the reference's array code), never a Python ZeroDivisionError
+            with np.errstate(all="ignore"):
+                nqf = np.float64(nq)
+                x = np.float64(q11 + q10) / nqf                   # mean of the boolean prediction (float64)
+                y32 = np.float32(q11 + q01) / np.float32(nq)      # mean of the float32 ground truth (float32 division)
+                b1, b0 = np.float32(1) - y32, np.float32(0) - y32
+                sxy = (q11 * ((1 - x) * b1) + q10 * ((1 - x) * b0) + q01 * ((0 - x) * b1) + q00 * ((0 - x) * b0)) / np.float64(nq - 1)
+                var_a = ((q11 + q10) * (1 - x) ** 2 + (q01 + q00) * (0 - x) ** 2) / nqf
+                var_b = np.float32(((q11 + q01) * np.float64(b1) ** 2 + (q10 + q00) * np.float64(b0) ** 2) / nqf)
+                alpha = 4 * x * y32 * sxy
+                beta = (x * x + y32 * y32) * (var_a + var_b)
+                ssim = alpha / (beta + 1e-8) if alpha != 0 else (1 if beta == 0 else 0)
+                reg += sizes[q] / n * ssim
         sm_v = 0.5 * obj + 0.5 * reg
     return dice_v, ea_v, float(sm_v)
 

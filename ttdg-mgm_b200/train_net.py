@@ -28,14 +28,11 @@ from adapteacher.config import add_ateacher_config  # noqa: E402
 from adapteacher.data import build_detection_test_loader  # noqa: E402
 from adapteacher.engine.trainer import BaselineTrainer  # noqa: E402
 
-META_ARCH_REGISTRY = {}
-
-
-def _registry():
-    if not META_ARCH_REGISTRY:
-        from adapteacher.modeling.meta_arch.rcnn import DAobjTwoStagePseudoLabGeneralizedRCNN
-        META_ARCH_REGISTRY["DAobjTwoStagePseudoLabGeneralizedRCNN"] = DAobjTwoStagePseudoLabGeneralizedRCNN
-    return META_ARCH_REGISTRY
+# hacky way to register (reference train_net.py:14-20): importing the modules fills the registries
+from adapteacher.modeling.meta_arch.rcnn import DAobjTwoStagePseudoLabGeneralizedRCNN, TwoStagePseudoLabGeneralizedRCNN  # noqa: E402,F401
+from adapteacher.modeling.proposal_generator.rpn import PseudoLabRPN  # noqa: E402,F401
+from adapteacher.modeling.roi_heads.roi_heads import StandardROIHeadsPseudoLab  # noqa: E402,F401
+from ttdg_b200.registry import META_ARCH_REGISTRY  # noqa: E402
 
 
 def _literal(v):
@@ -78,7 +75,9 @@ def _load_yaml(path):
 def setup(args):
     cfg = add_ateacher_config()
     cfg.MODEL = SimpleNamespace(WEIGHTS="", META_ARCHITECTURE="DAobjTwoStagePseudoLabGeneralizedRCNN",
-                                ROI_HEADS=SimpleNamespace(NUM_CLASSES=2))
+                                BACKBONE=SimpleNamespace(NAME="build_resnet_fpn_backbone"),
+                                PROPOSAL_GENERATOR=SimpleNamespace(NAME="PseudoLabRPN"),
+                                ROI_HEADS=SimpleNamespace(NAME="StandardROIHeadsPseudoLab", NUM_CLASSES=2))
     cfg.INPUT = SimpleNamespace(FORMAT="BGR", MIN_SIZE_TEST=800, MAX_SIZE_TEST=1333)
     cfg.OUTPUT_DIR = "./output"
     if args.config_file:
@@ -100,8 +99,8 @@ def setup(args):
 class Trainer(BaselineTrainer):
     @classmethod
     def build_model(cls, cfg):
-        arch = _registry()[cfg.MODEL.META_ARCHITECTURE]         # KeyError = unknown META_ARCHITECTURE, like the d2 registry
-        return arch(cfg.MODEL.ROI_HEADS.NUM_CLASSES, getattr(cfg.SEMISUPNET, "DIS_TYPE", "p2")).to("cuda")
+        arch = META_ARCH_REGISTRY.get(cfg.MODEL.META_ARCHITECTURE)      # KeyError = unknown name, like the d2 registry
+        return arch.from_config(cfg).to("cuda")                         # sub-modules by MODEL.{BACKBONE,PROPOSAL_GENERATOR,ROI_HEADS}.NAME
 
     @classmethod
     def build_optimizer(cls, cfg, model):
@@ -124,7 +123,7 @@ def main(args):
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         torch.distributed.init_process_group("nccl")
     model = Trainer.build_model(cfg)
-    DetectionCheckpointer(model, save_dir=cfg.OUTPUT_DIR).resume_or_load(cfg.MODEL.WEIGHTS, resume=args.resume)
+    DetectionCheckpointer(model, save_dir=cfg.OUTPUT_DIR).resume_or_load(cfg.MODEL.WEIGHTS, resume=args.resume, strict=True)
     loaders = {name: Trainer.build_test_loader(cfg, name) for name in cfg.DATASETS.TEST}
     res = Trainer.test(cfg, model, Trainer.build_optimizer(cfg, model), data_loaders=loaders, world_size=world)
     if world == 1 or torch.distributed.get_rank() == 0:
@@ -138,11 +137,20 @@ def main(args):
     return res
 
 
+def _free_port():
+    import socket
+    with socket.socket() as sck:
+        sck.bind(("127.0.0.1", 0))
+        return sck.getsockname()[1]
+
+
 def default_argument_parser():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config-file", default="", metavar="FILE")
     ap.add_argument("--config", dest="config_file", help=argparse.SUPPRESS)       # the README's spelling (README.md:93-94)
-    ap.add_argument("--resume", action="store_true")
+    ap.add_argument("--resume", action="store_true", default=True,
+                    help="a last_checkpoint in OUTPUT_DIR wins over MODEL.WEIGHTS (the reference forces this, train_net.py:92)")
+    ap.add_argument("--no-resume", dest="resume", action="store_false")
     ap.add_argument("--eval-only", action="store_true")
     ap.add_argument("--num-gpus", type=int, default=1)
     ap.add_argument("opts", nargs=argparse.REMAINDER, default=[])
@@ -153,5 +161,5 @@ if __name__ == "__main__":
     args = default_argument_parser().parse_args()
     if args.num_gpus > 1 and "WORLD_SIZE" not in os.environ:       # d2 launch(): one process per GPU
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.num_gpus}",
-                                   "--master-addr", "127.0.0.1", "--master-port", "29511"] + sys.argv)
+                                   "--master-addr", "127.0.0.1", "--master-port", str(_free_port())] + sys.argv)
     main(args)

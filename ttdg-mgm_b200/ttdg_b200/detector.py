@@ -398,7 +398,13 @@ class Backbone(nn.Module):
             setattr(self, f"fpn_lateral{lvl}", Conv2d(c, 256, 1, 1, 0, bias=True))
             setattr(self, f"fpn_output{lvl}", Conv2d(256, 256, 3, 1, 1, bias=True))
 
-    def forward(self, x, width=None):
+    out_features = ("p2", "p3", "p4", "p5", "p6")
+
+    def pyramid(self, x, width=None):
+        """[p2 .. p6] as N x H x W x 256 (NHWC) maps.  x: the preprocessed image tensor (``preprocess``); width: the image
+        width when x carries the stem's zero padding (also read from the ``stem_width`` attribute ``preprocess`` sets)."""
+        if width is None:
+            width = getattr(x, "stem_width", None)
         res = self.bottom_up(x, width)
         outs, prev = {}, None
         for lvl in (5, 4, 3, 2):
@@ -406,6 +412,11 @@ class Backbone(nn.Module):
             prev = lat(res[f"res{lvl}"]) if prev is None else lat(res[f"res{lvl}"], residual=prev, res_mode=2)
             outs[lvl] = getattr(self, f"fpn_output{lvl}")(prev)
         return [outs[2], outs[3], outs[4], outs[5], _Subsample2.apply(outs[5])]
+
+    def forward(self, x, width=None):
+        """d2 Backbone.forward (called as ``self.backbone(images.tensor)``, rcnn.py:226): {"p2": .., "p6": ..} in NCHW - views
+        of the NHWC maps the kernels write, so turning them back (``_nhwc``) costs nothing."""
+        return dict(zip(self.out_features, (f.permute(0, 3, 1, 2) for f in self.pyramid(x, width))))
 
 
 class RPNHead(nn.Module):
@@ -428,6 +439,20 @@ def cell_anchors():
 
 
 _NMS_SCRATCH = {}
+
+
+def _nhwc(f):
+    """NCHW view of an NHWC map (what Backbone.forward hands out) -> the NHWC map; a real NCHW tensor is re-laid out."""
+    return f.permute(0, 2, 3, 1).contiguous()
+
+
+def _sizes(image_sizes, n):
+    """(h, w) for all images, or one (h, w) per image (d2 ImageList.image_sizes) -> (list of n sizes, all equal?)."""
+    if len(image_sizes) == 2 and not isinstance(image_sizes[0], (tuple, list)):
+        return [tuple(image_sizes)] * n, True
+    sizes = [tuple(int(v) for v in s) for s in image_sizes]
+    assert len(sizes) == n
+    return sizes, all(s == sizes[0] for s in sizes)
 
 
 def nms_sorted(boxes, cats, thresh, max_keep):
@@ -460,13 +485,21 @@ class RPN(nn.Module):
         self.nms_thresh, self.post_topk = 0.7, 1000
         self._cell = cell_anchors()
 
-    @torch.no_grad()
+    in_features = ("p2", "p3", "p4", "p5", "p6")
+
     def forward(self, feats, image_size, training):
+        return self.predict(feats, image_size, training)
+
+    @torch.no_grad()
+    def predict(self, feats, image_size, training):
+        """feats: [p2 .. p6] NHWC; image_size: (h, w) or one (h, w) per image (boxes are clipped to the image's own size, d2
+        find_top_rpn_proposals).  Returns per image (proposal boxes k x 4, objectness logits k), sorted by logit."""
         L = _C.lib()
         A = self._cell.shape[0]
         pre_topk = 2000 if training else 1000
         N = feats[0].shape[0]
         dev = feats[0].device
+        sizes, same = _sizes(image_size, N)
         cell_h = (ctypes.c_float * (A * 4))(*self._cell.reshape(-1).tolist())
         boxes_l, scores_l, valid_l, lvl_l = [], [], [], []
         for l, f in enumerate(feats):
@@ -480,9 +513,16 @@ class RPN(nn.Module):
             sc, idx = torch.topk(flat, k, dim=1, sorted=True)           # ordering only (plumbing)
             boxes = torch.empty(N, k, 4, dtype=torch.float32, device=dev)
             valid = torch.empty(N, k, dtype=torch.uint8, device=dev)
-            check(L.ttdg_rpn_decode(_p(deltas), deltas.shape[-1], _p(idx.contiguous()), N, k, H, W, A, STRIDES[l],
-                                    ctypes.cast(cell_h, ctypes.c_void_p), float(image_size[0]), float(image_size[1]), _p(boxes),
-                                    _p(valid), _stream()), "rpn_decode")
+            idx = idx.contiguous()
+            if same:
+                check(L.ttdg_rpn_decode(_p(deltas), deltas.shape[-1], _p(idx), N, k, H, W, A, STRIDES[l],
+                                        ctypes.cast(cell_h, ctypes.c_void_p), float(sizes[0][0]), float(sizes[0][1]), _p(boxes),
+                                        _p(valid), _stream()), "rpn_decode")
+            else:                                                       # mixed image sizes in one padded batch: clip per image
+                for n in range(N):
+                    check(L.ttdg_rpn_decode(_p(deltas[n]), deltas.shape[-1], _p(idx[n]), 1, k, H, W, A, STRIDES[l],
+                                            ctypes.cast(cell_h, ctypes.c_void_p), float(sizes[n][0]), float(sizes[n][1]),
+                                            _p(boxes[n]), _p(valid[n]), _stream()), "rpn_decode")
             boxes_l.append(boxes); scores_l.append(sc); valid_l.append(valid)
             lvl_l.append(torch.full((k,), l, dtype=torch.int32, device=dev))
         boxes, scores, valid, lvl = torch.cat(boxes_l, 1), torch.cat(scores_l, 1), torch.cat(valid_l, 1).bool(), torch.cat(lvl_l)
@@ -579,8 +619,19 @@ class ROIHeads(nn.Module):
         pb = torch.cat(props).contiguous()
         cand_b = torch.empty(R * K, 4, dtype=torch.float32, device=dev)
         cand_s = torch.empty(R * K, dtype=torch.float32, device=dev)
-        check(L.ttdg_box_predict(_p(cls), cls.shape[1], _p(reg), reg.shape[1], _p(pb), R, K, float(image_size[0]), float(image_size[1]),
-                                 self.score_thresh, _p(cand_b), _p(cand_s), _stream()), "box_predict")
+        sizes, same = _sizes(image_size, len(props))
+        if same:
+            check(L.ttdg_box_predict(_p(cls), cls.shape[1], _p(reg), reg.shape[1], _p(pb), R, K, float(sizes[0][0]), float(sizes[0][1]),
+                                     self.score_thresh, _p(cand_b), _p(cand_s), _stream()), "box_predict")
+        else:                                                           # clip to each image's own size
+            o = 0
+            for i, p in enumerate(props):
+                n = len(p)
+                if n:
+                    check(L.ttdg_box_predict(_p(cls[o:o + n]), cls.shape[1], _p(reg[o:o + n]), reg.shape[1], _p(pb[o:o + n]), n, K,
+                                             float(sizes[i][0]), float(sizes[i][1]), self.score_thresh, _p(cand_b[o * K:(o + n) * K]),
+                                             _p(cand_s[o * K:(o + n) * K]), _stream()), "box_predict")
+                o += n
         # pad every image to the same candidate count (invalid candidates: score -1, unique negative category)
         B = len(props)
         nmax = max(len(p) for p in props) * K
@@ -611,89 +662,144 @@ class ROIHeads(nn.Module):
         return [(b_sel[i, :counts[i]], s_sel[i, :counts[i]], c_sel[i, :counts[i]]) for i in range(B)]
 
     @torch.no_grad()
+    def mask_logits(self, feats, dets):
+        """Mask branch up to the predictor (d2 _forward_mask in inference form): R x 28 x 28 x Kpad logits (K used) for the
+        R = sum of detections of the batch, or None when there are none."""
+        L = _C.lib()
+        feats4 = [f.detach() for f in feats[:4]]
+        boxes = [d[0] for d in dets]
+        R = sum(len(b) for b in boxes)
+        if R == 0:
+            return None
+        x = roi_align(feats4, _rois(boxes), 14)
+        for i in range(1, 5):
+            x = getattr(self.mask_head, f"mask_fcn{i}")(x, relu=True)
+        y4 = self.mask_head.deconv(x, relu=True)                     # R x 14 x 14 x (4 * 256)
+        y = torch.empty(R, 28, 28, 256, dtype=torch.float32, device=y4.device)
+        check(L.ttdg_pixel_shuffle2(_p(y4), R, 14, 14, 256, _p(y), _stream()), "pixel_shuffle")
+        return self.mask_head.predictor(y)                           # R x 28 x 28 x 64 (K used)
+
+    @torch.no_grad()
+    def paste(self, logits, dets, out_size, image_size):
+        """d2 detector_postprocess + paste_masks_in_image for the whole batch: boxes rescaled from the network input size to
+        the requested output size, clipped, empty ones dropped, the class's 28 x 28 logits pasted (sigmoid, bilinear, >= 0.5).
+        out_size / image_size: (h, w) for all images or one per image.  Same sizes everywhere = one paste launch and one host
+        sync for the batch; per-image results are views."""
+        L = _C.lib()
+        B = len(dets)
+        dev = dets[0][0].device
+        counts = [len(d[0]) for d in dets]
+        R = sum(counts)
+        outs, same_o = _sizes(out_size, B)
+        ins, same_i = _sizes(image_size, B)
+        bs = torch.cat([d[0] for d in dets]) if R else torch.zeros(0, 4, dtype=torch.float32, device=dev)
+        scores = torch.cat([d[1] for d in dets]) if R else torch.zeros(0, dtype=torch.float32, device=dev)
+        classes = (torch.cat([d[2] for d in dets]) if R else torch.zeros(0, dtype=torch.int64, device=dev)).contiguous()
+        if same_o and same_i:
+            H, W = outs[0]
+            sx, sy = W / ins[0][1], H / ins[0][0]
+            if sx != 1.0 or sy != 1.0:
+                bs = torch.stack((bs[:, 0] * sx, bs[:, 1] * sy, bs[:, 2] * sx, bs[:, 3] * sy), dim=1)
+            bs = torch.stack((bs[:, 0].clamp(0, W), bs[:, 1].clamp(0, H), bs[:, 2].clamp(0, W), bs[:, 3].clamp(0, H)), dim=1).contiguous()
+            masks = torch.empty(R, H, W, dtype=torch.uint8, device=dev)     # the paste kernel writes every pixel
+            if R:
+                check(L.ttdg_mask_paste(_p(logits), logits.shape[-1], 28, _p(bs), _p(classes), R, H, W, 0.5, _p(masks), _stream()), "mask_paste")
+            per_image = [(bs[o:o + n], masks[o:o + n]) for o, n in zip(_offsets(counts), counts)]
+        else:                                                               # every image pasted at its own size
+            per_image = []
+            for i, (o, n) in enumerate(zip(_offsets(counts), counts)):
+                H, W = outs[i]
+                sx, sy = W / ins[i][1], H / ins[i][0]
+                b = bs[o:o + n]
+                b = torch.stack(((b[:, 0] * sx).clamp(0, W), (b[:, 1] * sy).clamp(0, H), (b[:, 2] * sx).clamp(0, W),
+                                 (b[:, 3] * sy).clamp(0, H)), dim=1).contiguous()
+                mk = torch.empty(n, H, W, dtype=torch.uint8, device=dev)
+                if n:
+                    check(L.ttdg_mask_paste(_p(logits[o:o + n]), logits.shape[-1], 28, _p(b), _p(classes[o:o + n]), n, H, W, 0.5, _p(mk),
+                                            _stream()), "mask_paste")
+                per_image.append((b, mk))
+        all_kept = True
+        if R:
+            allb = torch.cat([b for b, _ in per_image])
+            keep = ((allb[:, 2] - allb[:, 0]) > 0) & ((allb[:, 3] - allb[:, 1]) > 0)        # Boxes.nonempty()
+            all_kept = bool(keep.all().item())
+        results = []
+        for (b, mk), o, n in zip(per_image, _offsets(counts), counts):
+            sl = slice(o, o + n)
+            mb = mk.view(torch.bool)                                        # the paste kernel writes 0 / 1
+            if all_kept:
+                results.append({"pred_boxes": b, "scores": scores[sl], "pred_classes": classes[sl], "pred_masks": mb})
+            else:
+                k = keep[sl]
+                results.append({"pred_boxes": b[k], "scores": scores[sl][k], "pred_classes": classes[sl][k], "pred_masks": mb[k]})
+        return results
+
+    @torch.no_grad()
     def forward_mask(self, feats, dets, out_size, image_size):
         """Mask branch + detector_postprocess: returns per image a dict with pred_boxes / scores / pred_classes /
         pred_masks (bool R x H x W)."""
-        L = _C.lib()
-        feats4 = [f.detach() for f in feats[:4]]
-        dev = feats4[0].device
-        boxes = [d[0] for d in dets]
-        results = []
-        R = sum(len(b) for b in boxes)
-        H, W = out_size
-        sx, sy = out_size[1] / image_size[1], out_size[0] / image_size[0]
-        if R > 0:
-            x = roi_align(feats4, _rois(boxes), 14)
-            for i in range(1, 5):
-                x = getattr(self.mask_head, f"mask_fcn{i}")(x, relu=True)
-            y4 = self.mask_head.deconv(x, relu=True)                     # R x 14 x 14 x (4 * 256)
-            y = torch.empty(R, 28, 28, 256, dtype=torch.float32, device=dev)
-            check(L.ttdg_pixel_shuffle2(_p(y4), R, 14, 14, 256, _p(y), _stream()), "pixel_shuffle")
-            logits = self.mask_head.predictor(y)                         # R x 28 x 28 x 4 (K used)
-        # detector_postprocess for the whole batch at once (one paste launch, one host sync); per-image results are views
-        counts = [len(b) for b in boxes]
-        bs = torch.cat(boxes) if R else torch.zeros(0, 4, dtype=torch.float32, device=dev)
-        if sx != 1.0 or sy != 1.0:
-            bs = torch.stack((bs[:, 0] * sx, bs[:, 1] * sy, bs[:, 2] * sx, bs[:, 3] * sy), dim=1)
-        bs = torch.stack((bs[:, 0].clamp(0, W), bs[:, 1].clamp(0, H), bs[:, 2].clamp(0, W), bs[:, 3].clamp(0, H)), dim=1).contiguous()
-        scores = torch.cat([d[1] for d in dets]) if R else torch.zeros(0, dtype=torch.float32, device=dev)
-        classes = (torch.cat([d[2] for d in dets]) if R else torch.zeros(0, dtype=torch.int64, device=dev)).contiguous()
-        masks = torch.empty(R, H, W, dtype=torch.uint8, device=dev)     # the paste kernel writes every pixel
-        all_kept = True
-        if R:
-            check(L.ttdg_mask_paste(_p(logits), logits.shape[-1], 28, _p(bs), _p(classes), R, H, W, 0.5, _p(masks), _stream()), "mask_paste")
-            keep = ((bs[:, 2] - bs[:, 0]) > 0) & ((bs[:, 3] - bs[:, 1]) > 0)        # Boxes.nonempty()
-            all_kept = bool(keep.all().item())
-        masks_b = masks.view(torch.bool)                                # the paste kernel writes 0 / 1
-        o = 0
-        for n in counts:
-            sl = slice(o, o + n)
-            if all_kept:
-                results.append({"pred_boxes": bs[sl], "scores": scores[sl], "pred_classes": classes[sl], "pred_masks": masks_b[sl]})
-            else:
-                k = keep[sl]
-                results.append({"pred_boxes": bs[sl][k], "scores": scores[sl][k], "pred_classes": classes[sl][k], "pred_masks": masks_b[sl][k]})
-            o += n
-        return results
+        return self.paste(self.mask_logits(feats, dets), dets, out_size, image_size)
+
+
+def _offsets(counts):
+    o, out = 0, []
+    for n in counts:
+        out.append(o)
+        o += n
+    return out
 
 
 def preprocess(images_u8, device, stem_padded=False):
-    """d2 preprocess_image: list of uint8 3 x H x W (same size) -> N x H x W x 4 fp32 NHWC, mean-subtracted, padded to
-    a multiple of 32 (size_divisibility).  stem_padded: rows carry the stem's zero padding as well (3 pixels left, 5
-    right), the layout ttdg_stem_tc reads; returns (tensor N x H32 x (W32 + 8) x 4, W32)."""
+    """d2 preprocess_image + ImageList.from_tensors: list of uint8 3 x H_i x W_i -> N x Hp x Wp x 4 fp32 NHWC, mean-subtracted
+    (std 1), every image in the top-left corner of a zero canvas of the batch's maximum size rounded up to a multiple of 32
+    (size_divisibility; d2 pads AFTER normalisation, so the padding is 0).  stem_padded: rows carry the stem's zero padding as
+    well (3 pixels left, 5 right), the layout ttdg_stem_tc reads; returns (tensor N x Hp x (Wp + 8) x 4, Wp)."""
     images_u8 = list(images_u8)
-    if images_u8[0].device.type == "cpu":                   # host images (pinned by the loader): one async H2D copy each, straight
-        x = torch.empty((len(images_u8),) + tuple(images_u8[0].shape), dtype=images_u8[0].dtype, device=device)     # into the batch
+    shapes = [tuple(im.shape) for im in images_u8]
+    assert all(len(sh) == 3 and sh[0] == 3 for sh in shapes) and all(im.dtype == torch.uint8 for im in images_u8)
+    same = all(sh == shapes[0] for sh in shapes)
+    Hm, Wm = max(sh[1] for sh in shapes), max(sh[2] for sh in shapes)
+    Hp, Wq = (Hm + 31) // 32 * 32, (Wm + 31) // 32 * 32
+    left, Wp = (STEM_LEFT, Wq + STEM_EXTRA) if stem_padded else (0, Wm)
+    N = len(images_u8)
+    L = _C.lib()
+    if same:
+        if images_u8[0].device.type == "cpu":               # host images (pinned by the loader): one async H2D copy each, straight
+            x = torch.empty((N,) + shapes[0], dtype=torch.uint8, device=device)                                     # into the batch
+            for n, im in enumerate(images_u8):
+                x[n].copy_(im, non_blocking=True)
+        else:
+            x = torch.stack(images_u8).contiguous()
+        H, W = shapes[0][1:]
+        if Hp != H:                                         # bottom padding: image by image into the taller zeroed buffer
+            out = torch.zeros(N, Hp, Wp, 4, dtype=torch.float32, device=device)
+            for n in range(N):
+                check(L.ttdg_preprocess(_p(x[n]), 1, H, W, Wp, left, *PIXEL_MEAN, _p(out[n]), _stream()), "preprocess")
+        else:
+            out = torch.empty(N, H, Wp, 4, dtype=torch.float32, device=device)
+            check(L.ttdg_preprocess(_p(x), N, H, W, Wp, left, *PIXEL_MEAN, _p(out), _stream()), "preprocess")
+    else:                                                   # mixed sizes: every image into its corner of the zero canvas
+        out = torch.zeros(N, Hp, Wp, 4, dtype=torch.float32, device=device)
         for n, im in enumerate(images_u8):
-            x[n].copy_(im, non_blocking=True)
-    else:
-        x = torch.stack(images_u8).contiguous()
-    N, C, H, W = x.shape
-    assert C == 3 and x.dtype == torch.uint8
-    ph, pw = (32 - H % 32) % 32, (32 - W % 32) % 32
-    left, Wp = (STEM_LEFT, W + pw + STEM_EXTRA) if stem_padded else (0, W)
-    if ph:                                                  # bottom padding: image by image into the taller zeroed buffer
-        out = torch.zeros(N, H + ph, Wp, 4, dtype=torch.float32, device=device)
-        for n in range(N):
-            check(_C.lib().ttdg_preprocess(_p(x[n]), 1, H, W, Wp, left, *PIXEL_MEAN, _p(out[n]), _stream()), "preprocess")
-    else:
-        out = torch.empty(N, H, Wp, 4, dtype=torch.float32, device=device)
-        check(_C.lib().ttdg_preprocess(_p(x), N, H, W, Wp, left, *PIXEL_MEAN, _p(out), _stream()), "preprocess")
+            xi = im.to(device, non_blocking=True).contiguous()
+            check(L.ttdg_preprocess(_p(xi), 1, im.shape[1], im.shape[2], Wp, left, *PIXEL_MEAN, _p(out[n]), _stream()), "preprocess")
     if stem_padded:
-        return out, W + pw
-    if pw:
-        out = torch.nn.functional.pad(out, (0, 0, 0, pw)).contiguous()
+        out.stem_width = Wq
+        return out, Wq
+    if Wq != Wm:
+        out = torch.nn.functional.pad(out, (0, 0, 0, Wq - Wm)).contiguous()
     return out
 
 
 class MaskRCNN(nn.Module):
-    """Backbone + PseudoLabRPN + StandardROIHeadsPseudoLab with d2's module / parameter names."""
+    """Backbone + PseudoLabRPN + StandardROIHeadsPseudoLab with d2's module / parameter names.  The three sub-module classes
+    can be substituted (the registries of train_net.py pass the reference-shaped adapters)."""
 
-    def __init__(self, num_classes=2):
+    def __init__(self, num_classes=2, backbone_cls=None, rpn_cls=None, roi_heads_cls=None):
         super().__init__()
-        self.backbone = Backbone()
-        self.proposal_generator = RPN()
-        self.roi_heads = ROIHeads(num_classes)
+        self.backbone = (backbone_cls or Backbone)()
+        self.proposal_generator = (rpn_cls or RPN)()
+        self.roi_heads = (roi_heads_cls or ROIHeads)(num_classes)
 
     def adapted_parameters(self):
         """Parameters the test-time loss reaches: res3-res5 and FPN (stem + res2 are frozen, FREEZE_AT = 2; RPN / ROI
@@ -706,27 +812,34 @@ class MaskRCNN(nn.Module):
             ps += list(getattr(self.backbone, f"fpn_output{lvl}").parameters())
         return ps
 
-    def features(self, images_u8):
+    def preprocess_image(self, images_u8):
+        """-> (image tensor for ``backbone.pyramid``, [(h, w) per image]): d2 preprocess_image (rcnn.py:219)."""
         _need_cuda(*[p for p in [self.backbone.fpn_output2.weight]])
         dev = self.backbone.fpn_output2.weight.device
+        sizes = [tuple(im.shape[-2:]) for im in images_u8]
         if STEM_TC[0] and CONV_MODE[0] != "simt":
-            x, width = preprocess(images_u8, dev, stem_padded=True)
-            return self.backbone(x, width)
-        return self.backbone(preprocess(images_u8, dev))
+            x, _ = preprocess(images_u8, dev, stem_padded=True)
+        else:
+            x = preprocess(images_u8, dev)
+        return x, sizes
+
+    def features(self, images_u8):
+        return self.backbone.pyramid(self.preprocess_image(images_u8)[0])
 
     def detect_ttt(self, images_u8):
         """rcnn.py:331-345: features (NHWC, grad-carrying), RPN proposals and box-head detections in TRAIN mode."""
-        size = tuple(images_u8[0].shape[-2:])
-        feats = self.features(images_u8)
-        props = self.proposal_generator(feats, size, training=True)
-        dets = self.roi_heads.forward_box(feats, props, size)
+        x, sizes = self.preprocess_image(images_u8)
+        feats = self.backbone.pyramid(x)
+        props = self.proposal_generator.predict(feats, sizes, training=True)
+        dets = self.roi_heads.forward_box(feats, props, sizes)
         return feats, props, dets
 
     @torch.no_grad()
     def inference(self, images_u8, out_sizes=None):
-        """GeneralizedRCNN.inference (rcnn.py:181-182): eval-mode detections with pasted masks."""
-        size = tuple(images_u8[0].shape[-2:])
-        feats = self.features(images_u8)
-        props = self.proposal_generator(feats, size, training=False)
-        dets = self.roi_heads.forward_box(feats, props, size)
-        return self.roi_heads.forward_mask(feats, dets, out_sizes or size, size), feats, props, dets
+        """GeneralizedRCNN.inference (rcnn.py:181-182): eval-mode detections with pasted masks.  out_sizes: (h, w) for all
+        images or one per image (the dataset dict's original 'height' / 'width'); default = the network input sizes."""
+        x, sizes = self.preprocess_image(images_u8)
+        feats = self.backbone.pyramid(x)
+        props = self.proposal_generator.predict(feats, sizes, training=False)
+        dets = self.roi_heads.forward_box(feats, props, sizes)
+        return self.roi_heads.forward_mask(feats, dets, out_sizes or sizes, sizes), feats, props, dets

@@ -3,6 +3,18 @@
 adapteacher/modeling/GModule/build_graph.py:78-85 and adapteacher/evaluation/dice_metric.py:34-36 read."""
 
 
+class ImageList:
+    """d2 ImageList: ``tensor`` = the padded batch (here: the preprocessed NHWC fp32 tensor the backbone kernels read),
+    ``image_sizes`` = [(h, w)] of every image before padding (boxes are clipped to these, not to the canvas)."""
+
+    def __init__(self, tensor, image_sizes):
+        self.tensor = tensor
+        self.image_sizes = [tuple(int(v) for v in s) for s in image_sizes]
+
+    def __len__(self):
+        return len(self.image_sizes)
+
+
 class Boxes:
     def __init__(self, tensor):
         self.tensor = tensor
