@@ -231,7 +231,7 @@ def conv_roofline(step_fn, conv, steps=2):
     SURVEY 8d) / summed kernel time; in the 3xTF32 parity mode the tensor pipe executes three TF32 MMAs per product, reported
     as `mma_tflops`.  `peak` = the measured dense bf16 rate (sustained: the kernels run inside a long step), halved for the
     TF32 modes (TF32 runs at half the 16-bit rate)."""
-    with timed_lib(("ttdg_conv_tc", "ttdg_wgrad_tc", "ttdg_stem_tc")) as rec:
+    with timed_lib(("ttdg_conv_tc", "ttdg_wgrad_tc", "ttdg_stem_tc", "ttdg_stem_tc2", "ttdg_conv_tc_bf16")) as rec:
         for _ in range(steps):
             step_fn()
         torch.cuda.synchronize()
@@ -239,6 +239,8 @@ def conv_roofline(step_fn, conv, steps=2):
     for name, a, e0, e1 in rec:
         if name == "ttdg_conv_tc":          # res_mode, relu, flip, N, H, W, Cin, Cout, R, S, pad, in_stride, ...
             N, H, W, Cin, Cout, R, S, pad, stride = a[3:12]
+        elif name == "ttdg_conv_tc_bf16":   # res_bf16, res_mode, relu, flip, N, H, W, Cin, Cout, R, S, pad, in_stride, ...
+            N, H, W, Cin, Cout, R, S, pad, stride = a[4:13]
         elif name == "ttdg_wgrad_tc":       # precise, N, H, W, Cin, Cout, R, S, stride, pad
             N, H, W, Cin, Cout, R, S, stride, pad = a[1:10]
         else:                               # stem: Wp, relu, N, H, W  (7 x 7 stride 2, 3 -> 64)

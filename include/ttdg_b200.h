@@ -289,6 +289,25 @@ int ttdg_tf32_split(const float *x, float *hi, float *lo, int64_t numel, void *s
 /* w [taps][Cin][Cout] -> wt_hi, wt_lo (may be NULL) [taps][Cout][Cin] */
 int ttdg_weight_transpose_split(const float *w, int taps, int Cin, int Cout, float *wt_hi, float *wt_lo, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * bf16 backbone (BASELINE.json configs[2]: "bf16 backbone / fp32 Sinkhorn").  Replaces the same Detectron2 ResNet-50-FPN
+ * convolutions as ttdg_conv_tc (meta_arch/rcnn.py:226, configs/Base-RCNN-FPN.yaml:3-8) with bf16 activations and weights in
+ * HBM: tcgen05.mma.kind::f16, fp32 accumulation in TMEM, fp32 epilogue (FrozenBN scale / bias, residual, ReLU).
+ * x: N x H x W x Cin bf16 (Cin % 64 == 0); wk: [taps][n][k] bf16 K-major (ttdg_weight_transpose_bf16 of the fp32 master
+ * weights, which stay in the optimizer's flat bucket); residual: bf16 when res_bf16 else fp32; y: bf16 when out_bf16 else fp32
+ * (the FPN output convolutions hand an fp32 pyramid to the heads and to the matching stage).  Other arguments as ttdg_conv_tc.
+ * ttdg_stem_tc2 = ttdg_stem_tc with an optional bf16 output; the two elementwise helpers are the stem max pool on bf16 maps
+ * and the ReLU-mask / FrozenBN-scale backward with the stored bf16 output as the mask (gradients stay fp32).
+ * --------------------------------------------------------------------------------------------- */
+int ttdg_conv_tc_bf16(const void *x, const void *wk, const float *scale, const float *bias, const void *residual, int res_bf16,
+                      int res_mode, int relu, int flip, int N, int H, int W, int Cin, int Cout, int R, int S, int pad,
+                      int in_stride, int out_stride, int outH, int outW, void *y, int out_bf16, void *stream);
+int ttdg_weight_transpose_bf16(const float *w, int taps, int Cin, int Cout, void *wt_bf16, void *stream);
+int ttdg_stem_tc2(const float *x_pad, int Wp, const float *wk_hi, const float *wk_lo, const float *scale, const float *bias,
+                  int relu, int N, int H, int W, void *y, int out_bf16, void *stream);
+int ttdg_maxpool3x3s2_bf16(const void *x, int N, int H, int W, int C, void *y, void *stream);
+int ttdg_relu_bn_bwd_bf16y(const float *g, const void *y_bf16, const float *scale, int C, int64_t numel, float *out, void *stream);
+
 /* RPN: decode + clip the anchors selected per level (d2 find_top_rpn_proposals / Box2BoxTransform.apply_deltas).
  * idx [n_img][k] indexes (pixel * A + a); deltas = NHWC head output, channel a * 4 + c, row pitch ld_deltas;
  * cell_anchors_h = HOST float[A][4].  valid = finite and non-empty after clipping. */

@@ -19,7 +19,7 @@ def test_train_net_eval_only_synthetic(tmp_path):
     import bench
     import train_net
     from adapteacher.checkpoint import DetectionCheckpointer
-    torch.save({"model": {"module." + k: v for k, v in bench.full_state().items()}}, tmp_path / "model_final.pth")
+    torch.save({"model": {"module." + k: v for k, v in bench.full_state(bench.CONFIGS[1]).items()}}, tmp_path / "model_final.pth")
     out_dir = tmp_path / "out"
     args = train_net.default_argument_parser().parse_args(
         ["--eval-only", "--config", os.path.join(ROOT, "ttdg-mgm_b200", "configs", "test_segment_synthetic.yaml"),

@@ -243,3 +243,29 @@ def test_sinkhorn_large_full_size_properties():
         torch.testing.assert_close(ops.sinkhorn(s2, max_iter=50, tau=0.05), out, atol=3e-4, rtol=1e-2)
         # batch items are independent
         torch.testing.assert_close(ops.sinkhorn(s[B // 2:B // 2 + 1], max_iter=50, tau=0.05), out[B // 2:B // 2 + 1], atol=0, rtol=0)
+
+
+@pytest.mark.parametrize("n1,n2", [(256, 256), (300, 512)])
+def test_affinity_large_vs_oracle(n1, n2):
+    """BASELINE.json configs[4] sizes (the microbench runs N = 256 / 512 / 1024): the separable-form affinity beyond the
+    96-node graphs of the matching stage, forward and every gradient, against the reference-form oracle (which materialises
+    the n1 x n2 x 512 tensor, utils/affinity.py:48-54)."""
+    from adapteacher.modeling.GModule.utils.affinity import Affinity
+    sd = synth.perturb_affinity_state(synth.mgm_unsup_state(0), 0)
+    aff = Affinity(256).cuda()
+    aff.load_state_dict({k[len("node_affinity."):]: v for k, v in sd.items() if k.startswith("node_affinity.")})
+    g = torch.Generator().manual_seed(31)
+    X, Y, up = torch.randn(n1, 256, generator=g), torch.randn(n2, 256, generator=g), torch.randn(n1, n2, generator=g)
+    sdc = {k: v.clone().double().requires_grad_(k.startswith("node_affinity.")) for k, v in sd.items()}
+    Xc, Yc = X.clone().double().requires_grad_(True), Y.clone().double().requires_grad_(True)
+    ref = mgm_port.affinity(sdc, Xc, Yc)
+    (ref * up.double()).sum().backward()
+    Xg, Yg = X.cuda().requires_grad_(True), Y.cuda().requires_grad_(True)
+    out = aff(Xg, Yg)
+    (out * up.cuda()).sum().backward()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), atol=2e-6 * float(ref.abs().max()), rtol=1e-5)
+    rel = lambda a, r: float((a.double().cpu() - r).norm() / r.norm())
+    assert rel(Xg.grad, Xc.grad) < 1e-5 and rel(Yg.grad, Yc.grad) < 1e-5
+    for name, p in (("fc_M.0.weight", aff.fc_M[0].weight), ("fc_M.2.weight", aff.fc_M[2].weight),
+                    ("project_sr.weight", aff.project_sr.weight), ("project_tg.weight", aff.project_tg.weight)):
+        assert rel(p.grad, sdc["node_affinity." + name].grad) < 1e-5, name

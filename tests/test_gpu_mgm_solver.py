@@ -150,7 +150,7 @@ def test_mgm3_unsup_end_to_end(path):
     U = aux["U"].cpu().numpy()
     # same solver call with the trajectory recorded: identical result, every iteration verified
     U2, info, trace, meta = ops.gagm_solve(aux["A"], aux["Wds"], aux["U0"], list(sizes), trace_cap=1300)
-    assert np.array_equal(U, U2.cpu().numpy()) and torch.equal(info, aux["info"])
+    assert np.array_equal(U, U2.cpu().numpy()) and torch.equal(info[:8], aux["info"][:8])     # [8:] = cycle counters
     verify_trajectory(aux["A"].cpu(), aux["Wds"].cpu(), aux["U0"].cpu(), list(sizes), trace, meta, info.cpu().tolist())
     assert set(np.unique(U)) <= {0.0, 1.0}
     for gi, n in enumerate(sizes):

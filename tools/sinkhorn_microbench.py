@@ -35,12 +35,27 @@ for n in (256, 512, 1024):
         gbs = alg / (ms * 1e-3) / 1e9
         print(json.dumps({"op": "sinkhorn", "N": n, "batch": batch, "iters": 50, "ms": round(ms, 4), "algorithmic_GBps": round(gbs, 1),
                           "frac_of_measured_hbm": round(gbs / peak, 3)}))
-# affinity pair kernel (separable form), one N x N pair
+# affinity (utils/affinity.py:44-57), one N x N pair, forward and forward + backward, separable form
+# (sum_k w1_k relu(a_ik + c_jk): no N x N x 512 tensor; the reference materialises 512 N^2 floats = 2.1 GB at N = 1024)
 from adapteacher.modeling.GModule.utils.affinity import Affinity  # noqa: E402
 aff = Affinity(256).to(dev)
-for n in (64, 96):
-    X = torch.randn(2 * n, 256, device=dev)
+for n in (64, 96, 256, 512, 1024):
+    X = torch.randn(n, 256, device=dev, requires_grad=True)
+    Y = torch.randn(n, 256, device=dev, requires_grad=True)
+    up = torch.randn(n, n, device=dev)
     with torch.no_grad():
-        ms = timeit(lambda: aff.forward_pairs(X, [n, n], [(0, 1)]))
+        ms_f = timeit(lambda: aff(X, Y))
+
+    def fb():
+        for p in list(aff.parameters()) + [X, Y]:
+            p.grad = None
+        (aff(X, Y) * up).sum().backward()
+    ms_fb = timeit(fb)
     flops_ref = 2 * n * n * (512 * 512 + 512) + 2 * 2 * n * 256 * 256
-    print(json.dumps({"op": "affinity_fwd", "N": n, "ms": round(ms, 4), "reference_form_GFLOPs": round(flops_ref / (ms * 1e-3) / 1e9, 1)}))
+    flops_sep = 2 * (2 * n) * 256 * (256 + 512) + 3 * n * n * 512
+    bytes_alg = 4 * (256 * 2 * n + n * n) + 4 * (2 * 256 * 256 + 512 * 512 + 1025)
+    print(json.dumps({"op": "affinity", "N": n, "fwd_ms": round(ms_f, 4), "fwd_bwd_ms": round(ms_fb, 4),
+                      "fwd_reference_form_GFLOPs": round(flops_ref / (ms_f * 1e-3) / 1e9, 1),
+                      "fwd_separable_form_GFLOPs": round(flops_sep / (ms_f * 1e-3) / 1e9, 1),
+                      "fwd_algorithmic_GBps": round(bytes_alg / (ms_f * 1e-3) / 1e9, 2),
+                      "bound": "fp64 CUDA-core ALU (3 * 512 * N^2 flops between the two contractions; no tensor cores: the ReLU sits between them)"}))

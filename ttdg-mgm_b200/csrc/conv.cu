@@ -15,6 +15,7 @@
 // top-down nearest upsample) -> optional ReLU -> Y[(img, ho*os, wo*os)][n].
 // Weights are stored [R][S][Cin][Cout] (the host wrapper permutes torch's [Cout][Cin][R][S]).
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace ttdg {
 
@@ -428,6 +429,79 @@ extern "C" int ttdg_relu_bn_bwd(const float *g, const float *y, const float *sca
     if (nb > 148 * 8) nb = 148 * 8;
     count_launches(1);
     relu_bn_bwd_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(g, y, scale, C, numel / 4, out);
+    TTDG_LAUNCH_RET();
+}
+
+namespace ttdg {
+__device__ __forceinline__ float4 bf16x4_to_float4(uint2 v) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&v.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&v.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+// bf16 backbone: the ReLU mask comes from the stored bf16 output, gradients stay fp32
+__global__ void __launch_bounds__(256)
+relu_bn_bwd_bf16y_kernel(const float *__restrict__ g, const __nv_bfloat16 *__restrict__ y, const float *__restrict__ scale, int C,
+                         int64_t n4, float *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+        float4 gv = reinterpret_cast<const float4 *>(g)[i];
+        const float4 yv = bf16x4_to_float4(reinterpret_cast<const uint2 *>(y)[i]);
+        gv.x = yv.x > 0.f ? gv.x : 0.f; gv.y = yv.y > 0.f ? gv.y : 0.f; gv.z = yv.z > 0.f ? gv.z : 0.f; gv.w = yv.w > 0.f ? gv.w : 0.f;
+        if (scale) {
+            const float4 sc = *reinterpret_cast<const float4 *>(scale + (int)((i * 4) % C));
+            gv.x *= sc.x; gv.y *= sc.y; gv.z *= sc.z; gv.w *= sc.w;
+        }
+        reinterpret_cast<float4 *>(out)[i] = gv;
+    }
+}
+// 3x3 stride-2 pad-1 max pooling on bf16 NHWC maps (the bf16 backbone's stem)
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_bf16_kernel(const __nv_bfloat16 *__restrict__ x, int N, int H, int W, int C, int Ho, int Wo, __nv_bfloat16 *__restrict__ y) {
+    const int64_t total = (int64_t)N * Ho * Wo * (C / 4);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int c4 = (int)(i % (C / 4));
+        int64_t t = i / (C / 4);
+        const int wo = (int)(t % Wo); t /= Wo;
+        const int ho = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int r = 0; r < 3; ++r) {
+            const int hi = ho * 2 + r - 1;
+            if (hi < 0 || hi >= H) continue;
+            for (int s = 0; s < 3; ++s) {
+                const int wi = wo * 2 + s - 1;
+                if (wi < 0 || wi >= W) continue;
+                const float4 v = bf16x4_to_float4(*reinterpret_cast<const uint2 *>(x + ((size_t)(n * H + hi) * W + wi) * C + c4 * 4));
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            }
+        }
+        const __nv_bfloat162 lo2 = __floats2bfloat162_rn(m.x, m.y), hi2 = __floats2bfloat162_rn(m.z, m.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t *>(&lo2); pk.y = *reinterpret_cast<const uint32_t *>(&hi2);
+        *reinterpret_cast<uint2 *>(y + i * 4) = pk;
+    }
+}
+}  // namespace ttdg
+
+extern "C" int ttdg_relu_bn_bwd_bf16y(const float *g, const void *y_bf16, const float *scale, int C, int64_t numel, float *out, void *stream) {
+    TTDG_CHECK_ARG(g && y_bf16 && out && C % 4 == 0 && numel % 4 == 0 && numel >= 0);
+    if (numel == 0) return 0;
+    int64_t nb = (numel / 4 + 255) / 256;
+    if (nb > 148 * 8) nb = 148 * 8;
+    count_launches(1);
+    relu_bn_bwd_bf16y_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(g, reinterpret_cast<const __nv_bfloat16 *>(y_bf16), scale, C, numel / 4, out);
+    TTDG_LAUNCH_RET();
+}
+
+extern "C" int ttdg_maxpool3x3s2_bf16(const void *x, int N, int H, int W, int C, void *y, void *stream) {
+    TTDG_CHECK_ARG(x && y && C % 4 == 0);
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const int64_t total = (int64_t)N * Ho * Wo * (C / 4);
+    if (total == 0) return 0;
+    int64_t nb = (total + 255) / 256;
+    if (nb > 148 * 8) nb = 148 * 8;
+    count_launches(1);
+    maxpool3x3s2_bf16_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16 *>(x), N, H, W, C, Ho, Wo,
+                                                                            reinterpret_cast<__nv_bfloat16 *>(y));
     TTDG_LAUNCH_RET();
 }
 

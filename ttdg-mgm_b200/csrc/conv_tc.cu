@@ -21,6 +21,7 @@
 // overlap); optional thread-block clusters share the weight tile by TMA multicast.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -41,8 +42,10 @@ constexpr int TC_BK = 32;            // fp32 channels per k-block = one 128-byte
 constexpr int TC_UMMA_K = 8;         // tf32
 
 struct TcParams {
-    float *y;
-    const float *scale, *bias, *residual;
+    void *y;                         // fp32, or bf16 when out_bf16
+    const float *scale, *bias;
+    const void *residual;            // fp32, or bf16 when res_bf16
+    int out_bf16, res_bf16;
     int N, Ho, Wo, Cout;
     int R, S, pad, flip;             // flip = 1: data gradient (taps mirrored)
     int BW, BH, BI;                  // box extents: pixels along W, rows, images
@@ -107,6 +110,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// kind::f16 with bf16 operands (instruction descriptor formats 1 / 1), both from shared-memory descriptors, K = 16 per MMA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
@@ -314,11 +325,17 @@ __device__ __forceinline__ void tc_drain(const TcSmem &sm, uint32_t tmem_base, i
 // tile are in flight while the current one computes, and - the accumulator being double buffered - the epilogue of tile t
 // (TMEM drain, residual read, global stores) overlaps the MMAs of tile t + 1.  (One tile per CTA serialised set-up, TMA
 // round trip, MMAs and epilogue: 13 us per CTA wave on the short-K 1x1 layers.)
-template <int BN_TILE, bool PRECISE, int CL>
+// BF16 = true (configs[2], "bf16 backbone"): activations and weights are bf16 in HBM, a k-block is 64 channels (again one
+// 128-byte swizzle row per pixel / per filter), both operands come from shared-memory descriptors and the MMAs are
+// tcgen05.mma.kind::f16 with K = 16 (the same 32 bytes of the row per MMA as K = 8 of tf32): the stage geometry, the ring,
+// the chunked fp32 accumulation in TMEM and the epilogue are those of the single-pass path.
+template <int BN_TILE, bool PRECISE, int CL, bool BF16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
+    static_assert(!(BF16 && PRECISE), "bf16 is a single-pass mode");
     using Cfg = TcCfg<BN_TILE, PRECISE>;
+    constexpr int KCH = BF16 ? 64 : TC_BK;                                        // channels per k-block
     extern __shared__ unsigned char tc_smem_raw[];
     TcSmem sm;
     const uint32_t tmem_base = tc_prologue<Cfg, CL>(sm, tc_smem_raw);
@@ -352,7 +369,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int stage = (int)(it % Cfg::STAGES);
                     const uint32_t phase = (it / Cfg::STAGES) & 1u;
-                    const int tap = kb / p.kslabs, c0 = (kb - tap * p.kslabs) * TC_BK;
+                    const int tap = kb / p.kslabs, c0 = (kb - tap * p.kslabs) * KCH;
                     const int r = tap / p.S, s = tap - r * p.S;
                     const int btap = p.flip ? (p.R - 1 - r) * p.S + (p.S - 1 - s) : tap;
                     mbar_wait(&sm.empty[stage], phase ^ 1);
@@ -375,7 +392,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== MMA issuer
         if (lane == 0) {
             // instruction descriptor: D = F32, A = B = TF32, both K-major, N = BN_TILE, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN_TILE >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            // (kind::f16: A = B = BF16 is format 1)
+            const uint32_t fmt = BF16 ? 1u : 2u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN_TILE >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             uint32_t it = 0, gc = 0;                                             // k-blocks consumed, accumulation chunks issued
             const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
             for (int item = clus; item < nitems; item += nclus) {
@@ -401,6 +420,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 umma_tf32_ts(tacc, ta + k * TC_UMMA_K, umma_desc(b + koff), idesc, first);
                                 umma_tf32_ts(tacc, ta + TC_BK + k * TC_UMMA_K, umma_desc(b + koff), idesc, 1);
                                 umma_tf32_ts(tacc, ta + k * TC_UMMA_K, umma_desc(blo + koff), idesc, 1);
+                            } else if (BF16) {
+                                umma_bf16(tacc, umma_desc(a + koff), umma_desc(b + koff), idesc, first);
                             } else {
                                 umma_tf32(tacc, umma_desc(a + koff), umma_desc(b + koff), idesc, first);
                             }
@@ -438,10 +459,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const size_t pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
                 const size_t opix = ((size_t)img * p.outH + ho * p.out_stride) * p.outW + wo * p.out_stride;
                 const int nb = n0 + col0;
-                float *yrow = p.y + opix * p.Cout + nb;
-                const float *rrow = nullptr;
-                if (p.res_mode == 1) rrow = p.residual + pix * p.Cout + nb;
-                else if (p.res_mode == 2) rrow = p.residual + (((size_t)img * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * p.Cout + nb;
+                const size_t rpix = p.res_mode == 2 ? (((size_t)img * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) : pix;
+                const float *rrow = (p.res_mode && !p.res_bf16) ? reinterpret_cast<const float *>(p.residual) + rpix * p.Cout + nb : nullptr;
+                const __nv_bfloat16 *rrow16 = (p.res_mode && p.res_bf16) ? reinterpret_cast<const __nv_bfloat16 *>(p.residual) + rpix * p.Cout + nb : nullptr;
+                float *yrow = p.out_bf16 ? nullptr : reinterpret_cast<float *>(p.y) + opix * p.Cout + nb;
+                __nv_bfloat16 *yrow16 = p.out_bf16 ? reinterpret_cast<__nv_bfloat16 *>(p.y) + opix * p.Cout + nb : nullptr;
 #pragma unroll
                 for (int j = 0; j < Cfg::EPI_COLS; j += 4) {
                     float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
@@ -449,8 +471,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (p.scale) { const float4 s4 = *reinterpret_cast<const float4 *>(p.scale + n); o.x *= s4.x; o.y *= s4.y; o.z *= s4.z; o.w *= s4.w; }
                     if (p.bias) { const float4 b4 = *reinterpret_cast<const float4 *>(p.bias + n); o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w; }
                     if (rrow) { const float4 r4 = *reinterpret_cast<const float4 *>(rrow + j); o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
+                    if (rrow16) {
+                        const uint2 rr = *reinterpret_cast<const uint2 *>(rrow16 + j);
+                        const float2 r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rr.x));
+                        const float2 r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rr.y));
+                        o.x += r01.x; o.y += r01.y; o.z += r23.x; o.w += r23.y;
+                    }
                     if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                    *reinterpret_cast<float4 *>(yrow + j) = o;
+                    if (yrow16) {
+                        const __nv_bfloat162 lo2 = __floats2bfloat162_rn(o.x, o.y), hi2 = __floats2bfloat162_rn(o.z, o.w);
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<const uint32_t *>(&lo2); pk.y = *reinterpret_cast<const uint32_t *>(&hi2);
+                        *reinterpret_cast<uint2 *>(yrow16 + j) = pk;
+                    } else {
+                        *reinterpret_cast<float4 *>(yrow + j) = o;
+                    }
                 }
             }
         }
@@ -707,7 +742,7 @@ static EncodeTiledFn get_encode() {
 // caching allocator hands back at the same address with the same geometry: keep a small cache keyed by
 // (base, dims, box).  The descriptor only names the address and the geometry, so a hit is always valid.
 struct MapKey {
-    const void *base; int rank; int swizzle; int estride; cuuint64_t d[4]; cuuint32_t b[4]; cuuint64_t st[3];
+    const void *base; int rank; int swizzle; int estride; cuuint64_t d[4]; cuuint32_t b[4]; cuuint64_t st[3];   // swizzle: + 64 for bf16 elements
     bool operator==(const MapKey &o) const {
         if (base != o.base || rank != o.rank || swizzle != o.swizzle || estride != o.estride) return false;
         for (int i = 0; i < rank; ++i) if (d[i] != o.d[i] || b[i] != o.b[i]) return false;
@@ -725,15 +760,16 @@ struct MapKeyHash {
 
 // estride: traversal stride of dimensions 1 and 2 (W, H) of a 4-D activation map - 2 for strided 1x1 convolutions (the
 // box then spans 2x the pixels and TMA delivers every other one)
-static int make_map(CUtensorMap *m, const float *base, int rank, const cuuint64_t *dims, const cuuint32_t *box,
-                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, int estride = 1, const cuuint64_t *strides_in = nullptr) {
+static int make_map(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dims, const cuuint32_t *box,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, int estride = 1, const cuuint64_t *strides_in = nullptr,
+                    bool bf16 = false) {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
     MapKey key = {};
     cuuint64_t strides[4];
     if (strides_in) for (int i = 0; i < rank - 1; ++i) strides[i] = strides_in[i];
-    else { cuuint64_t sb = sizeof(float); for (int i = 0; i < rank - 1; ++i) { sb *= dims[i]; strides[i] = sb; } }
-    key.base = base; key.rank = rank; key.swizzle = (int)swizzle; key.estride = estride;
+    else { cuuint64_t sb = bf16 ? 2 : sizeof(float); for (int i = 0; i < rank - 1; ++i) { sb *= dims[i]; strides[i] = sb; } }
+    key.base = base; key.rank = rank; key.swizzle = (int)swizzle + (bf16 ? 64 : 0); key.estride = estride;
     for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
     for (int i = 0; i < rank - 1; ++i) key.st[i] = strides[i];
     {
@@ -745,7 +781,7 @@ static int make_map(CUtensorMap *m, const float *base, int rank, const cuuint64_
     if (!enc) return TTDG_E_LIMIT;
     // estride > 0: W and H strided (1x1 stride-2 convs); estride = -2: H only (stem: W is already a stride-2 window index)
     cuuint32_t estr[4] = {1, (cuuint32_t)(estride > 0 ? estride : 1), (cuuint32_t)(estride > 0 ? estride : -estride), 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float *>(base), dims, strides, box, estr,
+    CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return TTDG_E_ARG;
@@ -779,10 +815,10 @@ static int tc_sm_count() {
     return n;
 }
 
-template <int BN_TILE, bool PRECISE, int CL>
+template <int BN_TILE, bool PRECISE, int CL, bool BF16 = false>
 static int launch_tc_cl(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &blo, const TcParams &p, cudaStream_t st) {
     using Cfg = TcCfg<BN_TILE, PRECISE>;
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_TILE, PRECISE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_TILE, PRECISE, CL, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return (int)e;
     // persistent grid: one CTA per SM (whole clusters), each walking its share of the (pixel-tile group, N tile) items;
     // a group is padded to CL pixel tiles - the extra ones run on out-of-range coordinates so that their share of the
@@ -802,7 +838,7 @@ static int launch_tc_cl(const CUtensorMap &a, const CUtensorMap &b, const CUtens
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = CL > 1 ? 1 : 0;
     count_launches(1);
-    return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN_TILE, PRECISE, CL>, a, b, blo, p);
+    return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN_TILE, PRECISE, CL, BF16>, a, b, blo, p);
 }
 
 // cl: cluster size the weight tensor maps were built for (their box holds BN_TILE / cl rows)
@@ -880,12 +916,19 @@ extern "C" int ttdg_wgrad_tc(const float *x, const float *dy, int precise, int N
 // row with element stride 2 (rows outside the image are TMA zero fill).  wk_hi / wk_lo: [7][64][32] with
 // wk[r][co][4 s + c] = w[r][s][c][co] (s < 7), zeros for s = 7, split like the other weights (wk_lo NULL = single pass).
 // y: N x H/2 x W/2 x 64.  H, W even.  Returns TTDG_E_ARG if the driver rejects the overlapping tensor map.
+extern "C" int ttdg_stem_tc2(const float *x_pad, int Wp, const float *wk_hi, const float *wk_lo, const float *scale, const float *bias,
+                             int relu, int N, int H, int W, void *y, int out_bf16, void *stream);
 extern "C" int ttdg_stem_tc(const float *x_pad, int Wp, const float *wk_hi, const float *wk_lo, const float *scale, const float *bias,
                             int relu, int N, int H, int W, float *y, void *stream) {
+    return ttdg_stem_tc2(x_pad, Wp, wk_hi, wk_lo, scale, bias, relu, N, H, W, y, 0, stream);
+}
+// out_bf16 != 0: y is N x H/2 x W/2 x 64 bf16 (the bf16 backbone's first activation)
+extern "C" int ttdg_stem_tc2(const float *x_pad, int Wp, const float *wk_hi, const float *wk_lo, const float *scale, const float *bias,
+                             int relu, int N, int H, int W, void *y, int out_bf16, void *stream) {
     TTDG_CHECK_ARG(x_pad && wk_hi && y && N >= 0 && H > 0 && W > 0 && Wp >= W + 8 && (H % 2) == 0 && (W % 2) == 0);
     if (N == 0) return 0;
     TcParams p = {};
-    p.y = y; p.scale = scale; p.bias = bias; p.relu = relu; p.stem = 1;
+    p.y = y; p.out_bf16 = out_bf16 ? 1 : 0; p.scale = scale; p.bias = bias; p.relu = relu; p.stem = 1;
     p.N = N; p.Ho = H / 2; p.Wo = W / 2; p.Cout = 64;
     p.in_stride = 1; p.out_stride = 1; p.outH = p.Ho; p.outW = p.Wo;
     p.R = 7; p.S = 1; p.pad = 0; p.flip = 0; p.kslabs = 1;
@@ -943,10 +986,13 @@ extern "C" int ttdg_conv_tc_supported(int Cin, int Cout, int stride) {
 // single-pass TF32; otherwise 3xTF32 with the activations split inside the pipeline.
 // in_stride = 2 (1x1 convs, pad 0): y[n, ho, wo] = W x[n, 2 ho, 2 wo] (forward of a strided 1x1 conv).  out_stride = 2: the
 // result for (ho, wo) is stored at (2 ho, 2 wo) of an outH x outW map the caller zero-filled (its data gradient).
-extern "C" int ttdg_conv_tc(const float *x, const float *wk_hi, const float *wk_lo, const float *scale, const float *bias,
-                            const float *residual, int res_mode, int relu, int flip, int N, int H, int W, int Cin, int Cout, int R,
-                            int S, int pad, int in_stride, int out_stride, int outH, int outW, float *y, void *stream) {
+static int conv_tc_impl(const void *x, const void *wk_hi, const void *wk_lo, const float *scale, const float *bias,
+                        const void *residual, int res_mode, int relu, int flip, int N, int H, int W, int Cin, int Cout, int R,
+                        int S, int pad, int in_stride, int out_stride, int outH, int outW, void *y, void *stream,
+                        bool bf16, int res_bf16, int out_bf16) {
     TTDG_CHECK_ARG(x && wk_hi && y && N >= 0 && H > 0 && W > 0 && R > 0 && S > 0 && pad >= 0);
+    const int KCH = bf16 ? 64 : TC_BK;
+    if (bf16 && (Cin % 64 != 0 || wk_lo)) return TTDG_E_LIMIT;
     TTDG_CHECK_ARG(res_mode == 0 || residual);
     TTDG_CHECK_ARG((in_stride == 1 || in_stride == 2) && (out_stride == 1 || out_stride == 2));
     if ((in_stride == 2 || out_stride == 2) && (R != 1 || S != 1 || pad != 0)) return TTDG_E_LIMIT;
@@ -954,11 +1000,12 @@ extern "C" int ttdg_conv_tc(const float *x, const float *wk_hi, const float *wk_
     if (N == 0) return 0;
     TcParams p = {};
     p.y = y; p.scale = scale; p.bias = bias; p.residual = residual; p.res_mode = res_mode; p.relu = relu;
+    p.out_bf16 = out_bf16 ? 1 : 0; p.res_bf16 = res_bf16 ? 1 : 0;
     p.N = N; p.Ho = (H + 2 * pad - R) / in_stride + 1; p.Wo = (W + 2 * pad - S) / in_stride + 1; p.Cout = Cout;
     p.in_stride = in_stride; p.out_stride = out_stride;
     p.outH = out_stride == 1 ? p.Ho : outH; p.outW = out_stride == 1 ? p.Wo : outW;
     if (out_stride == 2 && ((p.Ho - 1) * 2 >= outH || (p.Wo - 1) * 2 >= outW)) return TTDG_E_ARG;
-    p.R = R; p.S = S; p.pad = pad; p.flip = flip; p.kslabs = Cin / TC_BK;
+    p.R = R; p.S = S; p.pad = pad; p.flip = flip; p.kslabs = Cin / KCH;
     if (p.Ho < 1 || p.Wo < 1) return TTDG_E_ARG;
     if (res_mode == 2 && ((p.Ho | p.Wo) & 1)) return TTDG_E_ARG;
     p.BW = pow2_ge(p.Wo) < TC_BM ? pow2_ge(p.Wo) : TC_BM;
@@ -980,20 +1027,66 @@ extern "C" int ttdg_conv_tc(const float *x, const float *wk_hi, const float *wk_
     p.a_tx = p.BW * p.BH * p.BI * 128;
     CUtensorMap ma, mb, mblo;
     const cuuint64_t adims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    const cuuint32_t abox[4] = {TC_BK, (cuuint32_t)(p.BW * in_stride), (cuuint32_t)(p.BH * in_stride), (cuuint32_t)p.BI};
+    const cuuint32_t abox[4] = {(cuuint32_t)KCH, (cuuint32_t)(p.BW * in_stride), (cuuint32_t)(p.BH * in_stride), (cuuint32_t)p.BI};
     const cuuint64_t bdims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(R * S)};
     const int tiles = p.tilesW * p.tilesH * p.tilesI;
     // (64-wide N tiles for the small res5 maps - 64 items on 148 SMs with 128-wide tiles - measured slower: 114 vs 105 us)
     const int bn_tile = Cout % 128 == 0 ? 128 : 64;
-    int cl = tc_cluster_size();
+    int cl = bf16 ? 1 : tc_cluster_size();
     while (cl > 1 && tiles < 2 * cl) cl >>= 1;              // tiny layers: no point padding the grid
-    const cuuint32_t bbox[3] = {TC_BK, (cuuint32_t)(bn_tile / cl), 1};
-    int rc = make_map(&ma, x, 4, adims, abox, CU_TENSOR_MAP_SWIZZLE_128B, in_stride);
-    if (!rc) rc = make_map(&mb, wk_hi, 3, bdims, bbox);
+    const cuuint32_t bbox[3] = {(cuuint32_t)KCH, (cuuint32_t)(bn_tile / cl), 1};
+    int rc = make_map(&ma, x, 4, adims, abox, CU_TENSOR_MAP_SWIZZLE_128B, in_stride, nullptr, bf16);
+    if (!rc) rc = make_map(&mb, wk_hi, 3, bdims, bbox, CU_TENSOR_MAP_SWIZZLE_128B, 1, nullptr, bf16);
     if (!rc && wk_lo) rc = make_map(&mblo, wk_lo, 3, bdims, bbox);
     if (rc) return rc;
     if (!wk_lo) mblo = mb;
     cudaStream_t st = (cudaStream_t)stream;
+    if (bf16) return bn_tile == 128 ? launch_tc_cl<128, false, 1, true>(ma, mb, mblo, p, st) : launch_tc_cl<64, false, 1, true>(ma, mb, mblo, p, st);
     if (wk_lo) return bn_tile == 128 ? launch_tc<128, true>(ma, mb, mblo, p, st, cl) : launch_tc<64, true>(ma, mb, mblo, p, st, cl);
     return bn_tile == 128 ? launch_tc<128, false>(ma, mb, mblo, p, st, cl) : launch_tc<64, false>(ma, mb, mblo, p, st, cl);
+}
+
+extern "C" int ttdg_conv_tc(const float *x, const float *wk_hi, const float *wk_lo, const float *scale, const float *bias,
+                            const float *residual, int res_mode, int relu, int flip, int N, int H, int W, int Cin, int Cout, int R,
+                            int S, int pad, int in_stride, int out_stride, int outH, int outW, float *y, void *stream) {
+    return conv_tc_impl(x, wk_hi, wk_lo, scale, bias, residual, res_mode, relu, flip, N, H, W, Cin, Cout, R, S, pad, in_stride,
+                        out_stride, outH, outW, y, stream, false, 0, 0);
+}
+
+// The bf16 backbone (BASELINE.json configs[2]): x N x H x W x Cin bf16 (Cin % 64 == 0), wk [taps][n][k] bf16 K-major
+// (ttdg_weight_transpose_bf16), tcgen05.mma.kind::f16 with fp32 accumulation in TMEM, the same fp32 epilogue (FrozenBN scale /
+// bias, residual, ReLU).  residual is bf16 when res_bf16 else fp32; y is bf16 when out_bf16 else fp32 (the FPN output
+// convolutions hand an fp32 pyramid to the heads and the matching stage).
+extern "C" int ttdg_conv_tc_bf16(const void *x, const void *wk, const float *scale, const float *bias, const void *residual,
+                                 int res_bf16, int res_mode, int relu, int flip, int N, int H, int W, int Cin, int Cout, int R, int S,
+                                 int pad, int in_stride, int out_stride, int outH, int outW, void *y, int out_bf16, void *stream) {
+    return conv_tc_impl(x, wk, nullptr, scale, bias, residual, res_mode, relu, flip, N, H, W, Cin, Cout, R, S, pad, in_stride,
+                        out_stride, outH, outW, y, stream, true, res_bf16, out_bf16);
+}
+
+namespace ttdg {
+// w [taps][Cin][Cout] fp32 (the master weights) -> [taps][Cout][Cin] bf16 (K-major for the forward GEMM); 32 x 32 tiles through smem
+__global__ void __launch_bounds__(256)
+weight_transpose_bf16_kernel(const float *__restrict__ w, int Cin, int Cout, __nv_bfloat16 *__restrict__ out) {
+    __shared__ float tile[32][33];
+    const int tap = blockIdx.z, ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int ci = ci0 + r, co = co0 + tx;
+        tile[r][tx] = (ci < Cin && co < Cout) ? w[((size_t)tap * Cin + ci) * Cout + co] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int co = co0 + r, ci = ci0 + tx;
+        if (co < Cout && ci < Cin) out[((size_t)tap * Cout + co) * Cin + ci] = __float2bfloat16_rn(tile[tx][r]);
+    }
+}
+}  // namespace ttdg
+
+extern "C" int ttdg_weight_transpose_bf16(const float *w, int taps, int Cin, int Cout, void *wt_bf16, void *stream) {
+    TTDG_CHECK_ARG(w && wt_bf16 && taps >= 1 && Cin >= 1 && Cout >= 1);
+    count_launches(1);
+    ttdg::weight_transpose_bf16_kernel<<<dim3(ceil_div(Cout, 32), ceil_div(Cin, 32), taps), 256, 0, (cudaStream_t)stream>>>(
+        w, Cin, Cout, reinterpret_cast<__nv_bfloat16 *>(wt_bf16));
+    TTDG_LAUNCH_RET();
 }

@@ -306,7 +306,7 @@ struct LapSmemNegCostP {             // cost(i, j) = -z[i * si + j * sj], plain 
     __device__ __forceinline__ double operator()(int i, int j) const { return -z[i * si + j * sj]; }
 };
 
-constexpr int LAP_ARR_ROUNDS = 3;
+constexpr int LAP_ARR_ROUNDS = 4;
 
 // Proves optimality and uniqueness of w.col4row from the duals w.u / w.v (fp64).  c̄ = (c - u) - v.
 //   feasibility:  c̄ >= -eps everywhere, |c̄| <= eps on the assignment, v <= eps, v = 0 on free columns  => optimal (weak duality);
@@ -322,7 +322,7 @@ __device__ bool lap_certificate(int nr, int nc, Cost cost, LapWork &w) {
     bool free_hit = false, bad = false;
     if (lane < nr) scale = fabs(w.u[lane]);
     for (int o = 16; o > 0; o >>= 1) scale = fmax(scale, __shfl_xor_sync(TTDG_FULL, scale, o));
-    const double delta = 1e-9 * (1.0 + scale), eps = 1e-12 * (1.0 + scale);
+    const double delta = 1e-9 * (1.0 + scale), eps = 1e-11 * (1.0 + scale);
     if (lane < nr) {
         const double ui = w.u[lane];
         const int mine = w.col4row[lane];
@@ -441,24 +441,23 @@ __device__ bool lap_lean_warp_t(int nr, int nc, Cost cost, LapWork &w) {
                 best = better ? cand : best;
                 bpk = better ? (((r4c[t] + 1) << 2) | t) : bpk;
             }
-            // distances are >= 0 up to rounding, so the high word orders them as a signed integer; ties on it are resolved on the low word
+            // arg-min over the warp in two 32-bit reductions, no ballot / shuffle: distances are >= 0 up to rounding, so the high
+            // word orders them as a signed integer; among the lanes that hold the minimal high word the second reduction takes
+            // the low word with its 7 lowest bits replaced by (slot, lane) - a 2^-45 relative perturbation of the comparison,
+            // far below the certificate's margin - so its result names the winning lane and slot AND carries minVal's low word
             const int hi = __double2hiint(best);
             const int mhi = __reduce_min_sync(TTDG_FULL, hi);
-            unsigned tied = __ballot_sync(TTDG_FULL, hi == mhi);
-            if (__popc(tied) != 1) {
-                const unsigned lo = (hi == mhi) ? (unsigned)__double2loint(best) : 0xFFFFFFFFu;
-                const unsigned mlo = __reduce_min_sync(TTDG_FULL, lo);
-                tied = __ballot_sync(TTDG_FULL, hi == mhi && lo == mlo);
-            }
-            const int src = __ffs(tied) - 1;
-            minVal = __shfl_sync(TTDG_FULL, best, src);
-            const int pk = __shfl_sync(TTDG_FULL, bpk, src);
-            const int rsel = (pk >> 2) - 1, ssel = pk & 3;
-            if (!(minVal < INFINITY)) return false;             // cannot happen with finite costs; never loop forever
+            const unsigned k2 = (hi == mhi) ? (((unsigned)__double2loint(best) & ~127u) | (unsigned)((bpk & 3) << 5) | (unsigned)lane) : 0xFFFFFFFFu;
+            const unsigned m2 = __reduce_min_sync(TTDG_FULL, k2);
+            const int src = (int)(m2 & 31u), ssel = (int)((m2 >> 5) & 3u);
+            minVal = __hiloint2double(mhi, (int)(m2 & ~127u));
+            const int jsel = src + 32 * ssel;
+            const int rsel = (mhi == 0x7FF00000) ? -2 : w.row4col[jsel];         // smem read by all lanes (broadcast)
+            if (rsel == -2) return false;                       // cannot happen with finite costs; never loop forever
 #pragma unroll
             for (int t = 0; t < SLOTS; ++t)
-                if (lane == src && t == ssel) { live[t] = false; scanned[t] = true; }
-            if (rsel < 0) { sink = src + 32 * ssel; break; }
+                if (lane == src && t == ssel) { live[t] = false; scanned[t] = true; sh[t] = minVal; }
+            if (rsel < 0) { sink = jsel; break; }
             i = rsel;
         }
         // dual update: u of the visited rows by the owner of their (scanned) column, v in registers; path of the scanned columns

@@ -57,6 +57,11 @@ SIGNATURES = {
     "ttdg_wgrad_tc_supported": (c_int, [c_int, c_int, c_int]),
     "ttdg_wgrad_tc": (c_int, [P, P] + [c_int] * 10 + [P, P]),
     "ttdg_tf32_split": (c_int, [P, P, P, c_int64, P]),
+    "ttdg_conv_tc_bf16": (c_int, [P, P, P, P, P] + [c_int] * 16 + [P, c_int, P]),
+    "ttdg_weight_transpose_bf16": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "ttdg_stem_tc2": (c_int, [P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, P, c_int, P]),
+    "ttdg_maxpool3x3s2_bf16": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
+    "ttdg_relu_bn_bwd_bf16y": (c_int, [P, P, P, c_int, c_int64, P, P]),
     "ttdg_weight_transpose_split": (c_int, [P, c_int, c_int, c_int, P, P, P]),
     "ttdg_rpn_decode": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_float, c_float, P, P, P]),
     "ttdg_box_predict": (c_int, [P, c_int, P, c_int, P, c_int, c_int, c_float, c_float, c_float, P, P, P]),

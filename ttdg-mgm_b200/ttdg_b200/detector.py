@@ -40,7 +40,12 @@ TC_STRIDE2 = [os.environ.get("TTDG_TC_STRIDE2", "1") == "1"]   # 1x1 stride-2 co
 
 
 def set_conv_mode(mode):
-    assert mode in ("simt", "tf32x3", "tf32")
+    """"bf16" = BASELINE.json configs[2]: the BACKBONE (stem output, res2-res5, FPN laterals) keeps bf16 activations in HBM
+    and runs tcgen05.mma.kind::f16 from bf16 copies of the fp32 master weights; the FPN output convolutions write the fp32
+    pyramid (node features of the matching stage, RoIAlign input); the heads cast their inputs to bf16 once and run kind::f16
+    too (predictors write fp32); the backward runs single-pass TF32 on fp32 gradients; the matching stage is unchanged
+    (fp32 / fp64)."""
+    assert mode in ("simt", "tf32x3", "tf32", "bf16")
     CONV_MODE[0] = mode
 
 
@@ -75,6 +80,22 @@ def _weights_kmajor(w, transposed, precise, owner=None):
     return hi, lo
 
 
+def _weights_bf16(w, owner):
+    """[taps][Cout][Cin] bf16 K-major copy of a [R][S][Cin][Cout] fp32 master parameter (cached like _weights_kmajor)."""
+    stamp = (PARAM_EPOCH[0], w._version, w.data_ptr())
+    cache = owner.__dict__.setdefault("_wk_cache", {}) if owner is not None else None
+    if cache is not None:
+        hit = cache.get("bf16")
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
+    R, S, Cin, Cout = w.shape
+    wt = torch.empty(R * S, Cout, Cin, dtype=torch.bfloat16, device=w.device)
+    check(_C.lib().ttdg_weight_transpose_bf16(_p(w), R * S, Cin, Cout, _p(wt), _stream()), "weight_transpose_bf16")
+    if cache is not None:
+        cache["bf16"] = (stamp, wt)
+    return wt
+
+
 def _tc_ok(Cin, Cout, stride, R=1, pad=0):
     """Tensor-core kernel coverage: stride 1, or the strided 1x1 convs (TMA element strides)."""
     if CONV_MODE[0] == "simt" or Cin % 32 or Cout % 64:
@@ -83,11 +104,22 @@ def _tc_ok(Cin, Cout, stride, R=1, pad=0):
 
 
 # ---------------------------------------------------------------------------------------------- raw op wrappers
-def conv_forward(x, w, scale, bias, residual, res_mode, relu, R, S, stride, pad, out=None, owner=None):
-    """x: N x H x W x Cin (NHWC contiguous) -> N x Ho x Wo x Cout."""
+def conv_forward(x, w, scale, bias, residual, res_mode, relu, R, S, stride, pad, out=None, owner=None, out_bf16=None):
+    """x: N x H x W x Cin (NHWC contiguous, fp32 - or bf16 inside the bf16 backbone) -> N x Ho x Wo x Cout (bf16 when
+    out_bf16; default: the input's dtype)."""
     N, H, W, Cin = x.shape
     Cout = w.shape[-1]
     Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+    if x.dtype == torch.bfloat16:
+        if not (_tc_ok(Cin, Cout, stride, R, pad) and Cin % 64 == 0):
+            raise _C.TTDGError(f"no bf16 kernel for this layer (Cin {Cin}, Cout {Cout}, stride {stride}, k {R})")
+        out_bf16 = True if out_bf16 is None else out_bf16
+        y = torch.empty(N, Ho, Wo, Cout, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device) if out is None else out
+        res_bf16 = residual is not None and residual.dtype == torch.bfloat16
+        check(_C.lib().ttdg_conv_tc_bf16(_p(x), _p(_weights_bf16(w, owner)), _p(scale), _p(bias), _p(residual), int(res_bf16),
+                                         int(res_mode), int(relu), 0, N, H, W, Cin, Cout, R, S, pad, stride, 1, 0, 0, _p(y),
+                                         int(y.dtype == torch.bfloat16), _stream()), "conv_tc_bf16")
+        return y
     y = torch.empty(N, Ho, Wo, Cout, dtype=torch.float32, device=x.device) if out is None else out
     if _tc_ok(Cin, Cout, stride, R, pad):
         precise = CONV_MODE[0] == "tf32x3"
@@ -104,12 +136,13 @@ class _ConvFn(torch.autograd.Function):
     """y = relu?(conv(x, w) * scale + bias + residual) with the gradients the TTT loss needs."""
 
     @staticmethod
-    def forward(ctx, x, w, bias_param, residual, scale, bias_const, res_mode, relu, R, S, stride, pad, owner):
+    def forward(ctx, x, w, bias_param, residual, scale, bias_const, res_mode, relu, R, S, stride, pad, owner, out_bf16=None):
         bias = bias_param if bias_param is not None else bias_const
-        y = conv_forward(x, w, scale, bias, residual, res_mode, relu, R, S, stride, pad, owner=owner)
+        y = conv_forward(x, w, scale, bias, residual, res_mode, relu, R, S, stride, pad, owner=owner, out_bf16=out_bf16)
         ctx.owner = owner
         ctx.save_for_backward(x, w, y if relu else None, scale)
         ctx.meta = (res_mode, relu, R, S, stride, pad, bias_param is not None, residual is not None and residual.requires_grad)
+        ctx.res_dtype = residual.dtype if residual is not None else None
         return y
 
     @staticmethod
@@ -119,11 +152,18 @@ class _ConvFn(torch.autograd.Function):
         res_mode, relu, R, S, stride, pad, has_bias, res_grad = ctx.meta
         N, H, W, Cin = x.shape
         Cout = w.shape[-1]
-        g = g.contiguous()
+        # bf16 backbone: the backward works on fp32 copies with the single-pass TF32 kernels (activations were saved in bf16:
+        # the ReLU mask reads them directly, the weight gradient needs them widened); gradients leave in the dtype autograd
+        # expects for each input
+        x_dtype = x.dtype
+        g = g.float().contiguous() if g.dtype != torch.float32 else g.contiguous()
         s = _stream()
         if relu:                                           # dPre = g * [y > 0]
             d_pre = torch.empty_like(g)
-            check(L.ttdg_relu_bn_bwd(_p(g), _p(y), None, Cout, g.numel(), _p(d_pre), s), "relu_bwd")
+            if y.dtype == torch.bfloat16:
+                check(L.ttdg_relu_bn_bwd_bf16y(_p(g), _p(y), None, Cout, g.numel(), _p(d_pre), s), "relu_bwd_bf16y")
+            else:
+                check(L.ttdg_relu_bn_bwd(_p(g), _p(y), None, Cout, g.numel(), _p(d_pre), s), "relu_bwd")
         else:
             d_pre = g
         g_res = None
@@ -134,6 +174,8 @@ class _ConvFn(torch.autograd.Function):
                 Ho, Wo = g.shape[1], g.shape[2]
                 g_res = torch.zeros(N, Ho // 2, Wo // 2, Cout, dtype=torch.float32, device=g.device)
                 check(L.ttdg_resample2(_p(d_pre), _p(g_res), N, Ho // 2, Wo // 2, Cout, 2, s), "upsample_bwd")
+            if ctx.res_dtype != torch.float32:
+                g_res = g_res.to(ctx.res_dtype)
         # Weight / bias gradients are ACCUMULATED by their kernels (atomics), so when the parameter already owns a gradient
         # buffer - the views of FlatSGD's flat bucket, zeroed by zero_grad() - they add straight into it and autograd gets
         # None: no zero-filled temporary and no separate "grad += temporary" pass per parameter (132 launches per step).
@@ -162,7 +204,11 @@ class _ConvFn(torch.autograd.Function):
                                      Cin, R, S, R - 1 - pad, 1, stride, H, W, _p(g_x), s), "conv_tc_dgrad")
             else:
                 check(L.ttdg_conv_dgrad(_p(d_conv), _p(w), N, H, W, Cin, Cout, R, S, stride, pad, _p(g_x), s), "conv_dgrad")
+        if g_x is not None and x_dtype != torch.float32:
+            g_x = g_x.to(x_dtype)
         if ctx.needs_input_grad[1]:
+            if x_dtype != torch.float32:
+                x = x.float()
             acc_w = _acc(owner.weight if owner is not None else None)
             if acc_w is not None and acc_w.shape != w.shape:
                 acc_w = None
@@ -173,7 +219,7 @@ class _ConvFn(torch.autograd.Function):
             else:
                 check(L.ttdg_conv_wgrad(_p(x), _p(d_conv), N, H, W, Cin, Cout, R, S, stride, pad, _p(gw), s), "conv_wgrad")
             g_w = None if acc_w is not None else gw
-        return g_x, g_w, g_bias, g_res, None, None, None, None, None, None, None, None, None
+        return g_x, g_w, g_bias, g_res, None, None, None, None, None, None, None, None, None, None
 
 
 class FrozenBN(nn.Module):
@@ -276,17 +322,18 @@ class Conv2d(nn.Module):
         self.fold_scale = torch.nn.functional.pad(scale, (0, self.cout_p - self.cout)).contiguous()
         self.fold_bias = torch.nn.functional.pad(bias, (0, self.cout_p - self.cout)).contiguous()
 
-    def forward(self, x, relu=False, residual=None, res_mode=0):
+    def forward(self, x, relu=False, residual=None, res_mode=0, out_bf16=None):
         if self.norm is not None and self.fold_scale is None:
             self.fold()
         scale = self.fold_scale if self.norm is not None else None
         bias_const = self.fold_bias if self.norm is not None else None
         k = 1 if self.kind != "conv" else self.k
         if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
-            return _ConvFn.apply(x, self.weight, self.bias, residual, scale, bias_const, res_mode, relu, k, k, self.stride, self.pad, self)
+            return _ConvFn.apply(x, self.weight, self.bias, residual, scale, bias_const, res_mode, relu, k, k, self.stride, self.pad, self,
+                                 out_bf16)
         bias = self.bias if self.bias is not None else bias_const
         return conv_forward(x, self.weight, scale, None if bias is None else bias.detach(), residual, res_mode, relu, k, k,
-                            self.stride, self.pad, owner=self)
+                            self.stride, self.pad, owner=self, out_bf16=out_bf16)
 
 
 class Bottleneck(nn.Module):
@@ -337,8 +384,10 @@ class Stem(nn.Module):
             c.fold()
         N, H, Wp, _ = x.shape
         hi, lo = self._weights_tc(CONV_MODE[0] == "tf32x3")
-        y = torch.empty(N, H // 2, width // 2, 64, dtype=torch.float32, device=x.device)
-        check(_C.lib().ttdg_stem_tc(_p(x), Wp, _p(hi), _p(lo), _p(c.fold_scale), _p(c.fold_bias), 1, N, H, width, _p(y), _stream()), "stem_tc")
+        bf16 = CONV_MODE[0] == "bf16"                      # the image is fp32 (3 channels); the first ACTIVATION is bf16
+        y = torch.empty(N, H // 2, width // 2, 64, dtype=torch.bfloat16 if bf16 else torch.float32, device=x.device)
+        check(_C.lib().ttdg_stem_tc2(_p(x), Wp, _p(hi), _p(lo), _p(c.fold_scale), _p(c.fold_bias), 1, N, H, width, _p(y), int(bf16),
+                                     _stream()), "stem_tc")
         return y
 
 
@@ -359,8 +408,11 @@ class ResNet50(nn.Module):
         with torch.no_grad():                                   # FREEZE_AT = 2: stem + res2
             y = self.stem(x, width)
             N, H, W, C = y.shape
-            p = torch.empty(N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C, dtype=torch.float32, device=y.device)
-            check(L.ttdg_maxpool3x3s2(_p(y), N, H, W, C, _p(p), _stream()), "maxpool")
+            p = torch.empty(N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C, dtype=y.dtype, device=y.device)
+            if y.dtype == torch.bfloat16:
+                check(L.ttdg_maxpool3x3s2_bf16(_p(y), N, H, W, C, _p(p), _stream()), "maxpool_bf16")
+            else:
+                check(L.ttdg_maxpool3x3s2(_p(y), N, H, W, C, _p(p), _stream()), "maxpool")
             y = self.res2(p)
         out = {"res2": y}
         for name in ("res3", "res4", "res5"):
@@ -410,7 +462,7 @@ class Backbone(nn.Module):
         for lvl in (5, 4, 3, 2):
             lat = getattr(self, f"fpn_lateral{lvl}")
             prev = lat(res[f"res{lvl}"]) if prev is None else lat(res[f"res{lvl}"], residual=prev, res_mode=2)
-            outs[lvl] = getattr(self, f"fpn_output{lvl}")(prev)
+            outs[lvl] = getattr(self, f"fpn_output{lvl}")(prev, out_bf16=False)      # the pyramid is fp32 in every mode
         return [outs[2], outs[3], outs[4], outs[5], _Subsample2.apply(outs[5])]
 
     def forward(self, x, width=None):
@@ -505,9 +557,11 @@ class RPN(nn.Module):
         for l, f in enumerate(feats):
             f = f.detach()
             _, H, W, _ = f.shape
+            if CONV_MODE[0] == "bf16":                                  # configs[2]: the heads' GEMMs run kind::f16 as well
+                f = f.to(torch.bfloat16)
             t = self.rpn_head.conv(f, relu=True)
-            logits = self.rpn_head.objectness_logits(t)                 # N x H x W x 16 (15 used)
-            deltas = self.rpn_head.anchor_deltas(t)                     # N x H x W x 60
+            logits = self.rpn_head.objectness_logits(t, out_bf16=False)     # N x H x W x 64 (15 used), fp32 for the decode kernels
+            deltas = self.rpn_head.anchor_deltas(t, out_bf16=False)         # N x H x W x 64 (60 used)
             flat = logits[..., :A].reshape(N, H * W * A)
             k = min(flat.shape[1], pre_topk)
             sc, idx = torch.topk(flat, k, dim=1, sorted=True)           # ordering only (plumbing)
@@ -612,10 +666,12 @@ class ROIHeads(nn.Module):
         rois = _rois(props)
         R = rois.shape[0]
         x = roi_align(feats4, rois, 7).reshape(R, 1, 1, 7 * 7 * 256)
+        if CONV_MODE[0] == "bf16":
+            x = x.to(torch.bfloat16)
         x = self.box_head.fc1(x, relu=True)
         x = self.box_head.fc2(x, relu=True)
-        cls = self.box_predictor.cls_score(x).reshape(R, -1)
-        reg = self.box_predictor.bbox_pred(x).reshape(R, -1)
+        cls = self.box_predictor.cls_score(x, out_bf16=False).reshape(R, -1)
+        reg = self.box_predictor.bbox_pred(x, out_bf16=False).reshape(R, -1)
         pb = torch.cat(props).contiguous()
         cand_b = torch.empty(R * K, 4, dtype=torch.float32, device=dev)
         cand_s = torch.empty(R * K, dtype=torch.float32, device=dev)
@@ -672,9 +728,11 @@ class ROIHeads(nn.Module):
         if R == 0:
             return None
         x = roi_align(feats4, _rois(boxes), 14)
+        if CONV_MODE[0] == "bf16":
+            x = x.to(torch.bfloat16)
         for i in range(1, 5):
             x = getattr(self.mask_head, f"mask_fcn{i}")(x, relu=True)
-        y4 = self.mask_head.deconv(x, relu=True)                     # R x 14 x 14 x (4 * 256)
+        y4 = self.mask_head.deconv(x, relu=True, out_bf16=False)     # R x 14 x 14 x (4 * 256), fp32 for the shuffle / predictor
         y = torch.empty(R, 28, 28, 256, dtype=torch.float32, device=y4.device)
         check(L.ttdg_pixel_shuffle2(_p(y4), R, 14, 14, 256, _p(y), _stream()), "pixel_shuffle")
         return self.mask_head.predictor(y)                           # R x 28 x 28 x 64 (K used)
