@@ -288,6 +288,11 @@ int ttdg_stem_tc(const float *x_pad, int Wp, const float *wk_hi, const float *wk
 int ttdg_tf32_split(const float *x, float *hi, float *lo, int64_t numel, void *stream);
 /* w [taps][Cin][Cout] -> wt_hi, wt_lo (may be NULL) [taps][Cout][Cin] */
 int ttdg_weight_transpose_split(const float *w, int taps, int Cin, int Cout, float *wt_hi, float *wt_lo, void *stream);
+/* All tensor-core weight copies of the adapted convolutions in ONE launch after an optimizer step (instead of one small launch
+ * per layer and variant on first use).  jobs_dev: device int64[njobs][8] = { src, dst_hi, dst_lo (0 = none), taps, Cin, Cout,
+ * mode, first_tile } with mode 0 = K-major transposed tf32 hi / lo (forward), 1 = same-layout hi / lo (data gradient),
+ * 2 = K-major transposed bf16 into dst_hi; tiles are 32 x 32 per tap, first_tile ascending, total_tiles their sum. */
+int ttdg_weight_refresh(const int64_t *jobs_dev, int njobs, int64_t total_tiles, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * bf16 backbone (BASELINE.json configs[2]: "bf16 backbone / fp32 Sinkhorn").  Replaces the same Detectron2 ResNet-50-FPN
@@ -326,6 +331,33 @@ int ttdg_box_predict(const float *cls, int ld_cls, const float *reg, int ld_reg,
 int64_t ttdg_nms_scratch_bytes(int batch, int n);
 int ttdg_nms(const float *boxes_sorted, const int32_t *category, int batch, int n, float iou_thresh, int max_keep,
              int32_t *keep, int32_t *n_keep, void *scratch, void *stream);
+/* ---------------------------------------------------------------------------------------------
+ * Device-side candidate selection (no host round trip between the RPN head and the box head).  Replaces Detectron2
+ * `find_top_rpn_proposals` (proposal_generator/rpn.py:52-54 -> predict_proposals) and the candidate ordering of
+ * `fast_rcnn_inference_single_image` (roi_heads/roi_heads.py:173-205), which the reference runs as torch sort / top-k /
+ * boolean indexing with data-dependent shapes.
+ * ttdg_rpn_select: per (image, level) radix-select top-k of the H*W*A objectness logits, sorted descending (ties: lower anchor
+ *   index first), anchors decoded (Box2BoxTransform weights 1, clamp log(1000/16)), clipped to the image's own size.
+ *   logits_h / deltas_h: HOST arrays of n_levels device pointers (N x H x W x ld, channel a resp. 4a + c); lvl_hw_h {H, W} per
+ *   level, k_h[l] = min(H*W*A, pre_nms_topk) <= 2048; img_hw_h {h, w} per image.  Outputs [n_img][sum k]: boxes, scores, valid
+ *   (finite and non-empty), level l occupying [off_l, off_l + k_l).
+ * ttdg_sort_candidates: per image, candidates ordered by (valid, score descending, position ascending); category for ttdg_nms =
+ *   cats_in[position] (cat_mod == 0) or position % cat_mod, invalid -> unique negative; valid == NULL means score > 0.
+ * ttdg_gather_kept: the kept (ttdg_nms) valid candidates padded to max_keep rows + per-image counts (device).
+ * ttdg_rois_from_padded / ttdg_mask_padded_candidates: padded proposals -> RoIAlign rois; candidates of padding rows -> -1.
+ * --------------------------------------------------------------------------------------------- */
+int ttdg_rpn_select(const void *const *logits_h, const void *const *deltas_h, const int32_t *lvl_hw_h, const int32_t *strides_h,
+                    const int32_t *k_h, int n_levels, int ld_logits, int ld_deltas, int A, const float *cell_anchors_h, int n_img,
+                    const float *img_hw_h, float *boxes, float *scores, unsigned char *valid, void *stream);
+int ttdg_sort_candidates(const float *boxes, const float *scores, const unsigned char *valid, const int32_t *cats_in, int cat_mod,
+                         int n_img, int n, float invalid_score, float *boxes_out, float *scores_out, int32_t *cats_out,
+                         int32_t *n_valid, void *stream);
+int ttdg_gather_kept(const float *boxes, const float *scores, const int32_t *cats, const int32_t *keep, const int32_t *n_keep,
+                     const int32_t *n_valid, int n_img, int n, int max_keep, float pad_score, float *boxes_out, float *scores_out,
+                     int64_t *cats_out, int32_t *counts, void *stream);
+int ttdg_rois_from_padded(const float *boxes, const int32_t *counts, int n_img, int P, float *rois, void *stream);
+int ttdg_mask_padded_candidates(float *cand_scores, const int32_t *counts, int n_img, int P, int K, void *stream);
+
 /* ROIPooler + ROIAlignV2 (aligned, sampling_ratio 0) over p2..p5: rois [n][5] = {image, x0, y0, x1, y1};
  * out [n][pooled][pooled][C].  feat_ptrs_h = HOST array of 4 device pointers, lvl_hw_h = HOST int32[4][2]. */
 int ttdg_roi_align(const float *const *feat_ptrs_h, const int32_t *lvl_hw_h, const float *rois, int n_rois, int C,

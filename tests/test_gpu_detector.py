@@ -319,3 +319,121 @@ def test_nms_vs_torchvision():
         keep, nk = det.nms_sorted(boxes[order].cuda().contiguous(), cats[order].int().cuda().contiguous(), 0.5, n)
         got = order[keep[:int(nk[0])].long().cpu()]
         assert torch.equal(got, ref)
+
+
+def _rpn_select_torch(rpn, logits_l, deltas_l, sizes, pre_topk):
+    """The round-1 torch formulation (topk / argsort / gather) of find_top_rpn_proposals, as the reference for csrc/select.cu."""
+    import ctypes
+    from ttdg_b200 import _C
+    from ttdg_b200.ops import _p, _stream
+    L = _C.lib()
+    A = rpn._cell.shape[0]
+    N = logits_l[0].shape[0]
+    dev = logits_l[0].device
+    cell_h = (ctypes.c_float * (A * 4))(*rpn._cell.reshape(-1).tolist())
+    boxes_l, scores_l, valid_l, lvl_l = [], [], [], []
+    for l, (logits, deltas) in enumerate(zip(logits_l, deltas_l)):
+        _, H, W, _ = logits.shape
+        flat = logits[..., :A].reshape(N, H * W * A)
+        k = min(flat.shape[1], pre_topk)
+        sc, idx = torch.topk(flat, k, dim=1, sorted=True)
+        boxes = torch.empty(N, k, 4, dtype=torch.float32, device=dev)
+        valid = torch.empty(N, k, dtype=torch.uint8, device=dev)
+        for n in range(N):
+            det.check(L.ttdg_rpn_decode(_p(deltas[n]), deltas.shape[-1], _p(idx[n].contiguous()), 1, k, H, W, A, det.STRIDES[l],
+                                        ctypes.cast(cell_h, ctypes.c_void_p), float(sizes[n][0]), float(sizes[n][1]), _p(boxes[n]),
+                                        _p(valid[n]), _stream()), "rpn_decode")
+        boxes_l.append(boxes); scores_l.append(sc); valid_l.append(valid)
+        lvl_l.append(torch.full((k,), l, dtype=torch.int32, device=dev))
+    boxes, scores, valid, lvl = torch.cat(boxes_l, 1), torch.cat(scores_l, 1), torch.cat(valid_l, 1).bool(), torch.cat(lvl_l)
+    key = torch.where(valid & torch.isfinite(scores), scores, torch.full_like(scores, -float("inf")))
+    order = torch.argsort(key, dim=1, descending=True, stable=True)
+    n_valid = (key > -float("inf")).sum(1)
+    out = []
+    for n in range(N):
+        o = order[n, :int(n_valid[n])]
+        b, s_, lv = boxes[n][o], scores[n][o], lvl[o]
+        keep = tvo_batched_nms(b, s_, lv, rpn.nms_thresh)[:rpn.post_topk]
+        out.append((b[keep], s_[keep]))
+    return out
+
+
+def tvo_batched_nms(b, s, c, t):
+    import torchvision.ops as tvo
+    return tvo.batched_nms(b.cpu(), s.cpu(), c.cpu().long(), t).to(b.device)
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_rpn_device_side_selection_vs_torch(model_and_sd, training):
+    """csrc/select.cu (radix-select top-k + sort + decode, cross-level ordering, compaction; no host round trip) against the
+    torch.topk / argsort / torchvision batched_nms formulation on random head outputs, mixed image sizes included."""
+    m, _ = model_and_sd
+    rpn = m.proposal_generator
+    g = torch.Generator().manual_seed(11)
+    N, S = 3, 256
+    sizes = [(256, 256), (200, 256), (256, 180)]
+    # distinct logits over ALL levels (one permutation): the order of EQUAL scores is unspecified in torch.topk / batched_nms,
+    # csrc/select.cu takes the lower index (see test_rpn_topk_ties_take_the_lowest_indices)
+    shapes = [(N, S // s, S // s, 64) for s in det.STRIDES]
+    tot = sum(a * b * c * d for a, b, c, d in shapes)
+    perm = (torch.randperm(tot, generator=g).float() / tot - 0.5) * 8
+    logits_l, o = [], 0
+    for sh in shapes:
+        n_el = sh[0] * sh[1] * sh[2] * sh[3]
+        logits_l.append(perm[o:o + n_el].reshape(sh).cuda())
+        o += n_el
+    deltas_l = [(torch.randn(N, S // s, S // s, 64, generator=g) * 0.5).cuda() for s in det.STRIDES]
+    deltas_l[1][0, 3, 3, 0] = float("nan")                                 # a non-finite box must be dropped, not crash
+    ref = _rpn_select_torch(rpn, logits_l, deltas_l, sizes, 2000 if training else 1000)
+    # feed the same head outputs through the device-side path (bypassing the head convolutions)
+    import ctypes
+    from ttdg_b200 import _C
+    from ttdg_b200.ops import _p, _stream
+    A = rpn._cell.shape[0]
+    ks = [min(t.shape[1] * t.shape[2] * A, 2000 if training else 1000) for t in logits_l]
+    Kt = sum(ks)
+    boxes = torch.empty(N, Kt, 4, device="cuda"); scores = torch.empty(N, Kt, device="cuda"); valid = torch.empty(N, Kt, dtype=torch.uint8, device="cuda")
+    vp = lambda ts: ctypes.cast((ctypes.c_void_p * 5)(*[t.data_ptr() for t in ts]), ctypes.c_void_p)
+    ip = lambda vs: ctypes.cast((ctypes.c_int32 * len(vs))(*vs), ctypes.c_void_p)
+    fp = lambda vs: ctypes.cast((ctypes.c_float * len(vs))(*vs), ctypes.c_void_p)
+    det.check(_C.lib().ttdg_rpn_select(vp(logits_l), vp(deltas_l), ip([v for t in logits_l for v in t.shape[1:3]]), ip(list(det.STRIDES)), ip(ks),
+                                       5, 64, 64, A, fp(rpn._cell.reshape(-1).tolist()), N, fp([float(v) for s_ in sizes for v in s_]),
+                                       _p(boxes), _p(scores), _p(valid), _stream()), "rpn_select")
+    lvl = torch.cat([torch.full((k,), l, dtype=torch.int32) for l, k in enumerate(ks)]).cuda()
+    bs, ss, cats, nv = det.sort_candidates(boxes, scores, valid, lvl, 0, -float("inf"))
+    keep, nk = det.nms_sorted(bs, cats, rpn.nms_thresh, rpn.post_topk)
+    ob, os_, _, counts = det.gather_kept(bs, ss, cats, keep, nk, nv, rpn.post_topk, -float("inf"), False)
+    for n in range(N):
+        c = int(counts[n])
+        assert c == len(ref[n][0])
+        assert torch.equal(os_[n, :c], ref[n][1]) and torch.equal(ob[n, :c], ref[n][0])
+        assert bool(torch.isinf(os_[n, c:]).all())
+
+
+def test_rpn_topk_ties_take_the_lowest_indices():
+    """More candidates tied at the k-th value than slots left: the selection is deterministic (lowest anchor index first)."""
+    import ctypes
+    from ttdg_b200 import _C
+    from ttdg_b200.ops import _p, _stream
+    H = W = 16
+    A = 15
+    logits = torch.zeros(1, H, W, 64).cuda()
+    logits[0, 2, 3, 4] = 5.0                                               # one clear winner, the other 3839 tie at 0
+    deltas = torch.zeros(1, H, W, 64).cuda()
+    k = 100
+    boxes = torch.empty(1, k, 4, device="cuda"); scores = torch.empty(1, k, device="cuda"); valid = torch.empty(1, k, dtype=torch.uint8, device="cuda")
+    cell = det.cell_anchors()
+    one = lambda t: ctypes.cast((ctypes.c_void_p * 1)(t.data_ptr()), ctypes.c_void_p)
+    ip = lambda vs: ctypes.cast((ctypes.c_int32 * len(vs))(*vs), ctypes.c_void_p)
+    fp = lambda vs: ctypes.cast((ctypes.c_float * len(vs))(*vs), ctypes.c_void_p)
+    det.check(_C.lib().ttdg_rpn_select(one(logits), one(deltas), ip([H, W]), ip([4]), ip([k]), 1, 64, 64, A, fp(cell.reshape(-1).tolist()), 1,
+                                       fp([64.0, 64.0]), _p(boxes), _p(scores), _p(valid), _stream()), "rpn_select")
+    assert float(scores[0, 0]) == 5.0 and bool((scores[0, 1:] == 0).all())
+    # anchor index -> decoded box with zero deltas = the anchor itself (clipped): entries 1.. are anchors 0, 1, 2, ... in order
+    flat_idx = [(2 * W + 3) * A + 4] + [i for i in range(k + 1) if i != (2 * W + 3) * A + 4][:k - 1]
+    for j, idx in enumerate(flat_idx[:20]):
+        pix, a = divmod(idx, A)
+        y, x = divmod(pix, W)
+        anc = cell[a] + torch.tensor([x * 4.0, y * 4.0, x * 4.0, y * 4.0])
+        want = torch.stack((anc[0].clamp(0, 64), anc[1].clamp(0, 64), anc[2].clamp(0, 64), anc[3].clamp(0, 64)))
+        assert torch.allclose(boxes[0, j].cpu(), want, atol=1e-5), (j, idx)

@@ -220,11 +220,12 @@ def test_hippi_matches_reference(golden_dir):
     assert h.last_iterations <= 50 and float(U.sum()) == float(sum(ms.tolist()))
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
 @pytest.mark.parametrize("sizes,seed", [((33, 34, 33, 33, 46, 30, 34, 38), 77), ((46, 33, 22, 41, 33, 32, 33, 34), 21), ((60,) * 8, 16), ((23, 40, 31, 57), 3), ((30, 30, 30, 30, 30), 5), ((12, 20), 9)])
 def test_certified_fast_lap_gives_the_same_solution(sizes, seed, mode):
     """Certified fast paths of the Hungarian projections (1: row-reduction start, 2: Jacobi-auction start, 3 - the default -
-    the lean solve: three auction rounds + Dijkstra without SciPy's bookkeeping; each followed by the optimality / uniqueness
+    the lean solve: auction rounds + Dijkstra without SciPy's bookkeeping, 4: the same with label-correcting rounds instead of
+    Dijkstra; each followed by the optimality / uniqueness
     certificate and the SciPy-order solve as the fall-back, lap.cuh): the whole GA-GM solve -
     every projection of ~200 iterations - must give the same U and the same iteration counts as the SciPy-order solver."""
     from ttdg_b200 import _C

@@ -184,7 +184,7 @@ elif what == "gagm_fixed":
             m([n.to(dev) for n in nodes], [l.to(dev) for l in labels], U)
         aux = m.last_aux
         from ttdg_b200 import _C
-        for mode in (0, 2, 3):
+        for mode in (0, 3, 4):
             prev = _C.lib().ttdg_gagm_set_lap_fast(mode)
             ms = 0.0
             for _ in range(reps + 1):
@@ -198,6 +198,36 @@ elif what == "gagm_fixed":
             inf = info.tolist()
             print("gagm_fixed lap_fast %d sizes %s: %.3f ms, iterations %d (sinkhorn %d, hungarian %d), %.1f us / hungarian iteration incl. everything, graph-0 LAP steps %d, fast-path fall-backs %d; CTA-0 kcycles: kernel %d, hungarian stage %d, in LAP %d, barrier wait %d"
                   % (mode, sizes, ms, inf[0], inf[1], inf[2], 1e3 * ms / max(inf[2], 1), inf[5], inf[7], inf[8], inf[9], inf[10], inf[11]))
+elif what == "gagm_bench":
+    # the GA-GM solver on the BENCH workload's own problems: run the bench step a few times (the weights drift), then time the
+    # solver alone on the step's (A, Wds, U0) under every LAP mode
+    sys.path.insert(0, ROOT)
+    import bench
+    from ttdg_b200 import _C
+    m, opt = bench.build_ours(dev)
+    inputs = [dict(d, image=d["image"].to(dev)) for d in bench.make_inputs(0)]
+    for step_i in range(16):
+        m.train()
+        loss, _, _, _ = m(inputs, branch="TTT")
+        opt.zero_grad(); loss.backward(); opt.step(1)
+        if step_i in (3, 9, 15):
+            aux = m.multi_matching_unsup.last_aux
+            sizes = list(aux["sizes"])
+            for mode in (0, 3, 4):
+                prev = _C.lib().ttdg_gagm_set_lap_fast(mode)
+                ms = 0.0
+                for r in range(reps + 1):
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    U2, info = ops.gagm_solve(aux["A"], aux["Wds"], aux["U0"], sizes, return_info=True)
+                    e1.record(); torch.cuda.synchronize()
+                    if r > 0:
+                        ms += e0.elapsed_time(e1) / reps
+                _C.lib().ttdg_gagm_set_lap_fast(prev)
+                inf = info.tolist()
+                print("gagm_bench step %d lap_fast %d sizes %s: %.3f ms, iterations %d (sinkhorn %d, hungarian %d), graph-0 LAP steps %d, fall-backs %d; "
+                      "CTA-0 kcycles: kernel %d, hungarian stage %d, in LAP %d, barrier wait %d" %
+                      (step_i, mode, sizes, ms, inf[0], inf[1], inf[2], inf[5], inf[7], inf[8], inf[9], inf[10], inf[11]))
 elif what == "busy":
     # hot (not cold-cache) per-kernel device time of the full step and the GPU-busy fraction, from CUPTI via torch.profiler
     sys.path.insert(0, ROOT)

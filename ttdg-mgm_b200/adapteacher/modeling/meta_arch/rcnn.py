@@ -77,8 +77,17 @@ class DAobjTwoStagePseudoLabGeneralizedRCNN(nn.Module):
         return self
 
     def adapted_parameters(self):
-        """Everything that receives a gradient in the TTT step: res3-res5, FPN and the affinity layer."""
-        return self._det[0].adapted_parameters() + list(self.multi_matching_unsup.node_affinity.parameters())
+        """Everything that receives a gradient in the TTT step: res3-res5, FPN and the affinity layer, in the order
+        the backward pass completes the gradients."""
+        return [p for g in self.adapted_parameter_groups() for p in g]
+
+    def adapted_parameter_groups(self):
+        """Gradient buckets for FlatSGD(buckets=[len(g) for g in groups]): [affinity + FPN + res5, res4, res3]."""
+        g = self._det[0].adapted_parameter_groups()
+        return [list(self.multi_matching_unsup.node_affinity.parameters()) + g[0], g[1], g[2]]
+
+    def refresh_weight_copies(self):
+        self._det[0].refresh_weight_copies()
 
     def preprocess_image(self, batched_inputs):
         """rcnn.py:219 -> d2 preprocess_image: normalise, pad to a common size divisible by 32, keep every image's own size."""
@@ -95,7 +104,7 @@ class DAobjTwoStagePseudoLabGeneralizedRCNN(nn.Module):
         proposals_rpn, _ = self.proposal_generator(images, features, None, compute_loss=False)              # rcnn.py:333-335
         proposals_roih, ROI_predictions = self.roi_heads(images, features, proposals_rpn, targets=None,
                                                          compute_loss=False, branch=branch)                 # rcnn.py:338-345
-        self.last_ttt = {"proposals": [(p.proposal_boxes.tensor, p.objectness_logits) for p in proposals_rpn],
+        self.last_ttt = {"proposals": proposals_rpn,
                          "detections": [(p.pred_boxes.tensor, p.scores, p.pred_classes) for p in proposals_roih]}   # parity tests
         features = [feat[1] for feat in features.items()]   # rcnn.py:351
         nodes, labels = self.graph_generator(features, proposals_roih)      # rcnn.py:352

@@ -17,6 +17,13 @@ class PseudoLabRPN(RPN):
         if (self.training and compute_loss) or compute_val_loss:        # rpn.py:43-48
             raise NotImplementedError("RPN training losses are outside the test-time path (call with compute_loss=False)")
         feats = [_nhwc(features[f]) for f in self.in_features]
-        out = self.predict(feats, images.image_sizes, self.training)     # rpn.py:52-54 predict_proposals
-        proposals = [Instances(size, proposal_boxes=Boxes(b), objectness_logits=s) for (b, s), size in zip(out, images.image_sizes)]
+        boxes, logits, counts = self.predict_padded(feats, images.image_sizes, self.training)    # rpn.py:52-54 predict_proposals
+        # Device-side selection keeps every image's proposals PADDED to POST_NMS_TOPK rows (padding: zero box, logit -inf) with
+        # the real count on the device, so that no host round trip separates the RPN from the ROI heads; the padded batch rides
+        # along for StandardROIHeadsPseudoLab (``num_valid()`` reads the count back if a caller needs it).
+        proposals = []
+        for n, size in enumerate(images.image_sizes):
+            inst = Instances(size, proposal_boxes=Boxes(boxes[n]), objectness_logits=logits[n])
+            inst._padded = (boxes, logits, counts, n)
+            proposals.append(inst)
         return proposals, {}

@@ -22,7 +22,14 @@ class StandardROIHeadsPseudoLab(ROIHeads):
         del targets
         feats = [_nhwc(features[f]) for f in self.in_features]
         sizes = [p.image_size for p in proposals]
-        dets = self.forward_box(feats, [(p.proposal_boxes.tensor, p.objectness_logits) for p in proposals], sizes)
+        pad = [getattr(p, "_padded", None) for p in proposals]
+        if all(q is not None and q[0] is pad[0][0] and q[3] == i for i, q in enumerate(pad)) and len(pad) == pad[0][0].shape[0]:
+            # proposals straight from PseudoLabRPN: the padded batch + device-side counts, one host read for the detections
+            b, s, c, counts = self.forward_box_padded(feats, pad[0][0], pad[0][2], sizes)
+            cnt = counts.cpu().tolist()
+            dets = [(b[i, :n], s[i, :n], c[i, :n]) for i, n in enumerate(cnt)]
+        else:
+            dets = self.forward_box(feats, [(p.proposal_boxes.tensor, p.objectness_logits) for p in proposals], sizes)
         pred_instances = [Instances(size, pred_boxes=Boxes(b), scores=s, pred_classes=c) for (b, s, c), size in zip(dets, sizes)]
         if branch == 'TTT':                                              # roi_heads.py:109-110
             return pred_instances, None

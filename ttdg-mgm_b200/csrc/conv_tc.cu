@@ -1090,3 +1090,75 @@ extern "C" int ttdg_weight_transpose_bf16(const float *w, int taps, int Cin, int
         w, Cin, Cout, reinterpret_cast<__nv_bfloat16 *>(wt_bf16));
     TTDG_LAUNCH_RET();
 }
+
+// ---------------------------------------------------------------------------------------------- batched operand refresh
+// After an optimizer step every adapted convolution needs fresh tensor-core copies of its weights: K-major transposed hi / lo
+// (forward), plain hi / lo (data gradient), or transposed bf16 (bf16 backbone).  Done lazily that was ~134 tiny launches per
+// step (86 weight_transpose_split + 48 tf32_split); here ONE launch walks a table of jobs, 32 x 32 tiles each.
+// job (int64 x 8): { src, dst_hi, dst_lo (0 = none), taps, Cin, Cout, mode, first_tile }   mode 0: transposed fp32 hi / lo,
+// 1: same layout hi / lo, 2: transposed bf16 (dst_hi).  first_tile[njobs] = total tiles.
+namespace ttdg {
+__global__ void __launch_bounds__(256)
+weight_refresh_kernel(const int64_t *__restrict__ jobs, int njobs) {
+    __shared__ float tile[32][33];
+    int lo_j = 0, hi_j = njobs - 1;
+    const int64_t b = blockIdx.x;
+    while (lo_j < hi_j) {                                   // the job this tile belongs to (first_tile is ascending)
+        const int mid = (lo_j + hi_j + 1) >> 1;
+        if (jobs[(size_t)mid * 8 + 7] <= b) lo_j = mid; else hi_j = mid - 1;
+    }
+    const int64_t *J = jobs + (size_t)lo_j * 8;
+    const float *w = reinterpret_cast<const float *>(J[0]);
+    const int Cin = (int)J[4], Cout = (int)J[5], mode = (int)J[6];
+    int64_t t = b - J[7];
+    const int tco = (Cout + 31) / 32, tci = (Cin + 31) / 32;
+    const int co0 = (int)(t % tco) * 32; t /= tco;
+    const int ci0 = (int)(t % tci) * 32;
+    const int tap = (int)(t / tci);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (mode == 1) {                                        // same layout: [tap][ci][co]
+        float *hi = reinterpret_cast<float *>(J[1]), *lo = reinterpret_cast<float *>(J[2]);
+        for (int r = ty; r < 32; r += 8) {
+            const int ci = ci0 + r, co = co0 + tx;
+            if (ci < Cin && co < Cout) {
+                const size_t o = ((size_t)tap * Cin + ci) * Cout + co;
+                const float v = w[o];
+                uint32_t u;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+                hi[o] = __uint_as_float(u);
+                if (lo) lo[o] = v - __uint_as_float(u);
+            }
+        }
+        return;
+    }
+    for (int r = ty; r < 32; r += 8) {
+        const int ci = ci0 + r, co = co0 + tx;
+        tile[r][tx] = (ci < Cin && co < Cout) ? w[((size_t)tap * Cin + ci) * Cout + co] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int co = co0 + r, ci = ci0 + tx;
+        if (co < Cout && ci < Cin) {
+            const float v = tile[tx][r];
+            const size_t o = ((size_t)tap * Cout + co) * Cin + ci;
+            if (mode == 2) {
+                reinterpret_cast<__nv_bfloat16 *>(J[1])[o] = __float2bfloat16_rn(v);
+            } else {
+                uint32_t u;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+                reinterpret_cast<float *>(J[1])[o] = __uint_as_float(u);
+                if (J[2]) reinterpret_cast<float *>(J[2])[o] = v - __uint_as_float(u);
+            }
+        }
+    }
+}
+}  // namespace ttdg
+
+extern "C" int ttdg_weight_refresh(const int64_t *jobs_dev, int njobs, int64_t total_tiles, void *stream) {
+    TTDG_CHECK_ARG(jobs_dev && njobs >= 0 && total_tiles >= 0);
+    if (njobs == 0 || total_tiles == 0) return 0;
+    if (total_tiles > 0x7FFFFFFF) return TTDG_E_LIMIT;
+    count_launches(1);
+    ttdg::weight_refresh_kernel<<<(unsigned)total_tiles, 256, 0, (cudaStream_t)stream>>>(jobs_dev, njobs);
+    TTDG_LAUNCH_RET();
+}

@@ -287,13 +287,14 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                     if (warp == 0) {
                         const long long ck_l = clock64();
                         const double *Zc = Z;
-                        const int lf = p.lap_fast == 3 ? 0 : p.lap_fast;
+                        const int lf = p.lap_fast >= 3 ? 0 : p.lap_fast;
+                        const bool lean = p.lap_fast >= 3, bfm = p.lap_fast == 4;
                         if (n <= NU) {
-                            if (!(p.lap_fast == 3 && lap_lean_warp(n, NU, LapSmemNegCostP{Zc, ZP, 1}, *lapw)))
+                            if (!(lean && lap_lean_warp(n, NU, LapSmemNegCostP{Zc, ZP, 1}, *lapw, bfm)))
                                 lap_solve_warp(n, NU, LapSmemNegCost{lap_smem_u32(Zc), ZP, 1}, *lapw, lf);
                             for (int i = lane; i < n; i += 32) Ug[i * NU + lapw->col4row[i]] = 1.0;
                         } else {
-                            if (!(p.lap_fast == 3 && lap_lean_warp(NU, n, LapSmemNegCostP{Zc, 1, ZP}, *lapw)))
+                            if (!(lean && lap_lean_warp(NU, n, LapSmemNegCostP{Zc, 1, ZP}, *lapw, bfm)))
                                 lap_solve_warp(NU, n, LapSmemNegCost{lap_smem_u32(Zc), 1, ZP}, *lapw, lf);
                             for (int i = lane; i < NU; i += 32) Ug[lapw->col4row[i] * NU + i] = 1.0;
                         }
@@ -383,7 +384,7 @@ static int g_lap_fast = -1;     // -1: read TTDG_LAP_FAST at first use
 // fall-backs of graph 0.  Returns the previous setting.
 extern "C" int ttdg_gagm_set_lap_fast(int on) {
     const int prev = g_lap_fast < 0 ? 3 : g_lap_fast;
-    g_lap_fast = (on >= 1 && on <= 3) ? on : 0;              // 2: Jacobi-auction start instead of the row reduction; 3: lean certified solve
+    g_lap_fast = (on >= 1 && on <= 4) ? on : 0;              // 2: Jacobi-auction start instead of the row reduction; 3: lean certified solve
     return prev;
 }
 
@@ -422,7 +423,7 @@ extern "C" int ttdg_gagm_solve(const float *A, const float *W, const float *U0, 
     p.init_tau = init_tau; p.min_tau = min_tau; p.sk_gamma = sk_gamma; p.tol = converge_tol; p.quad_weight = quad_weight;
     p.max_iter = max_iter; p.sk_iter = sk_iter; p.mode = mode; p.step_projector = step_projector;
     p.trace = trace; p.trace_meta = trace_meta; p.trace_cap = trace ? trace_cap : 0;
-    if (g_lap_fast < 0) { const char *e = getenv("TTDG_LAP_FAST"); g_lap_fast = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3; }
+    if (g_lap_fast < 0) { const char *e = getenv("TTDG_LAP_FAST"); g_lap_fast = (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 3; }
     p.lap_fast = g_lap_fast;
 
     const size_t smem = gagm_smem_bytes();

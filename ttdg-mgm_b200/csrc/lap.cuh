@@ -356,7 +356,7 @@ __device__ bool lap_certificate(int nr, int nc, Cost cost, LapWork &w) {
     return alive == 0u;
 }
 
-template <int SLOTS, class Cost>
+template <int SLOTS, bool BF, class Cost>
 __device__ bool lap_lean_warp_t(int nr, int nc, Cost cost, LapWork &w) {
     const int lane = threadIdx.x & 31;
     for (int k = lane; k < nr; k += 32) { w.u[k] = 0.0; w.col4row[k] = -1; }
@@ -406,6 +406,108 @@ __device__ bool lap_lean_warp_t(int nr, int nc, Cost cost, LapWork &w) {
             myc = lane < nr ? w.col4row[lane] : 0;
         }
     }
+    if (BF) {
+    // ---- (B) augmentations for the rows still free, lane = column: LABEL-CORRECTING shortest paths instead of Dijkstra.
+    // Dijkstra settles one column per step and every step is a ~360-cycle chain of dependent warp-wide operations (load the row,
+    // relax, 64-bit arg-min over the lanes, fetch the next row); near-square problems with near-tied costs - the bench workload
+    // after a few adaptation steps - need 300-500 such steps per solve.  Here a ROUND relaxes all rows whose distance improved
+    // (independent, pipelined: ~15 cycles each) and only then reduces once: the free column's best distance bounds the search
+    // (rows at or beyond it are never expanded), distances below it come out exact, and the number of rounds is the hop depth
+    // of the shortest-path tree, not the number of columns.  Duals: v_j -= max(0, D - d_j), u_{row(j)} += the same, u_cur += D.
+    double vj[SLOTS];
+    int jc[SLOTS];
+    bool colok[SLOTS];
+#pragma unroll
+    for (int t = 0; t < SLOTS; ++t) { colok[t] = lane + 32 * t < nc; jc[t] = min(lane + 32 * t, nc - 1); vj[t] = w.v[jc[t]]; }
+    double *Drow = w.shortest;                                  // distance of every row (through its matched column); [cur] = 0
+    for (int cur = 0; cur < nr; ++cur) {
+        if (w.col4row[cur] != -1) continue;                     // warp-uniform
+        double d[SLOTS];
+        int pth[SLOTS], r4c[SLOTS];
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) { d[t] = INFINITY; pth[t] = -1; r4c[t] = w.row4col[jc[t]]; }
+        if (lane < nr) Drow[lane] = lane == cur ? 0.0 : INFINITY;
+        __syncwarp();
+        unsigned active = 1u << cur;
+        double best_free = INFINITY;
+        int rounds = 0;
+        while (active) {
+            if (++rounds > 2 * LAP_MAX_DIM) return false;       // cannot happen (distances only decrease); never loop forever
+            bool chg[SLOTS];
+#pragma unroll
+            for (int t = 0; t < SLOTS; ++t) chg[t] = false;
+            unsigned a = active;
+            while (a) {
+                const int i = __ffs(a) - 1;
+                a &= a - 1;
+                ++steps;
+                // reduced costs are >= 0 in exact arithmetic; clamping the rounding noise (-1e-17) rules out negative cycles, on
+                // which a label-correcting search would improve forever by one ulp per round
+                const double Di = Drow[i], ui = w.u[i];
+#pragma unroll
+                for (int t = 0; t < SLOTS; ++t) {
+                    const double r = fmax((cost(i, jc[t]) - vj[t]) - ui, 0.0) + Di;
+                    const bool upd = colok[t] && (r < d[t]);
+                    d[t] = upd ? r : d[t];
+                    pth[t] = upd ? i : pth[t];
+                    chg[t] = chg[t] || upd;
+                }
+            }
+            // best distance of a free column (64-bit min in two 32-bit reductions; distances are >= 0 up to rounding)
+            double bf = INFINITY;
+#pragma unroll
+            for (int t = 0; t < SLOTS; ++t) if (colok[t] && r4c[t] < 0) bf = fmin(bf, d[t]);
+            const int hi = __double2hiint(bf);
+            const int mhi = __reduce_min_sync(TTDG_FULL, hi);
+            const unsigned mlo = __reduce_min_sync(TTDG_FULL, hi == mhi ? (unsigned)__double2loint(bf) : 0xFFFFFFFFu);
+            best_free = __hiloint2double(mhi, (int)mlo);
+            // rows to expand next: matched rows of the columns that improved and are still closer than the best free column
+            unsigned bits = 0u;
+#pragma unroll
+            for (int t = 0; t < SLOTS; ++t)
+                if (chg[t] && r4c[t] >= 0 && d[t] < best_free) { bits |= 1u << r4c[t]; Drow[r4c[t]] = d[t]; }
+            __syncwarp();
+            active = __reduce_or_sync(TTDG_FULL, bits);
+        }
+        if (!(best_free < INFINITY)) return false;              // no free column reachable: impossible for nr <= nc
+        // sink = a free column at the best distance
+        int mine = -1;
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) if (mine < 0 && colok[t] && r4c[t] < 0 && d[t] == best_free) mine = lane + 32 * t;
+        const unsigned who = __ballot_sync(TTDG_FULL, mine >= 0);
+        if (who == 0u) return false;
+        const int sink = __shfl_sync(TTDG_FULL, mine, __ffs(who) - 1);
+        const double minVal = best_free;
+        if (lane == 0) w.u[cur] += minVal;
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t)
+            if (colok[t] && d[t] < INFINITY) {
+                w.path[lane + 32 * t] = pth[t];
+                if (d[t] < minVal && r4c[t] >= 0) {
+                    const double dd = minVal - d[t];
+                    w.u[r4c[t]] += dd;
+                    vj[t] -= dd;
+                }
+            }
+        __syncwarp();
+        if (lane == 0) {                                        // augment along the path (sequential, short)
+            int j = sink, guard = 0;
+            while (true) {
+                ++hops;
+                const int r = w.path[j];
+                w.row4col[j] = r;
+                const int t = w.col4row[r];
+                w.col4row[r] = j;
+                j = t;
+                if (r == cur || ++guard > LAP_MAX_DIM) break;
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int t = 0; t < SLOTS; ++t) if (lane + 32 * t < nc) w.v[lane + 32 * t] = vj[t];
+    }
+    else {
     // ---- (B) lean Dijkstra augmentations for the rows still free, lane = column
     double vj[SLOTS];
     int jc[SLOTS];
@@ -485,9 +587,10 @@ __device__ bool lap_lean_warp_t(int nr, int nc, Cost cost, LapWork &w) {
         }
         __syncwarp();
     }
-    if (lane == 0) { w.stat_steps += steps; w.stat_hops += hops; }
 #pragma unroll
     for (int t = 0; t < SLOTS; ++t) if (lane + 32 * t < nc) w.v[lane + 32 * t] = vj[t];
+    }
+    if (lane == 0) { w.stat_steps += steps; w.stat_hops += hops; }
     __syncwarp();
     const bool ok = lap_certificate(nr, nc, cost, w);
     if (lane == 0) { if (ok) ++w.stat_fast_ok; else ++w.stat_fast_fallback; }
@@ -496,12 +599,19 @@ __device__ bool lap_lean_warp_t(int nr, int nc, Cost cost, LapWork &w) {
 }
 
 // lean certified solve; false = not certified (the caller runs the SciPy-order solve).  Full warp, nr <= 32.
+// bf = false: Dijkstra augmentations (one column settled per step); true: label-correcting rounds (all improved rows relaxed per
+// round, one reduction per round)
 template <class Cost>
-__device__ __forceinline__ bool lap_lean_warp(int nr, int nc, Cost cost, LapWork &w) {
+__device__ __forceinline__ bool lap_lean_warp(int nr, int nc, Cost cost, LapWork &w, bool bf) {
     if (nr > 32 || nc > LAP_MAX_DIM) return false;
-    if (nc <= 32) return lap_lean_warp_t<1>(nr, nc, cost, w);
-    if (nc <= 64) return lap_lean_warp_t<2>(nr, nc, cost, w);
-    return lap_lean_warp_t<LAP_SLOTS>(nr, nc, cost, w);
+    if (bf) {
+        if (nc <= 32) return lap_lean_warp_t<1, true>(nr, nc, cost, w);
+        if (nc <= 64) return lap_lean_warp_t<2, true>(nr, nc, cost, w);
+        return lap_lean_warp_t<LAP_SLOTS, true>(nr, nc, cost, w);
+    }
+    if (nc <= 32) return lap_lean_warp_t<1, false>(nr, nc, cost, w);
+    if (nc <= 64) return lap_lean_warp_t<2, false>(nr, nc, cost, w);
+    return lap_lean_warp_t<LAP_SLOTS, false>(nr, nc, cost, w);
 }
 
 // fast != 0: try the certified row-reduction solve first (rows <= 32 only), fall back to the SciPy-order solve

@@ -106,8 +106,15 @@ class Trainer(BaselineTrainer):
     def build_optimizer(cls, cfg, model):
         from ttdg_b200.optim import FlatSGD
         s = cfg.SOLVER
-        return FlatSGD(model.adapted_parameters(), lr=s.BASE_LR, momentum=getattr(s, "MOMENTUM", 0.9),
-                       weight_decay=getattr(s, "WEIGHT_DECAY", 1e-4))
+        opt = FlatSGD(model.adapted_parameters(), lr=s.BASE_LR, momentum=getattr(s, "MOMENTUM", 0.9),
+                      weight_decay=getattr(s, "WEIGHT_DECAY", 1e-4), buckets=[len(g) for g in model.adapted_parameter_groups()],
+                      on_step=model.refresh_weight_copies)
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world > 1:                                       # bucketed all-reduce overlapped with the backward pass
+            from ttdg_b200 import detector
+            opt.enable_overlap(world)
+            detector.GRAD_READY_HOOK[0] = opt.grad_ready
+        return opt
 
     @classmethod
     def build_test_loader(cls, cfg, dataset_name):

@@ -57,6 +57,12 @@ SIGNATURES = {
     "ttdg_wgrad_tc_supported": (c_int, [c_int, c_int, c_int]),
     "ttdg_wgrad_tc": (c_int, [P, P] + [c_int] * 10 + [P, P]),
     "ttdg_tf32_split": (c_int, [P, P, P, c_int64, P]),
+    "ttdg_weight_refresh": (c_int, [P, c_int, c_int64, P]),
+    "ttdg_rpn_select": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, c_int, P, P, P, P, P]),
+    "ttdg_sort_candidates": (c_int, [P, P, P, P, c_int, c_int, c_int, c_float, P, P, P, P, P]),
+    "ttdg_gather_kept": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_float, P, P, P, P, P]),
+    "ttdg_rois_from_padded": (c_int, [P, P, c_int, c_int, P, P]),
+    "ttdg_mask_padded_candidates": (c_int, [P, P, c_int, c_int, c_int, P]),
     "ttdg_conv_tc_bf16": (c_int, [P, P, P, P, P] + [c_int] * 16 + [P, c_int, P]),
     "ttdg_weight_transpose_bf16": (c_int, [P, c_int, c_int, c_int, P, P]),
     "ttdg_stem_tc2": (c_int, [P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, P, c_int, P]),

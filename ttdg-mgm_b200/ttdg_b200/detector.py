@@ -96,6 +96,49 @@ def _weights_bf16(w, owner):
     return wt
 
 
+_REFRESH_TABLES = {}
+
+
+def refresh_weight_copies(modules):
+    """Re-derive, in ONE launch, every cached tensor-core weight copy (K-major hi / lo, data-gradient hi / lo, bf16) of the
+    given layers from their (just updated) fp32 master weights - in place, so the copies keep their addresses and the cached
+    TMA descriptors stay valid.  Call after FlatSGD.step (which bumps PARAM_EPOCH); layers / variants that have no cached copy
+    yet are created lazily on first use as before."""
+    jobs, keep = [], []
+    for m in modules:
+        cache = m.__dict__.get("_wk_cache")
+        if not cache:
+            continue
+        w = m.weight
+        R, S, Cin, Cout = w.shape
+        for key, ent in cache.items():
+            if key == "bf16":
+                jobs.append((w.data_ptr(), ent[1].data_ptr(), 0, R * S, Cin, Cout, 2))
+            else:
+                transposed, precise = key
+                jobs.append((w.data_ptr(), ent[1].data_ptr(), ent[2].data_ptr() if ent[2] is not None else 0, R * S, Cin, Cout,
+                             0 if transposed else 1))
+            keep.append((m, key))
+    if not jobs:
+        return
+    sig = tuple(jobs)
+    dev = modules[0].weight.device
+    tab = _REFRESH_TABLES.get(sig)
+    if tab is None:
+        rows, tot = [], 0
+        for j in jobs:
+            rows.append(list(j) + [tot])
+            tot += j[3] * ((j[4] + 31) // 32) * ((j[5] + 31) // 32)
+        _REFRESH_TABLES.clear()                              # one live table per model is enough
+        tab = (torch.tensor(rows, dtype=torch.int64).to(dev), tot)
+        _REFRESH_TABLES[sig] = tab
+    check(_C.lib().ttdg_weight_refresh(_p(tab[0]), len(jobs), tab[1], _stream()), "weight_refresh")
+    for m, key in keep:                                      # the copies are current again
+        ent = m._wk_cache[key]
+        stamp = (PARAM_EPOCH[0], m.weight._version, m.weight.data_ptr())
+        m._wk_cache[key] = (stamp,) + tuple(ent[1:])
+
+
 def _tc_ok(Cin, Cout, stride, R=1, pad=0):
     """Tensor-core kernel coverage: stride 1, or the strided 1x1 convs (TMA element strides)."""
     if CONV_MODE[0] == "simt" or Cin % 32 or Cout % 64:
@@ -351,6 +394,7 @@ class Bottleneck(nn.Module):
         return self.conv3(out, relu=True, residual=sc, res_mode=1)                   # relu(bn(conv3) + shortcut)
 
 
+GRAD_READY_HOOK = [None]      # callable(k): the gradients of bucket k are complete (FlatSGD.grad_ready), see ResNet50.forward
 STEM_TC = [os.environ.get("TTDG_STEM_TC", "1") == "1"]        # stem on tensor cores (padded image, overlapping TMA windows)
 STEM_LEFT, STEM_EXTRA = 3, 8                                   # padded image rows: 3 zero pixels | image | 5 zero pixels
 
@@ -415,9 +459,15 @@ class ResNet50(nn.Module):
                 check(L.ttdg_maxpool3x3s2(_p(y), N, H, W, C, _p(p), _stream()), "maxpool")
             y = self.res2(p)
         out = {"res2": y}
-        for name in ("res3", "res4", "res5"):
+        for k, name in enumerate(("res3", "res4", "res5")):
             y = getattr(self, name)(y)
             out[name] = y
+            # Overlapped gradient all-reduce: when the gradient w.r.t. a stage's OUTPUT is complete, every parameter above it
+            # has its gradient (weight gradients are produced by the same autograd nodes as the data gradients).  With
+            # adapted_parameters() ordered [affinity, FPN, res5 | res4 | res3]: d(res4 out) -> bucket 0, d(res3 out) -> bucket 1.
+            if GRAD_READY_HOOK[0] is not None and name != "res5" and y.requires_grad:
+                bucket = 1 - k
+                y.register_hook(lambda g, b=bucket: (GRAD_READY_HOOK[0](b), None)[1])
         return out
 
 
@@ -543,60 +593,80 @@ class RPN(nn.Module):
         return self.predict(feats, image_size, training)
 
     @torch.no_grad()
-    def predict(self, feats, image_size, training):
+    def predict_padded(self, feats, image_size, training):
         """feats: [p2 .. p6] NHWC; image_size: (h, w) or one (h, w) per image (boxes are clipped to the image's own size, d2
-        find_top_rpn_proposals).  Returns per image (proposal boxes k x 4, objectness logits k), sorted by logit."""
+        find_top_rpn_proposals).  Everything after the head convolutions runs in five launches without touching the host
+        (csrc/select.cu): top-k + sort + decode for all (image, level) pairs, per-image ordering across levels, per-level NMS
+        (2 launches), compaction.  Returns (boxes N x 1000 x 4, objectness logits N x 1000 - padding rows hold -inf -, counts
+        N int32 on the device)."""
         L = _C.lib()
         A = self._cell.shape[0]
         pre_topk = 2000 if training else 1000
         N = feats[0].shape[0]
         dev = feats[0].device
-        sizes, same = _sizes(image_size, N)
-        cell_h = (ctypes.c_float * (A * 4))(*self._cell.reshape(-1).tolist())
-        boxes_l, scores_l, valid_l, lvl_l = [], [], [], []
+        sizes, _ = _sizes(image_size, N)
+        logits_l, deltas_l, hw, ks = [], [], [], []
         for l, f in enumerate(feats):
             f = f.detach()
             _, H, W, _ = f.shape
             if CONV_MODE[0] == "bf16":                                  # configs[2]: the heads' GEMMs run kind::f16 as well
                 f = f.to(torch.bfloat16)
             t = self.rpn_head.conv(f, relu=True)
-            logits = self.rpn_head.objectness_logits(t, out_bf16=False)     # N x H x W x 64 (15 used), fp32 for the decode kernels
-            deltas = self.rpn_head.anchor_deltas(t, out_bf16=False)         # N x H x W x 64 (60 used)
-            flat = logits[..., :A].reshape(N, H * W * A)
-            k = min(flat.shape[1], pre_topk)
-            sc, idx = torch.topk(flat, k, dim=1, sorted=True)           # ordering only (plumbing)
-            boxes = torch.empty(N, k, 4, dtype=torch.float32, device=dev)
-            valid = torch.empty(N, k, dtype=torch.uint8, device=dev)
-            idx = idx.contiguous()
-            if same:
-                check(L.ttdg_rpn_decode(_p(deltas), deltas.shape[-1], _p(idx), N, k, H, W, A, STRIDES[l],
-                                        ctypes.cast(cell_h, ctypes.c_void_p), float(sizes[0][0]), float(sizes[0][1]), _p(boxes),
-                                        _p(valid), _stream()), "rpn_decode")
-            else:                                                       # mixed image sizes in one padded batch: clip per image
-                for n in range(N):
-                    check(L.ttdg_rpn_decode(_p(deltas[n]), deltas.shape[-1], _p(idx[n]), 1, k, H, W, A, STRIDES[l],
-                                            ctypes.cast(cell_h, ctypes.c_void_p), float(sizes[n][0]), float(sizes[n][1]),
-                                            _p(boxes[n]), _p(valid[n]), _stream()), "rpn_decode")
-            boxes_l.append(boxes); scores_l.append(sc); valid_l.append(valid)
-            lvl_l.append(torch.full((k,), l, dtype=torch.int32, device=dev))
-        boxes, scores, valid, lvl = torch.cat(boxes_l, 1), torch.cat(scores_l, 1), torch.cat(valid_l, 1).bool(), torch.cat(lvl_l)
-        # invalid (non-finite / empty) boxes sort last and never interact (unique negative category)
-        key = torch.where(valid & torch.isfinite(scores), scores, torch.full_like(scores, -float("inf")))
-        order = torch.argsort(key, dim=1, descending=True, stable=True)
-        n_valid = (key > -float("inf")).sum(1).to(torch.int32)
-        Kt = boxes.shape[1]
-        ar = torch.arange(Kt, device=dev)
-        b_sorted = torch.gather(boxes, 1, order.unsqueeze(-1).expand(-1, -1, 4))
-        s_sorted = torch.gather(scores, 1, order)
-        cats = torch.where(ar.unsqueeze(0) < n_valid.unsqueeze(1), lvl[order], (-1 - ar).to(torch.int32).unsqueeze(0)).to(torch.int32)
+            logits_l.append(self.rpn_head.objectness_logits(t, out_bf16=False))     # N x H x W x 64 (15 used), fp32
+            deltas_l.append(self.rpn_head.anchor_deltas(t, out_bf16=False))         # N x H x W x 64 (60 used)
+            hw += [H, W]
+            ks.append(min(H * W * A, pre_topk))
+        nl, Kt = len(feats), sum(ks)
+        boxes = torch.empty(N, Kt, 4, dtype=torch.float32, device=dev)
+        scores = torch.empty(N, Kt, dtype=torch.float32, device=dev)
+        valid = torch.empty(N, Kt, dtype=torch.uint8, device=dev)
+        vp = lambda ts: ctypes.cast((ctypes.c_void_p * nl)(*[t.data_ptr() for t in ts]), ctypes.c_void_p)
+        ip = lambda vs: ctypes.cast((ctypes.c_int32 * len(vs))(*vs), ctypes.c_void_p)
+        fp = lambda vs: ctypes.cast((ctypes.c_float * len(vs))(*vs), ctypes.c_void_p)
+        check(L.ttdg_rpn_select(vp(logits_l), vp(deltas_l), ip(hw), ip(list(STRIDES[:nl])), ip(ks), nl, logits_l[0].shape[-1],
+                                deltas_l[0].shape[-1], A, fp(self._cell.reshape(-1).tolist()), N,
+                                fp([float(v) for s_ in sizes for v in s_]), _p(boxes), _p(scores), _p(valid), _stream()), "rpn_select")
+        key = (tuple(ks), dev)
+        lvl = self.__dict__.setdefault("_lvl_cache", {}).get(key)
+        if lvl is None:                                                 # level of every candidate position: the NMS category
+            lvl = torch.cat([torch.full((k,), l, dtype=torch.int32) for l, k in enumerate(ks)]).to(dev)
+            self._lvl_cache[key] = lvl
+        b_sorted, s_sorted, cats, n_valid = sort_candidates(boxes, scores, valid, lvl, 0, -float("inf"))
         keep, n_keep = nms_sorted(b_sorted, cats, self.nms_thresh, self.post_topk)          # all images, one launch pair
-        ak = torch.arange(self.post_topk, device=dev).unsqueeze(0)
-        counts = ((keep < n_valid.unsqueeze(1)) & (ak < n_keep.unsqueeze(1))).sum(1).cpu().tolist()      # one host sync per batch
-        # one padded gather for the whole batch (the tail of keep is zero-filled: a valid index), per-image results are views
-        kk = keep[:, :max(counts)].long() if max(counts) > 0 else keep[:, :0].long()
-        b_sel = torch.gather(b_sorted, 1, kk.unsqueeze(-1).expand(-1, -1, 4))
-        s_sel = torch.gather(s_sorted, 1, kk)
-        return [(b_sel[n, :counts[n]], s_sel[n, :counts[n]]) for n in range(N)]
+        out_b, out_s, _, counts = gather_kept(b_sorted, s_sorted, cats, keep, n_keep, n_valid, self.post_topk, -float("inf"), False)
+        return out_b, out_s, counts
+
+    @torch.no_grad()
+    def predict(self, feats, image_size, training):
+        """List form of predict_padded: per image (proposal boxes k x 4, objectness logits k), sorted by logit; one host read."""
+        out_b, out_s, counts = self.predict_padded(feats, image_size, training)
+        cnt = counts.cpu().tolist()
+        return [(out_b[n, :c], out_s[n, :c]) for n, c in enumerate(cnt)]
+
+
+def sort_candidates(boxes, scores, valid, cats_in, cat_mod, invalid_score):
+    """boxes B x n x 4, scores B x n (+ valid B x n uint8 or None: valid <=> score > 0) -> candidates of every image ordered by
+    score (invalid last) with the NMS category: cats_in[position] or position % cat_mod."""
+    B, n = scores.shape
+    dev = scores.device
+    b_out, s_out = torch.empty_like(boxes), torch.empty_like(scores)
+    cats = torch.empty(B, n, dtype=torch.int32, device=dev)
+    n_valid = torch.empty(B, dtype=torch.int32, device=dev)
+    check(_C.lib().ttdg_sort_candidates(_p(boxes), _p(scores), _p(valid), _p(cats_in), int(cat_mod), B, n, float(invalid_score), _p(b_out),
+                                        _p(s_out), _p(cats), _p(n_valid), _stream()), "sort_candidates")
+    return b_out, s_out, cats, n_valid
+
+
+def gather_kept(b_sorted, s_sorted, cats, keep, n_keep, n_valid, max_keep, pad_score, want_cats=True):
+    B, n = s_sorted.shape
+    dev = s_sorted.device
+    out_b = torch.empty(B, max_keep, 4, dtype=torch.float32, device=dev)
+    out_s = torch.empty(B, max_keep, dtype=torch.float32, device=dev)
+    out_c = torch.empty(B, max_keep, dtype=torch.int64, device=dev) if want_cats else None
+    counts = torch.empty(B, dtype=torch.int32, device=dev)
+    check(_C.lib().ttdg_gather_kept(_p(b_sorted), _p(s_sorted), _p(cats), _p(keep), _p(n_keep), _p(n_valid), B, n, int(max_keep),
+                                    float(pad_score), _p(out_b), _p(out_s), _p(out_c), _p(counts), _stream()), "gather_kept")
+    return out_b, out_s, out_c, counts
 
 
 class BoxHead(nn.Module):
@@ -657,14 +727,19 @@ class ROIHeads(nn.Module):
         self.score_thresh, self.nms_thresh, self.topk = 0.05, 0.5, 100
 
     @torch.no_grad()
-    def forward_box(self, feats, proposals, image_size):
+    def forward_box_padded(self, feats, pboxes, pcounts, image_size):
+        """_forward_box + FastRCNNOutputLayers.inference on PADDED proposals (N x P x 4 with per-image counts on the device):
+        RoIAlign, the two FCs, class-specific decoding, score threshold, per-class NMS, top 100 - without a host round trip.
+        Returns (boxes N x 100 x 4, scores N x 100, classes N x 100 int64, counts N int32); padding rows: score 0, class -1."""
         L = _C.lib()
         K = self.num_classes
         feats4 = [f.detach() for f in feats[:4]]
         dev = feats4[0].device
-        props = [p[0] for p in proposals]
-        rois = _rois(props)
-        R = rois.shape[0]
+        N, P = pboxes.shape[0], pboxes.shape[1]
+        R = N * P
+        pb = pboxes.reshape(R, 4).contiguous()
+        rois = torch.empty(R, 5, dtype=torch.float32, device=dev)
+        check(L.ttdg_rois_from_padded(_p(pb), _p(pcounts), N, P, _p(rois), _stream()), "rois_from_padded")
         x = roi_align(feats4, rois, 7).reshape(R, 1, 1, 7 * 7 * 256)
         if CONV_MODE[0] == "bf16":
             x = x.to(torch.bfloat16)
@@ -672,50 +747,40 @@ class ROIHeads(nn.Module):
         x = self.box_head.fc2(x, relu=True)
         cls = self.box_predictor.cls_score(x, out_bf16=False).reshape(R, -1)
         reg = self.box_predictor.bbox_pred(x, out_bf16=False).reshape(R, -1)
-        pb = torch.cat(props).contiguous()
         cand_b = torch.empty(R * K, 4, dtype=torch.float32, device=dev)
         cand_s = torch.empty(R * K, dtype=torch.float32, device=dev)
-        sizes, same = _sizes(image_size, len(props))
+        sizes, same = _sizes(image_size, N)
         if same:
             check(L.ttdg_box_predict(_p(cls), cls.shape[1], _p(reg), reg.shape[1], _p(pb), R, K, float(sizes[0][0]), float(sizes[0][1]),
                                      self.score_thresh, _p(cand_b), _p(cand_s), _stream()), "box_predict")
         else:                                                           # clip to each image's own size
-            o = 0
-            for i, p in enumerate(props):
-                n = len(p)
-                if n:
-                    check(L.ttdg_box_predict(_p(cls[o:o + n]), cls.shape[1], _p(reg[o:o + n]), reg.shape[1], _p(pb[o:o + n]), n, K,
-                                             float(sizes[i][0]), float(sizes[i][1]), self.score_thresh, _p(cand_b[o * K:(o + n) * K]),
-                                             _p(cand_s[o * K:(o + n) * K]), _stream()), "box_predict")
-                o += n
-        # pad every image to the same candidate count (invalid candidates: score -1, unique negative category)
-        B = len(props)
-        nmax = max(len(p) for p in props) * K
-        if all(len(p) * K == nmax for p in props):          # same proposal count everywhere: the padded layout is a view
-            cs, cb = cand_s.view(B, nmax), cand_b.view(B, nmax, 4)
-        else:
-            cs = torch.full((B, nmax), -1.0, dtype=torch.float32, device=dev)
-            cb = torch.zeros(B, nmax, 4, dtype=torch.float32, device=dev)
-            o = 0
-            for i, p in enumerate(props):
-                n = len(p) * K
-                cs[i, :n], cb[i, :n] = cand_s[o:o + n], cand_b[o:o + n]
-                o += n
-        order = torch.argsort(cs, dim=1, descending=True, stable=True)
-        ss = torch.gather(cs, 1, order)
-        bb = torch.gather(cb, 1, order.unsqueeze(-1).expand(-1, -1, 4))
-        cc = (order % K).to(torch.int32)                                 # candidate t = roi * K + class
-        n_valid = (ss > 0).sum(1).to(torch.int32)
-        ar = torch.arange(nmax, device=dev)
-        cats = torch.where(ar.unsqueeze(0) < n_valid.unsqueeze(1), cc, (-1 - ar).to(torch.int32).unsqueeze(0)).to(torch.int32)
+            for i in range(N):
+                o = i * P
+                check(L.ttdg_box_predict(_p(cls[o:o + P]), cls.shape[1], _p(reg[o:o + P]), reg.shape[1], _p(pb[o:o + P]), P, K,
+                                         float(sizes[i][0]), float(sizes[i][1]), self.score_thresh, _p(cand_b[o * K:(o + P) * K]),
+                                         _p(cand_s[o * K:(o + P) * K]), _stream()), "box_predict")
+        check(L.ttdg_mask_padded_candidates(_p(cand_s), _p(pcounts), N, P, K, _stream()), "mask_padded")
+        # candidate t = roi * K + class: the NMS category is t % K
+        bb, ss, cats, n_valid = sort_candidates(cand_b.view(N, P * K, 4), cand_s.view(N, P * K), None, None, K, -1.0)
         keep, n_keep = nms_sorted(bb, cats, self.nms_thresh, self.topk)
-        ak = torch.arange(self.topk, device=dev).unsqueeze(0)
-        counts = ((keep < n_valid.unsqueeze(1)) & (ak < n_keep.unsqueeze(1))).sum(1).cpu().tolist()      # one host sync per batch
-        kk = keep[:, :max(counts)].long() if max(counts) > 0 else keep[:, :0].long()
-        b_sel = torch.gather(bb, 1, kk.unsqueeze(-1).expand(-1, -1, 4))
-        s_sel = torch.gather(ss, 1, kk)
-        c_sel = torch.gather(cc, 1, kk).long()
-        return [(b_sel[i, :counts[i]], s_sel[i, :counts[i]], c_sel[i, :counts[i]]) for i in range(B)]
+        return gather_kept(bb, ss, cats, keep, n_keep, n_valid, self.topk, 0.0, True)
+
+    @torch.no_grad()
+    def forward_box(self, feats, proposals, image_size):
+        """List form: proposals = per image (boxes k x 4, logits k) -> per image (boxes, scores, classes); one host read."""
+        dev = feats[0].device
+        lens = [len(p[0]) for p in proposals]
+        P = max(max(lens), 1)
+        if all(n == P for n in lens):
+            pboxes = torch.stack([p[0] for p in proposals])
+        else:
+            pboxes = torch.zeros(len(proposals), P, 4, dtype=torch.float32, device=dev)
+            for i, p in enumerate(proposals):
+                pboxes[i, :lens[i]] = p[0]
+        pcounts = torch.tensor(lens, dtype=torch.int32).to(dev, non_blocking=True)
+        b, s_, c, counts = self.forward_box_padded(feats, pboxes, pcounts, image_size)
+        cnt = counts.cpu().tolist()
+        return [(b[i, :n], s_[i, :n], c[i, :n]) for i, n in enumerate(cnt)]
 
     @torch.no_grad()
     def mask_logits(self, feats, dets):
@@ -862,13 +927,25 @@ class MaskRCNN(nn.Module):
     def adapted_parameters(self):
         """Parameters the test-time loss reaches: res3-res5 and FPN (stem + res2 are frozen, FREEZE_AT = 2; RPN / ROI
         heads are not in the TTT loss graph)."""
-        ps = []
-        for name in ("res3", "res4", "res5"):
-            ps += list(getattr(self.backbone.bottom_up, name).parameters())
+        return [p for group in self.adapted_parameter_groups() for p in group]
+
+    def adapted_parameter_groups(self):
+        """[FPN + res5, res4, res3]: the order in which the backward pass completes their gradients (gradient buckets)."""
+        fpn = []
         for lvl in (2, 3, 4, 5):
-            ps += list(getattr(self.backbone, f"fpn_lateral{lvl}").parameters())
-            ps += list(getattr(self.backbone, f"fpn_output{lvl}").parameters())
-        return ps
+            fpn += list(getattr(self.backbone, f"fpn_lateral{lvl}").parameters())
+            fpn += list(getattr(self.backbone, f"fpn_output{lvl}").parameters())
+        bu = self.backbone.bottom_up
+        return [fpn + list(bu.res5.parameters()), list(bu.res4.parameters()), list(bu.res3.parameters())]
+
+    def refresh_weight_copies(self):
+        """FlatSGD(on_step=...): all tensor-core copies of the adapted weights in one launch (see refresh_weight_copies)."""
+        mods = self.__dict__.get("_adapted_convs")
+        if mods is None:
+            ids = {id(p) for p in self.adapted_parameters()}
+            mods = [m for m in self.modules() if isinstance(m, Conv2d) and id(m.weight) in ids]
+            self.__dict__["_adapted_convs"] = mods
+        refresh_weight_copies(mods)
 
     def preprocess_image(self, images_u8):
         """-> (image tensor for ``backbone.pyramid``, [(h, w) per image]): d2 preprocess_image (rcnn.py:219)."""
@@ -888,9 +965,19 @@ class MaskRCNN(nn.Module):
         """rcnn.py:331-345: features (NHWC, grad-carrying), RPN proposals and box-head detections in TRAIN mode."""
         x, sizes = self.preprocess_image(images_u8)
         feats = self.backbone.pyramid(x)
-        props = self.proposal_generator.predict(feats, sizes, training=True)
-        dets = self.roi_heads.forward_box(feats, props, sizes)
+        props, dets = self._detect(feats, sizes, training=True)
         return feats, props, dets
+
+    @torch.no_grad()
+    def _detect(self, feats, sizes, training):
+        """RPN -> box head on padded device-side tensors; ONE host read (both count vectors) turns them into the per-image
+        lists of the API."""
+        pb, ps, pc = self.proposal_generator.predict_padded(feats, sizes, training)
+        b, s, c, dc = self.roi_heads.forward_box_padded(feats, pb, pc, sizes)
+        cnt = torch.stack((pc, dc)).cpu().tolist()
+        props = [(pb[n, :k], ps[n, :k]) for n, k in enumerate(cnt[0])]
+        dets = [(b[n, :k], s[n, :k], c[n, :k]) for n, k in enumerate(cnt[1])]
+        return props, dets
 
     @torch.no_grad()
     def inference(self, images_u8, out_sizes=None):
@@ -898,6 +985,5 @@ class MaskRCNN(nn.Module):
         images or one per image (the dataset dict's original 'height' / 'width'); default = the network input sizes."""
         x, sizes = self.preprocess_image(images_u8)
         feats = self.backbone.pyramid(x)
-        props = self.proposal_generator.predict(feats, sizes, training=False)
-        dets = self.roi_heads.forward_box(feats, props, sizes)
+        props, dets = self._detect(feats, sizes, training=False)
         return self.roi_heads.forward_mask(feats, dets, out_sizes or sizes, sizes), feats, props, dets

@@ -59,6 +59,11 @@ class Instances:
             return len(v)
         return 0
 
+    def num_valid(self):
+        """Rows that are real when the fields are padded to a fixed capacity (PseudoLabRPN proposals); = len() otherwise."""
+        pad = self.__dict__.get("_padded")
+        return int(pad[2][pad[3]].item()) if pad is not None else len(self)
+
     def to(self, device):
         out = Instances(self._image_size)
         for k, v in self._fields.items():
