@@ -413,17 +413,29 @@ def main():
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t.item())
 
+    if world > 1:
+        # one process per GPU shares the host: keep every rank's launch thread on its own cores (the step issues ~560 launches
+        # from Python; a rank that loses its core for a few ms makes all the others wait in the gradient all-reduce)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = len(cores) // world
+            if per >= 1:
+                os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per])
+        except (AttributeError, OSError):
+            pass
     warm = max(args.warmup, 3)
     for _ in range(warm):
         step(batches_dev, False)
     barrier()
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(local_rank) if rank == 0 else None      # one nvidia-smi poller per job, not per rank
     l0 = lib.ttdg_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    h0 = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()                                        # L2 flush between steps (inside the timed region: 256 MiB memset)
         step(batches_dev, False)
+    host_ms = (time.perf_counter() - h0) * 1e3 / args.steps  # host time to ENQUEUE a step (no sync inside)
     e1.record()
     barrier()
     launches = lib.ttdg_launch_count() - l0
@@ -443,7 +455,7 @@ def main():
     e1.record()
     barrier()
     e2e_val = IMAGES_PER_GPU * world * args.steps / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks is not None else None
 
     # ---- where the time goes, per rank (3 extra instrumented steps: CUDA events at the stage boundaries + around the solver)
     marks = []
@@ -455,7 +467,7 @@ def main():
     n3 = 3.0
     mine = [sum(t[0].elapsed_time(t[1]) for t in marks) / n3, sum(t[1].elapsed_time(t[2]) for t in marks) / n3,
             sum(t[2].elapsed_time(t[3]) for t in marks) / n3, sum(t[3].elapsed_time(t[4]) for t in marks) / n3,
-            sum(a.elapsed_time(b) for _, _, a, b in grec) / n3]
+            sum(a.elapsed_time(b) for _, _, a, b in grec) / n3, host_ms]
     tl = torch.tensor(mine, dtype=torch.float64, device=device)
     if world > 1:
         allr = [torch.zeros_like(tl) for _ in range(world)]
@@ -463,9 +475,10 @@ def main():
         allr = torch.stack(allr).cpu()
     else:
         allr = tl.cpu().unsqueeze(0)
-    keys = ("ttt_forward_ms", "backward_ms", "allreduce_wait_ms", "sgd_ms", "gagm_ms")
+    keys = ("ttt_forward_ms", "backward_ms", "allreduce_wait_ms", "sgd_ms", "gagm_ms", "host_enqueue_ms")
     per_rank = {k: {"max": round(float(allr[:, i].max()), 3), "min": round(float(allr[:, i].min()), 3)} for i, k in enumerate(keys)}
-    per_rank["note"] = "per step, mean of 3 instrumented steps, max / min over ranks; gagm_ms is part of ttt_forward_ms"
+    per_rank["note"] = ("per step, mean of 3 instrumented steps, max / min over ranks; gagm_ms is part of ttt_forward_ms; "
+                        "host_enqueue_ms = host time to issue one step of the timed loop (no sync inside)")
 
     roof_conv = conv_roofline(lambda: step(batches_dev, False), conv)     # every rank runs it (the all-reduce inside is collective)
     if rank == 0:

@@ -235,6 +235,9 @@ int ttdg_conv_wgrad(const float *x, const float *dy, int N, int H, int W, int Ci
 /* out = (y > 0 ? g : 0) * scale[c]: backward through ReLU (mask from the stored output y, may be NULL) and the
  * FrozenBN scale (may be NULL). */
 int ttdg_relu_bn_bwd(const float *g, const float *y, const float *scale, int C, int64_t numel, float *out, void *stream);
+/* the same in one pass with both results: out_pre = g * [y > 0] (gradient of the residual branch), out_conv = out_pre * scale */
+int ttdg_relu_bn_bwd2(const float *g, const float *y, const float *scale, int C, int64_t numel, float *out_pre, float *out_conv,
+                      void *stream);
 /* out[c] += sum over pixels of g[pixel][c]  (conv bias gradient) */
 int ttdg_bias_grad(const float *g, int64_t pixels, int C, float *out, void *stream);
 int ttdg_maxpool3x3s2(const float *x, int N, int H, int W, int C, float *y, void *stream);           /* ResNet stem pool */

@@ -36,12 +36,15 @@ elif what == "full_step":
     import bench
     m, opt = bench.build_ours(dev)
     inputs = [dict(d, image=d["image"].to(dev)) for d in bench.make_inputs(0)]
-    for _ in range(reps):
+    for r in range(reps):
+        if r == reps - 1:                                  # ncu --profile-from-start off: exactly the last step is captured
+            torch.cuda.synchronize(); torch.cuda.profiler.start()
         m.train()
         loss, _, _, _ = m(inputs, branch="TTT")
         opt.zero_grad(); loss.backward(); opt.step(1)
         m.eval()
         out = m(inputs)
+    torch.cuda.synchronize(); torch.cuda.profiler.stop()
     print("loss", float(loss), "dets", [len(o["instances"]) for o in out])
 elif what == "timing":
     # CUDA-event timing of the stages of one full step (not under a profiler)

@@ -433,6 +433,20 @@ extern "C" int ttdg_relu_bn_bwd(const float *g, const float *y, const float *sca
 }
 
 namespace ttdg {
+// one pass, two results: out_pre = (y > 0 ? g : 0) (the gradient of the residual branch), out_conv = out_pre * scale[c]
+__global__ void __launch_bounds__(256)
+relu_bn_bwd2_kernel(const float *__restrict__ g, const float *__restrict__ y, const float *__restrict__ scale, int C, int64_t n4,
+                    float *__restrict__ out_pre, float *__restrict__ out_conv) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+        float4 gv = reinterpret_cast<const float4 *>(g)[i];
+        const float4 yv = reinterpret_cast<const float4 *>(y)[i];
+        gv.x = yv.x > 0.f ? gv.x : 0.f; gv.y = yv.y > 0.f ? gv.y : 0.f; gv.z = yv.z > 0.f ? gv.z : 0.f; gv.w = yv.w > 0.f ? gv.w : 0.f;
+        reinterpret_cast<float4 *>(out_pre)[i] = gv;
+        const float4 sc = *reinterpret_cast<const float4 *>(scale + (int)((i * 4) % C));
+        gv.x *= sc.x; gv.y *= sc.y; gv.z *= sc.z; gv.w *= sc.w;
+        reinterpret_cast<float4 *>(out_conv)[i] = gv;
+    }
+}
 __device__ __forceinline__ float4 bf16x4_to_float4(uint2 v) {
     const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&v.x));
     const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&v.y));
@@ -481,6 +495,17 @@ maxpool3x3s2_bf16_kernel(const __nv_bfloat16 *__restrict__ x, int N, int H, int 
     }
 }
 }  // namespace ttdg
+
+extern "C" int ttdg_relu_bn_bwd2(const float *g, const float *y, const float *scale, int C, int64_t numel, float *out_pre, float *out_conv,
+                                 void *stream) {
+    TTDG_CHECK_ARG(g && y && scale && out_pre && out_conv && C % 4 == 0 && numel % 4 == 0 && numel >= 0);
+    if (numel == 0) return 0;
+    int64_t nb = (numel / 4 + 255) / 256;
+    if (nb > 148 * 8) nb = 148 * 8;
+    count_launches(1);
+    relu_bn_bwd2_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(g, y, scale, C, numel / 4, out_pre, out_conv);
+    TTDG_LAUNCH_RET();
+}
 
 extern "C" int ttdg_relu_bn_bwd_bf16y(const float *g, const void *y_bf16, const float *scale, int C, int64_t numel, float *out, void *stream) {
     TTDG_CHECK_ARG(g && y_bf16 && out && C % 4 == 0 && numel % 4 == 0 && numel >= 0);

@@ -56,6 +56,7 @@ struct TcParams {
     int stem;                        // 7x7 stride-2 stem on the padded image: k-block r = filter row, box = 8-pixel windows
     int out_stride, outH, outW;      // output pixel (ho, wo) is stored at (ho, wo) * out_stride of an outH x outW map
     int a_tx;                        // bytes one activation box delivers: BW * BH * BI rows of 128 B (<= A_BYTES)
+    int chunk;                       // k-blocks per TMEM accumulation chunk (see TcCfg::CHUNK)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -296,12 +297,12 @@ __device__ __forceinline__ void tc_split_loop_tmem(const TcSmem &sm, uint32_t tm
 // epilogue warps: add the drained TMEM chunks (columns col0 .. col0 + EPI_COLS of lane group q) in registers
 // gc0: chunks this CTA has already drained (persistent conv kernel: the ping-pong continues across tiles)
 template <class Cfg>
-__device__ __forceinline__ void tc_drain(const TcSmem &sm, uint32_t tmem_base, int KB, int q, int col0, float (&acc)[Cfg::EPI_COLS],
+__device__ __forceinline__ void tc_drain(const TcSmem &sm, uint32_t tmem_base, int KB, int chunk, int q, int col0, float (&acc)[Cfg::EPI_COLS],
                                          uint32_t gc0 = 0) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int j = 0; j < Cfg::EPI_COLS; ++j) acc[j] = 0.f;
-    const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
+    const int nchunks = (KB + chunk - 1) / chunk;
     for (int ch = 0; ch < nchunks; ++ch) {
         const int buf = (int)((gc0 + ch) & 1u);
         mbar_wait(&sm.tmem_full[buf], ((gc0 + ch) >> 1) & 1u);
@@ -396,15 +397,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t fmt = BF16 ? 1u : 2u;
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN_TILE >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             uint32_t it = 0, gc = 0;                                             // k-blocks consumed, accumulation chunks issued
-            const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
+            const int CHK = p.chunk, nchunks = (KB + CHK - 1) / CHK;
             for (int item = clus; item < nitems; item += nclus) {
                 for (int ch = 0; ch < nchunks; ++ch, ++gc) {
                     const int buf = (int)(gc & 1u);
                     mbar_wait(&sm.tmem_empty[buf], ((gc >> 1) & 1u) ^ 1u);       // epilogue has drained this buffer
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t tacc = tmem_base + (uint32_t)(buf * BN_TILE);
-                    const int kb_end = min(KB, (ch + 1) * Cfg::CHUNK);
-                    for (int kb = ch * Cfg::CHUNK; kb < kb_end; ++kb, ++it) {
+                    const int kb_end = min(KB, (ch + 1) * CHK);
+                    for (int kb = ch * CHK; kb < kb_end; ++kb, ++it) {
                         const int stage = (int)(it % Cfg::STAGES);
                         const uint32_t phase = (it / Cfg::STAGES) & 1u;
                         mbar_wait(PRECISE ? &sm.conv[stage] : &sm.full[stage], phase);
@@ -415,7 +416,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
                             const uint32_t koff = k * TC_UMMA_K * 4;         // bytes inside the 128-byte swizzled row
-                            const uint32_t first = (kb != ch * Cfg::CHUNK) || k != 0;
+                            const uint32_t first = (kb != ch * CHK) || k != 0;
                             if (PRECISE) {
                                 umma_tf32_ts(tacc, ta + k * TC_UMMA_K, umma_desc(b + koff), idesc, first);
                                 umma_tf32_ts(tacc, ta + TC_BK + k * TC_UMMA_K, umma_desc(b + koff), idesc, 1);
@@ -446,7 +447,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int row = q * 32 + lane;                                       // GEMM row inside the tile = TMEM lane
         const int bi = row / (p.BH * p.BW), rem = row - bi * p.BH * p.BW;
         const int bh = rem / p.BW, bw = rem - bh * p.BW;
-        const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
+        const int nchunks = (KB + p.chunk - 1) / p.chunk;
         uint32_t gc = 0;
         for (int item = clus; item < nitems; item += nclus, gc += nchunks) {
             int w0, h0, i0, n0;
@@ -454,7 +455,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int img = i0 + bi, ho = h0 + bh, wo = w0 + bw;
             const bool ok = bi < p.BI && img < p.N && ho < p.Ho && wo < p.Wo;       // bi >= BI: rows past a box of < 128 pixels
             float acc[Cfg::EPI_COLS];
-            tc_drain<Cfg>(sm, tmem_base, KB, q, col0, acc, gc);
+            tc_drain<Cfg>(sm, tmem_base, KB, p.chunk, q, col0, acc, gc);
             if (ok) {
                 const size_t pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
                 const size_t opix = ((size_t)img * p.outH + ho * p.out_stride) * p.outW + wo * p.out_stride;
@@ -464,27 +465,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const __nv_bfloat16 *rrow16 = (p.res_mode && p.res_bf16) ? reinterpret_cast<const __nv_bfloat16 *>(p.residual) + rpix * p.Cout + nb : nullptr;
                 float *yrow = p.out_bf16 ? nullptr : reinterpret_cast<float *>(p.y) + opix * p.Cout + nb;
                 __nv_bfloat16 *yrow16 = p.out_bf16 ? reinterpret_cast<__nv_bfloat16 *>(p.y) + opix * p.Cout + nb : nullptr;
-#pragma unroll
-                for (int j = 0; j < Cfg::EPI_COLS; j += 4) {
-                    float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                // one pixel's EPI_COLS channels per thread; 16-byte accesses in both storage types (8 bf16 or 4 fp32 per access:
+                // neighbouring lanes are a whole row apart, so the access width is the sector efficiency)
+                auto finish = [&](int j, float4 o) -> float4 {
                     const int n = nb + j;
                     if (p.scale) { const float4 s4 = *reinterpret_cast<const float4 *>(p.scale + n); o.x *= s4.x; o.y *= s4.y; o.z *= s4.z; o.w *= s4.w; }
                     if (p.bias) { const float4 b4 = *reinterpret_cast<const float4 *>(p.bias + n); o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w; }
-                    if (rrow) { const float4 r4 = *reinterpret_cast<const float4 *>(rrow + j); o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
-                    if (rrow16) {
-                        const uint2 rr = *reinterpret_cast<const uint2 *>(rrow16 + j);
-                        const float2 r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rr.x));
-                        const float2 r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rr.y));
-                        o.x += r01.x; o.y += r01.y; o.z += r23.x; o.w += r23.y;
-                    }
+                    return o;
+                };
+                auto relu4 = [&](float4 o) -> float4 {
                     if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    return o;
+                };
+#pragma unroll
+                for (int j = 0; j < Cfg::EPI_COLS; j += 8) {
+                    float4 o0 = finish(j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+                    float4 o1 = finish(j + 4, make_float4(acc[j + 4], acc[j + 5], acc[j + 6], acc[j + 7]));
+                    if (rrow) {
+                        const float4 r0 = *reinterpret_cast<const float4 *>(rrow + j), r1 = *reinterpret_cast<const float4 *>(rrow + j + 4);
+                        o0.x += r0.x; o0.y += r0.y; o0.z += r0.z; o0.w += r0.w; o1.x += r1.x; o1.y += r1.y; o1.z += r1.z; o1.w += r1.w;
+                    }
+                    if (rrow16) {
+                        const uint4 rr = *reinterpret_cast<const uint4 *>(rrow16 + j);
+                        const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rr.x));
+                        const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rr.y));
+                        const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rr.z));
+                        const float2 a3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rr.w));
+                        o0.x += a0.x; o0.y += a0.y; o0.z += a1.x; o0.w += a1.y; o1.x += a2.x; o1.y += a2.y; o1.z += a3.x; o1.w += a3.y;
+                    }
+                    o0 = relu4(o0); o1 = relu4(o1);
                     if (yrow16) {
-                        const __nv_bfloat162 lo2 = __floats2bfloat162_rn(o.x, o.y), hi2 = __floats2bfloat162_rn(o.z, o.w);
-                        uint2 pk;
-                        pk.x = *reinterpret_cast<const uint32_t *>(&lo2); pk.y = *reinterpret_cast<const uint32_t *>(&hi2);
-                        *reinterpret_cast<uint2 *>(yrow16 + j) = pk;
+                        const __nv_bfloat162 q0 = __floats2bfloat162_rn(o0.x, o0.y), q1 = __floats2bfloat162_rn(o0.z, o0.w);
+                        const __nv_bfloat162 q2 = __floats2bfloat162_rn(o1.x, o1.y), q3 = __floats2bfloat162_rn(o1.z, o1.w);
+                        uint4 pk;
+                        pk.x = *reinterpret_cast<const uint32_t *>(&q0); pk.y = *reinterpret_cast<const uint32_t *>(&q1);
+                        pk.z = *reinterpret_cast<const uint32_t *>(&q2); pk.w = *reinterpret_cast<const uint32_t *>(&q3);
+                        *reinterpret_cast<uint4 *>(yrow16 + j) = pk;
                     } else {
-                        *reinterpret_cast<float4 *>(yrow + j) = o;
+                        *reinterpret_cast<float4 *>(yrow + j) = o0;
+                        *reinterpret_cast<float4 *>(yrow + j + 4) = o1;
                     }
                 }
             }
@@ -509,6 +528,7 @@ struct WgParams {
     int kblocks;                                 // patches in total
     int splits;
     int stride;                                  // 1, or 2 (1x1 convs): X is read through element strides {1, 2, 2, 1}
+    int chunk;                                   // k-blocks per TMEM accumulation chunk
     uint64_t desc_hi;                            // shared-memory descriptor without the start address (see umma_desc_mn)
 };
 
@@ -620,14 +640,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                                    ((uint32_t)(BN_TILE >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
-            const int nchunks = (KB + Cfg::CHUNK - 1) / Cfg::CHUNK;
+            const int CHK = p.chunk, nchunks = (KB + CHK - 1) / CHK;
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int buf = ch & 1;
                 mbar_wait(&sm.tmem_empty[buf], ((ch >> 1) & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * BN_TILE);
-                const int kend = min(KB, (ch + 1) * Cfg::CHUNK);
-                for (int kb = ch * Cfg::CHUNK; kb < kend; ++kb) {
+                const int kend = min(KB, (ch + 1) * CHK);
+                for (int kb = ch * CHK; kb < kend; ++kb) {
                     mbar_wait(PRECISE ? &sm.conv[stage] : &sm.full[stage], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a = smem_u32(sm.tiles + stage * Cfg::STAGE_BYTES), b = a + Cfg::A_BYTES;
@@ -636,7 +656,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {                            // 32 pixels = 4 MMAs of K = 8
                         const uint32_t koff = k * 1024;
-                        const uint32_t first = (kb != ch * Cfg::CHUNK) || k != 0;
+                        const uint32_t first = (kb != ch * CHK) || k != 0;
                         if (PRECISE) {
                             umma_tf32_ts(tacc, ta + k * 8, umma_desc_mn(b + koff, p.desc_hi), idesc, first);
                             umma_tf32_ts(tacc, ta + 32 + k * 8, umma_desc_mn(b + koff, p.desc_hi), idesc, 1);
@@ -657,7 +677,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int q = warp & 3, col0 = (warp >> 2) * Cfg::EPI_COLS;
         const int row = q * 32 + lane;                                       // input channel inside the tile
         float acc[Cfg::EPI_COLS];
-        tc_drain<Cfg>(sm, tmem_base, KB, q, col0, acc);
+        tc_drain<Cfg>(sm, tmem_base, KB, p.chunk, q, col0, acc);
         // staged like the conv epilogue: thread = input-channel row in phase 1, a warp per row in phase 2, so that each
         // reduction instruction adds 32 consecutive floats of dW (was: 32 rows Cout * 4 bytes apart)
         constexpr int PITCH = BN_TILE + 4;
@@ -805,6 +825,18 @@ static int tc_cluster_size() {
     return g_tc_cluster;
 }
 
+// k-blocks per accumulation chunk (TTDG_TC_CHUNK, default TcCfg::CHUNK): the tensor core truncates when it adds into the fp32
+// accumulator, the chunks are summed with round-to-nearest by the epilogue warps - smaller chunks = less truncation error
+static int tc_chunk() {
+    static int c = 0;
+    if (!c) {
+        const char *e = getenv("TTDG_TC_CHUNK");
+        c = e ? atoi(e) : 8;
+        if (c < 1 || c > 64) c = 8;
+    }
+    return c;
+}
+
 static int tc_sm_count() {
     static int n = 0;
     if (!n) {
@@ -892,6 +924,7 @@ extern "C" int ttdg_wgrad_tc(const float *x, const float *dy, int precise, int N
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     p.splits = splits;
+    p.chunk = tc_chunk();
     p.desc_hi = umma_desc_mn_hi(4096 >> 4, 512 >> 4, 1);
     CUtensorMap mx, md;
     const cuuint64_t xdims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -937,6 +970,7 @@ extern "C" int ttdg_stem_tc2(const float *x_pad, int Wp, const float *wk_hi, con
     p.BI = TC_BM / (p.BW * p.BH);
     p.tilesW = ceil_div(p.Wo, p.BW); p.tilesH = ceil_div(p.Ho, p.BH); p.tilesI = ceil_div(N, p.BI);
     p.a_tx = p.BW * p.BH * p.BI * 128;
+    p.chunk = tc_chunk();
     CUtensorMap ma, mb, mblo;
     const cuuint64_t adims[4] = {32, (cuuint64_t)p.Wo, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t astr[3] = {32, (cuuint64_t)Wp * 16, (cuuint64_t)H * Wp * 16};
@@ -1025,6 +1059,7 @@ static int conv_tc_impl(const void *x, const void *wk_hi, const void *wk_lo, con
         }
     }
     p.a_tx = p.BW * p.BH * p.BI * 128;
+    p.chunk = tc_chunk();
     CUtensorMap ma, mb, mblo;
     const cuuint64_t adims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint32_t abox[4] = {(cuuint32_t)KCH, (cuuint32_t)(p.BW * in_stride), (cuuint32_t)(p.BH * in_stride), (cuuint32_t)p.BI};

@@ -64,62 +64,88 @@ __device__ __forceinline__ void rpn_apply(const float a[4], const float *d, floa
     o[2] = __fadd_rn(pcx, __fmul_rn(0.5f, pw)); o[3] = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
 }
 
-// grid (levels, images), 1024 threads.  Radix select of the k-th largest logit (4 passes of 8 bits over the ordered key, shared
-// histogram), collection of the selected (key, anchor index) pairs, bitonic sort, anchor decoding.
+// grid (levels, images), 1024 threads.  Radix select of the k-th largest logit (3 digits of 11 / 11 / 10 bits of the ordered key,
+// run-length-aggregated shared histogram), collection of the selected (key, anchor index) pairs, bitonic sort, anchor decoding.
 __global__ void __launch_bounds__(1024)
 rpn_topk_decode_kernel(const __grid_constant__ RpnSelParams p) {
     __shared__ unsigned long long sel[SEL_TOPK_CAP];
-    __shared__ unsigned int hist[256];
+    __shared__ unsigned int hist[2048];
     __shared__ unsigned int s_prefix, s_remaining, s_cnt, s_tie_base;
     __shared__ unsigned int warp_off[32];
     const int l = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
     const int HW = p.H[l] * p.W[l], A = p.A, T = HW * A, k = p.k[l];
     const float *lg = p.logits[l] + (size_t)n * HW * p.ld_logits;
     if (k <= 0) return;
-    unsigned int kth = 0u, need_eq = 0u;              // k-th largest key; how many elements EQUAL to it are selected
+    unsigned int kth = 0u, need_eq = 0u, n_eq = 0u;   // k-th largest key; how many elements EQUAL to it are selected / exist
     bool all = T <= k;
     if (!all) {
         if (tid == 0) { s_prefix = 0u; s_remaining = (unsigned)k; }
-        for (int pass = 3; pass >= 0; --pass) {
-            for (int b = tid; b < 256; b += 1024) hist[b] = 0u;
+        // three digits of 11 / 11 / 10 bits (sign + exponent + 2 mantissa bits first: logits of one map share their top BYTE, so
+        // an 8-bit first digit would resolve nothing and every pass would rescan everything at full contention)
+        for (int pass = 2; pass >= 0; --pass) {
+            const int shift = pass == 2 ? 21 : (pass == 1 ? 10 : 0), bits = pass == 0 ? 10 : 11;
+            for (int b = tid; b < 2048; b += 1024) hist[b] = 0u;
             __syncthreads();
-            const unsigned int prefix = s_prefix, hmask = pass == 3 ? 0u : (0xFFFFFFFFu << (8 * (pass + 1)));
+            const unsigned int prefix = s_prefix, hmask = pass == 2 ? 0u : (0xFFFFFFFFu << (shift + bits));
+            // run-length aggregation in registers: the 15 anchors of a pixel and neighbouring pixels of a thread mostly fall into the
+            // same coarse bin, so a thread issues one shared-memory atomic per RUN instead of one per element
+            unsigned int run_bin = 0xFFFFFFFFu, run_cnt = 0u;
             for (int pix = tid; pix < HW; pix += 1024) {
                 const float *row = lg + (size_t)pix * p.ld_logits;
                 for (int a = 0; a < A; ++a) {
                     const unsigned int key = f32_ord(row[a]);
-                    if ((key & hmask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1u);
+                    if ((key & hmask) == prefix) {
+                        const unsigned int bin = (key >> shift) & ((1u << bits) - 1u);
+                        if (bin == run_bin) ++run_cnt;
+                        else { if (run_cnt) atomicAdd(&hist[run_bin], run_cnt); run_bin = bin; run_cnt = 1u; }
+                    }
+                }
+            }
+            if (run_cnt) atomicAdd(&hist[run_bin], run_cnt);
+            __syncthreads();
+            if (tid < 32) {                           // warp 0: the bin where the running count from the top reaches `remaining`
+                unsigned int rem = s_remaining;
+                const int nb = 1 << bits, per = nb / 32;
+                unsigned int mine = 0u;               // lane l owns bins [nb - (l + 1) * per, nb - l * per): lane 0 = the top bins
+                for (int q = 0; q < per; ++q) mine += hist[nb - 1 - (tid * per + q)];
+                unsigned int incl = mine;
+                for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(TTDG_FULL, incl, o); if (tid >= o) incl += t; }
+                const unsigned int excl = incl - mine;
+                const unsigned int hit = __ballot_sync(TTDG_FULL, incl >= rem);
+                const int owner = hit ? __ffs(hit) - 1 : 31;
+                if (tid == owner) {
+                    unsigned int r = rem - excl;
+                    int b = nb - 1 - tid * per;
+                    for (int q = 0; q < per - 1; ++q, --b) { if (hist[b] >= r) break; r -= hist[b]; }
+                    s_prefix = prefix | ((unsigned)b << shift);
+                    s_remaining = r;                  // elements still to take inside bin b
+                    if (pass == 0) s_cnt = hist[b];   // (scratch) how many elements carry exactly the k-th key
                 }
             }
             __syncthreads();
-            if (tid == 0) {
-                unsigned int rem = s_remaining;
-                int b = 255;
-                for (; b > 0; --b) { if (hist[b] >= rem) break; rem -= hist[b]; }
-                s_prefix = prefix | ((unsigned)b << (8 * pass));
-                s_remaining = rem;                    // elements still to take inside bin b
-            }
-            __syncthreads();
         }
-        kth = s_prefix; need_eq = s_remaining;
+        kth = s_prefix; need_eq = s_remaining; n_eq = s_cnt;
+        __syncthreads();
     }
-    // ---- collect: everything above the threshold (any order: the sort below fixes it), then exactly need_eq ties by lowest index
+    // ---- collect: everything above the threshold (any order: the sort below fixes it); the ties too when all of them are taken
+    const bool ties_all = !all && n_eq == need_eq;
     if (tid == 0) { s_cnt = 0u; s_tie_base = 0u; }
     __syncthreads();
     for (int pix = tid; pix < HW; pix += 1024) {
         const float *row = lg + (size_t)pix * p.ld_logits;
         for (int a = 0; a < A; ++a) {
             const unsigned int key = f32_ord(row[a]);
-            if (all || key > kth) {
+            if (all || key > kth || (ties_all && key == kth)) {
                 const unsigned int pos = atomicAdd(&s_cnt, 1u);
                 if (pos < SEL_TOPK_CAP) sel[pos] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(pix * A + a));
             }
         }
     }
     __syncthreads();
-    if (!all) {
+    if (!all && !ties_all) {
+        // more candidates tied at the k-th value than slots left: exactly need_eq of them by lowest index (deterministic) -
+        // chunks of 1024 consecutive elements, block-wide exclusive scan of the tie flags
         const unsigned int n_gt = s_cnt;
-        // ties in index order: chunks of 1024 consecutive elements, block-wide exclusive scan of the tie flags
         for (int base = 0; base < T && s_tie_base < need_eq; base += 1024) {
             const int e = base + tid;
             bool tie = false;

@@ -46,6 +46,7 @@ SIGNATURES = {
     "ttdg_conv_dgrad": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     "ttdg_conv_wgrad": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     "ttdg_relu_bn_bwd": (c_int, [P, P, P, c_int, c_int64, P, P]),
+    "ttdg_relu_bn_bwd2": (c_int, [P, P, P, c_int, c_int64, P, P, P]),
     "ttdg_bias_grad": (c_int, [P, c_int64, c_int, P, P]),
     "ttdg_maxpool3x3s2": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "ttdg_resample2": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),

@@ -201,14 +201,34 @@ class _ConvFn(torch.autograd.Function):
         x_dtype = x.dtype
         g = g.float().contiguous() if g.dtype != torch.float32 else g.contiguous()
         s = _stream()
-        if relu:                                           # dPre = g * [y > 0]
-            d_pre = torch.empty_like(g)
-            if y.dtype == torch.bfloat16:
-                check(L.ttdg_relu_bn_bwd_bf16y(_p(g), _p(y), None, Cout, g.numel(), _p(d_pre), s), "relu_bwd_bf16y")
+        # ReLU mask (from the stored output) and FrozenBN scale: ONE elementwise pass.  d_pre = g * [y > 0] is only materialised
+        # when something consumes it (a residual branch, a bias gradient); d_conv = d_pre * scale feeds dgrad / wgrad.
+        need_pre = res_grad or (has_bias and ctx.needs_input_grad[2])
+        d_pre = d_conv = None
+        if relu and scale is not None and y.dtype == torch.float32:
+            d_conv = torch.empty_like(g)
+            if need_pre:
+                d_pre = torch.empty_like(g)
+                check(L.ttdg_relu_bn_bwd2(_p(g), _p(y), _p(scale), Cout, g.numel(), _p(d_pre), _p(d_conv), s), "relu_bn_bwd2")
             else:
-                check(L.ttdg_relu_bn_bwd(_p(g), _p(y), None, Cout, g.numel(), _p(d_pre), s), "relu_bwd")
+                check(L.ttdg_relu_bn_bwd(_p(g), _p(y), _p(scale), Cout, g.numel(), _p(d_conv), s), "relu_bn_bwd")
+        elif relu and scale is not None and not need_pre:      # bf16 backbone: mask from the stored bf16 output, same single pass
+            d_conv = torch.empty_like(g)
+            check(L.ttdg_relu_bn_bwd_bf16y(_p(g), _p(y), _p(scale), Cout, g.numel(), _p(d_conv), s), "relu_bn_bwd_bf16y")
         else:
-            d_pre = g
+            if relu:                                       # dPre = g * [y > 0]
+                d_pre = torch.empty_like(g)
+                if y.dtype == torch.bfloat16:
+                    check(L.ttdg_relu_bn_bwd_bf16y(_p(g), _p(y), None, Cout, g.numel(), _p(d_pre), s), "relu_bwd_bf16y")
+                else:
+                    check(L.ttdg_relu_bn_bwd(_p(g), _p(y), None, Cout, g.numel(), _p(d_pre), s), "relu_bwd")
+            else:
+                d_pre = g
+            if scale is not None:                          # through the FrozenBN scale
+                d_conv = torch.empty_like(d_pre)
+                check(L.ttdg_relu_bn_bwd(_p(d_pre), None, _p(scale), Cout, d_pre.numel(), _p(d_conv), s), "bn_bwd")
+            else:
+                d_conv = d_pre
         g_res = None
         if res_grad:
             if res_mode == 1:
@@ -232,11 +252,6 @@ class _ConvFn(torch.autograd.Function):
             gb = acc_b if acc_b is not None else torch.zeros(Cout, dtype=torch.float32, device=g.device)
             check(L.ttdg_bias_grad(_p(d_pre), d_pre.numel() // Cout, Cout, _p(gb), s), "bias_grad")
             g_bias = None if acc_b is not None else gb
-        if scale is not None:                              # through the FrozenBN scale
-            d_conv = torch.empty_like(d_pre)
-            check(L.ttdg_relu_bn_bwd(_p(d_pre), None, _p(scale), Cout, d_pre.numel(), _p(d_conv), s), "bn_bwd")
-        else:
-            d_conv = d_pre
         g_x = g_w = None
         if ctx.needs_input_grad[0]:
             g_x = (torch.zeros if stride == 2 else torch.empty)(N, H, W, Cin, dtype=torch.float32, device=g.device)
