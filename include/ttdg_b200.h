@@ -268,6 +268,16 @@ int ttdg_conv_tc_supported(int Cin, int Cout, int stride);
  * loads 1/cl of it and TMA multicasts the slice to all of them.  cl = 1 (default; also env TTDG_TC_CLUSTER), 2 or 4.
  * Results do not depend on it.  Returns the previous value, or TTDG_E_ARG. */
 int ttdg_conv_tc_set_cluster(int cl);
+/* Epilogue of ttdg_conv_tc / ttdg_conv_tc_bf16 / ttdg_stem_tc (env TTDG_TC_EPI): 1 = each epilogue warp transposes its 32
+ * pixel rows through 4 KB of shared memory so that global loads (residual) and stores are 128-byte row segments; 0 = every
+ * thread stores its own pixel row (32 lines per warp access); 2 (default) = chosen per layer.  Same arithmetic in the same
+ * order: results are bit-identical.  Returns the previous value, or TTDG_E_ARG. */
+int ttdg_conv_tc_set_epilogue(int mode);
+/* Diagnostics: while dev_buf != NULL, CTA 0 of every ttdg_conv_tc* launch records clock64() at 8 points of its first `items`
+ * tiles into dev_buf[item * 8 + slot] (slot 0 / 1: first / last k-block's TMA issue, 2: MMA warp owns the accumulator,
+ * 3: last k-block's operands ready, 4: last commit issued, 7 / 5 / 6: epilogue warp 0 starts the tile / has drained the
+ * accumulator / has issued its stores).  dev_buf = NULL or items = 0 switches it off (the default). */
+int ttdg_conv_tc_set_trace(long long *dev_buf, int items);
 int ttdg_conv_tc(const float *x, const float *wk_hi, const float *wk_lo, const float *scale, const float *bias,
                  const float *residual, int res_mode, int relu, int flip, int N, int H, int W, int Cin, int Cout, int R,
                  int S, int pad, int in_stride, int out_stride, int outH, int outW, float *y, void *stream);

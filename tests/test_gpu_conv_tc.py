@@ -264,3 +264,43 @@ def test_conv_tc_cluster_multicast(cl, cin, cout, k, pad, H, W, N):
         L.ttdg_conv_tc_set_cluster(prev)
     assert torch.equal(y1, y2)
     assert L.ttdg_conv_tc_set_cluster(3) == -1
+
+
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32", "bf16"])
+@pytest.mark.parametrize("cin,cout,k,pad,stride,H,W,N,res", [
+    (64, 256, 1, 0, 1, 40, 24, 2, 1),        # short-K 1x1 with residual (the layers the transposed epilogue is for)
+    (256, 64, 1, 0, 1, 32, 32, 2, 0),        # 64-wide N tile
+    (256, 256, 3, 1, 1, 14, 14, 7, 0),       # 14 x 14 boxes: 126 of the 128 tile rows, partial last image group
+    (256, 512, 1, 0, 2, 26, 38, 1, 0),       # strided 1x1 (TMA element strides), ragged tiles
+    (128, 128, 3, 1, 1, 19, 23, 3, 1),       # ragged tiles with residual
+])
+def test_conv_tc_transposed_epilogue_is_bit_identical(mode, cin, cout, k, pad, stride, H, W, N, res):
+    """The warp-transposed (coalesced) epilogue performs the same operations per element as the row-per-thread one: both
+    must give the same bits for fp32 and bf16 outputs / residuals, every box shape and ragged tiles."""
+    from ttdg_b200 import _C
+    det.set_conv_mode(mode)
+    try:
+        g = torch.Generator().manual_seed(cin + cout + H)
+        layer = det.Conv2d(cin, cout, k, stride, pad, bias=True).cuda()
+        layer.load_state_dict({"weight": torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5, "bias": torch.randn(cout, generator=g)})
+        x = nhwc(torch.randn(N, cin, H, W, generator=g)).cuda()
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        r = torch.randn(N, Ho, Wo, cout, generator=g).cuda() if res else None
+        if mode == "bf16":
+            x = x.to(torch.bfloat16)
+            r = r.to(torch.bfloat16) if res else None
+        L = _C.lib()
+        prev = L.ttdg_conv_tc_set_epilogue(0)
+        try:
+            with torch.no_grad():
+                y0 = layer(x, relu=True, residual=r, res_mode=int(res))
+                assert L.ttdg_conv_tc_set_epilogue(1) == 0
+                y1 = layer(x, relu=True, residual=r, res_mode=int(res))
+            torch.cuda.synchronize()
+        finally:
+            L.ttdg_conv_tc_set_epilogue(prev)
+        assert y0.dtype == y1.dtype and torch.equal(y0, y1)
+        assert float(y0.float().abs().sum()) > 0
+        assert L.ttdg_conv_tc_set_epilogue(3) == -1
+    finally:
+        det.set_conv_mode("tf32x3")

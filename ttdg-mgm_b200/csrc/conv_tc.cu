@@ -57,7 +57,11 @@ struct TcParams {
     int out_stride, outH, outW;      // output pixel (ho, wo) is stored at (ho, wo) * out_stride of an outH x outW map
     int a_tx;                        // bytes one activation box delivers: BW * BH * BI rows of 128 B (<= A_BYTES)
     int chunk;                       // k-blocks per TMEM accumulation chunk (see TcCfg::CHUNK)
+    int epi;                         // 1: warp-transposed (coalesced) epilogue, 0: one pixel row per thread straight to global
+    long long *trace;                // optional: CTA 0 records clock64() at 8 points of its first trace_items tiles
+    int trace_items;
 };
+#define TC_TRACE(li, slot) do { if (p.trace && blockIdx.x == 0 && (li) < p.trace_items) p.trace[(li) * 8 + (slot)] = clock64(); } while (0)
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,6 +146,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// explicit shared-space accesses: the tile / staging pointers are carved out of the dynamic shared memory through integer
+// arithmetic, which hides the address space from the compiler (it emitted generic LD.E / ST.E - long-scoreboard loads)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const float4 &v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // 3xTF32 operand split INSIDE the pipeline.  TMA lands the raw fp32 activations; the four split warps rewrite the tile in
 // place as hi = tf32(x) and store lo = x - hi at the same offset of the stage's "lo" half, then hand the stage to the
 // MMA warp.  Elementwise on the raw bytes, so it is independent of the swizzle; activations are read from HBM once as
@@ -151,15 +166,15 @@ __device__ __forceinline__ void split_stage(unsigned char *raw, unsigned char *l
     static_assert(BYTES % (TC_CVT_THREADS * 16) == 0, "tile must divide over the split warps");
 #pragma unroll
     for (int off = 0; off < BYTES; off += TC_CVT_THREADS * 16) {
-        const float4 v = *reinterpret_cast<const float4 *>(raw + off + t * 16);
+        const float4 v = lds128(smem_u32(raw) + off + t * 16);
         float4 h, l;
         uint32_t u;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
-        *reinterpret_cast<float4 *>(raw + off + t * 16) = h;
-        *reinterpret_cast<float4 *>(lo + off + t * 16) = l;
+        sts128(smem_u32(raw) + off + t * 16, h);
+        sts128(smem_u32(lo) + off + t * 16, l);
     }
 }
 
@@ -170,6 +185,30 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// issue only: the registers are valid after tmem_ld_wait() + tmem_ld_pin() of the same registers
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]), "=f"(r[9]),
+          "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// orders every later use of these registers after the preceding (volatile) wait
+__device__ __forceinline__ void tmem_ld_pin(float *r) {
+    asm volatile("" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]), "+f"(r[8]), "+f"(r[9]),
+                      "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]));
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
@@ -184,14 +223,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 // chunk c sits at chunk position c ^ (row & 7)), and stores hi = tf32(x) into columns [a_col, a_col + 32) and
 // lo = x - hi into [a_col + 32, a_col + 64) of its lane.
 __device__ __forceinline__ void split_stage_tmem(const unsigned char *raw, uint32_t tmem_row, int t) {
-    const unsigned char *rowp = raw + t * 128;
+    const uint32_t rowp = smem_u32(raw) + t * 128;
     const int sw = t & 7;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const float4 v = *reinterpret_cast<const float4 *>(rowp + (((half * 4 + c) ^ sw) << 4));
+            const float4 v = lds128(rowp + (((half * 4 + c) ^ sw) << 4));
             const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -218,7 +257,10 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = A_BYTES + (PRECISE ? 2 : 1) * B_BYTES;
     static constexpr int TX_BYTES = STAGE_BYTES;                                     // what TMA delivers per stage
     static constexpr int STAGES = PRECISE ? (BN_TILE == 128 ? 4 : 6) : (BN_TILE == 128 ? 6 : 8);
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+    // epilogue staging: 4 KB per epilogue warp (32 pixel rows x 32 fp32 channels, 128-byte swizzled) - see the epilogue
+    static constexpr int EPI_BYTES = TC_EPI_WARPS * 4096;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static constexpr int ACC_COLS = 2 * BN_TILE;         // two accumulator buffers (ping-pong between MMA and epilogue)
     static constexpr int A_COLS = 2 * TC_BK;             // TMEM columns of one stage's A operand: 32 hi + 32 lo
     static constexpr int TMEM_COLS = PRECISE ? 512 : ACC_COLS;      // power of two >= ACC_COLS + STAGES * A_COLS
@@ -232,7 +274,7 @@ struct TcCfg {
 };
 
 struct TcSmem {
-    unsigned char *tiles;
+    unsigned char *tiles, *epi;
     uint64_t *full, *empty, *conv, *tmem_full, *tmem_empty;
     uint32_t *tmem_slot;
 };
@@ -241,7 +283,8 @@ struct TcSmem {
 template <class Cfg, int CL = 1>
 __device__ __forceinline__ uint32_t tc_prologue(TcSmem &sm, unsigned char *raw_smem) {
     sm.tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(raw_smem) + 1023) & ~(uintptr_t)1023);
-    sm.full = reinterpret_cast<uint64_t *>(sm.tiles + Cfg::STAGES * Cfg::STAGE_BYTES);
+    sm.epi = sm.tiles + Cfg::STAGES * Cfg::STAGE_BYTES;
+    sm.full = reinterpret_cast<uint64_t *>(sm.epi + Cfg::EPI_BYTES);
     sm.empty = sm.full + Cfg::STAGES;
     sm.conv = sm.empty + Cfg::STAGES;
     sm.tmem_full = sm.conv + Cfg::STAGES;                // [2]
@@ -300,23 +343,44 @@ template <class Cfg>
 __device__ __forceinline__ void tc_drain(const TcSmem &sm, uint32_t tmem_base, int KB, int chunk, int q, int col0, float (&acc)[Cfg::EPI_COLS],
                                          uint32_t gc0 = 0) {
     const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int j = 0; j < Cfg::EPI_COLS; ++j) acc[j] = 0.f;
     const int nchunks = (KB + chunk - 1) / chunk;
-    for (int ch = 0; ch < nchunks; ++ch) {
-        const int buf = (int)((gc0 + ch) & 1u);
-        mbar_wait(&sm.tmem_full[buf], ((gc0 + ch) >> 1) & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
+    if (nchunks <= 0) {
 #pragma unroll
-        for (int c0 = 0; c0 < Cfg::EPI_COLS; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * (Cfg::ACC_COLS / 2) + col0 + c0), v);   // warp-collective
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);                      // round-to-nearest fp32
-        }
+        for (int j = 0; j < Cfg::EPI_COLS; ++j) acc[j] = 0.f;
+        return;
+    }
+    auto release = [&](int buf) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.tmem_empty[buf])) : "memory");
+    };
+    {
+        // first chunk: all loads in flight at once, straight into the accumulator registers
+        const int buf = (int)(gc0 & 1u);
+        mbar_wait(&sm.tmem_full[buf], (gc0 >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tbuf = tlane + (uint32_t)(buf * (Cfg::ACC_COLS / 2));
+#pragma unroll
+        for (int c0 = 0; c0 < Cfg::EPI_COLS; c0 += 16) tmem_ld16_nowait(tbuf + c0, acc + c0);              // warp-collective
+        tmem_ld_wait();
+#pragma unroll
+        for (int c0 = 0; c0 < Cfg::EPI_COLS; c0 += 16) tmem_ld_pin(acc + c0);
+        release(buf);
+    }
+    for (int ch = 1; ch < nchunks; ++ch) {
+        const int buf = (int)((gc0 + ch) & 1u);
+        mbar_wait(&sm.tmem_full[buf], ((gc0 + ch) >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tbuf = tlane + (uint32_t)(buf * (Cfg::ACC_COLS / 2));
+#pragma unroll
+        for (int c0 = 0; c0 < Cfg::EPI_COLS; c0 += 16) {                                              // x16: 16 temporaries beside acc
+            uint32_t v[16];
+            tmem_ld16(tbuf + c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(v[j]);                        // round-to-nearest fp32
+        }
+        release(buf);
     }
 }
 
@@ -367,6 +431,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int item = clus; item < nitems; item += nclus) {
                 int w0, h0, i0, n0;
                 decode(item, w0, h0, i0, n0);
+                const int li = (item - clus) / nclus;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int stage = (int)(it % Cfg::STAGES);
                     const uint32_t phase = (it / Cfg::STAGES) & 1u;
@@ -374,6 +439,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int r = tap / p.S, s = tap - r * p.S;
                     const int btap = p.flip ? (p.R - 1 - r) * p.S + (p.S - 1 - s) : tap;
                     mbar_wait(&sm.empty[stage], phase ^ 1);
+                    if (kb == 0) TC_TRACE(li, 0);
+                    if (kb == KB - 1) TC_TRACE(li, 1);
                     unsigned char *st = sm.tiles + stage * Cfg::STAGE_BYTES;
                     mbar_expect_tx(&sm.full[stage], (uint32_t)(p.a_tx + (PRECISE ? 2 : 1) * Cfg::B_BYTES));
                     if (p.stem) tma_load_4d(st, &tmA, &sm.full[stage], 0, w0, 2 * h0 + r - 3, i0);
@@ -399,9 +466,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t it = 0, gc = 0;                                             // k-blocks consumed, accumulation chunks issued
             const int CHK = p.chunk, nchunks = (KB + CHK - 1) / CHK;
             for (int item = clus; item < nitems; item += nclus) {
+                const int li = (item - clus) / nclus;
                 for (int ch = 0; ch < nchunks; ++ch, ++gc) {
                     const int buf = (int)(gc & 1u);
                     mbar_wait(&sm.tmem_empty[buf], ((gc >> 1) & 1u) ^ 1u);       // epilogue has drained this buffer
+                    if (ch == 0) TC_TRACE(li, 2);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t tacc = tmem_base + (uint32_t)(buf * BN_TILE);
                     const int kb_end = min(KB, (ch + 1) * CHK);
@@ -410,6 +479,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t phase = (it / Cfg::STAGES) & 1u;
                         mbar_wait(PRECISE ? &sm.conv[stage] : &sm.full[stage], phase);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (kb == KB - 1) TC_TRACE(li, 3);
                         const uint32_t a = smem_u32(sm.tiles + stage * Cfg::STAGE_BYTES), b = a + Cfg::A_BYTES;
                         const uint32_t blo = b + Cfg::B_BYTES;
                         const uint32_t ta = tmem_base + (uint32_t)(Cfg::ACC_COLS + stage * Cfg::A_COLS);  // A hi | A lo (3xTF32)
@@ -431,6 +501,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         else umma_commit_mc(&sm.empty[stage], CL_MASK);      // ... in every CTA of the cluster
                     }
                     umma_commit(&sm.tmem_full[buf]);                         // this chunk's accumulator is complete
+                    if (ch == nchunks - 1) TC_TRACE(li, 4);
                 }
             }
         }
@@ -454,6 +525,123 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             decode(item, w0, h0, i0, n0);
             const int img = i0 + bi, ho = h0 + bh, wo = w0 + bw;
             const bool ok = bi < p.BI && img < p.N && ho < p.Ho && wo < p.Wo;       // bi >= BI: rows past a box of < 128 pixels
+            if (p.epi) {
+                // ---- warp-transposed epilogue.  tcgen05.ld hands each thread one pixel ROW of the accumulator; a thread that
+                // stores its row straight to global makes every 16-byte access of a warp touch 32 different 128-byte lines
+                // (ncu / B200: ~2 cycles of the L1 wavefront pipe per line - 8 warps x 16 stores x 32 lines = 4 us per tile, twice
+                // that with a residual: the short-K 1x1 layers ran at 1.8-2 TB/s).  Instead each warp transposes through its own
+                // 4 KB of shared memory, 32 fp32 channels at a time: phase 1, thread = pixel row writes FrozenBN(acc) as 8 chunks
+                // of 16 B at chunk position c ^ (row & 7) (conflict-free); phase 2, 8 lanes = one 128-byte row segment, 4 rows
+                // per instruction: read back, add the residual (loaded with the same coalesced pattern, issued before the
+                // accumulator is waited for), ReLU, store.  Only __syncwarp between the phases - no CTA barrier.
+                constexpr int HALVES = Cfg::EPI_COLS / 32;
+                const uint32_t stg = smem_u32(sm.epi) + warp * 4096;
+                const int sub = lane >> 3, ch = lane & 7;
+                const size_t pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
+                const size_t opix = ((size_t)img * p.outH + ho * p.out_stride) * p.outW + wo * p.out_stride;
+                const size_t rpix = p.res_mode == 2 ? (((size_t)img * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) : pix;
+                const int my_op = ok ? (int)opix : -1, my_rp = (int)rpix;
+                const int nb = n0 + col0;
+                const bool has_res = p.res_mode != 0;
+                // residual rows of phase 2 (8 lanes = one row's 128 bytes), loaded as raw 16 bytes (bf16: 8) per lane.  Half 0 is
+                // issued BEFORE the accumulator is waited for - nothing else is live in registers then, and the DRAM latency
+                // hides behind the MMAs of this tile; half h + 1 is issued once phase 1 of half h has retired its 32 accumulators.
+                auto load_res = [&](int h, uint4 (&rs)[8]) {
+                    const int n = nb + h * 32 + ch * 4;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int o_i = __shfl_sync(0xffffffffu, my_op, i * 4 + sub), r_i = __shfl_sync(0xffffffffu, my_rp, i * 4 + sub);
+                        rs[i] = make_uint4(0u, 0u, 0u, 0u);
+                        if (has_res && o_i >= 0) {
+                            if (p.res_bf16) {
+                                const uint2 t2 = *reinterpret_cast<const uint2 *>(reinterpret_cast<const __nv_bfloat16 *>(p.residual) + (size_t)r_i * p.Cout + n);
+                                rs[i].x = t2.x; rs[i].y = t2.y;
+                            } else {
+                                rs[i] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const float *>(p.residual) + (size_t)r_i * p.Cout + n);
+                            }
+                        }
+                    }
+                };
+                uint4 rs[HALVES][8];
+                const int li = (item - clus) / nclus;
+                if (threadIdx.x == 0) TC_TRACE(li, 7);
+                load_res(0, rs[0]);
+                float acc[Cfg::EPI_COLS];
+                tc_drain<Cfg>(sm, tmem_base, KB, p.chunk, q, col0, acc, gc);
+                if (threadIdx.x == 0) TC_TRACE(li, 5);
+#pragma unroll
+                for (int h = 0; h < HALVES; ++h) {
+                    // phase 1: thread = pixel row
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int j = h * 32 + c * 4;
+                        sts128(stg + lane * 128 + ((c ^ (lane & 7)) << 4), make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+                    }
+                    __syncwarp();
+                    // phase 2: 8 lanes = one row's 128 bytes, 4 rows per instruction; a lane serves the same 4 channels in every
+                    // row, so FrozenBN scale / bias are two 16-byte loads per half instead of two per 4 accumulators.  Straight-line
+                    // code, 4 rows in flight: the per-layer options are applied as arithmetic identities (scale 1, bias 0,
+                    // residual 0 - bit-neutral) or selects, not branches - the tile epilogue is a dependent instruction chain and
+                    // its length, not memory, is what the short-K layers wait for (tools/conv_layer.py timeline).
+                    const int n = nb + h * 32 + ch * 4;
+                    float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.scale) s4 = __ldg(reinterpret_cast<const float4 *>(p.scale + n));
+                    if (p.bias) b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
+                    const bool r16 = p.res_bf16 != 0, relu = p.relu != 0;
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        float4 o[4];
+                        int oi[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int r2 = (g * 4 + k) * 4 + sub;
+                            oi[k] = __shfl_sync(0xffffffffu, my_op, r2);
+                            o[k] = lds128(stg + r2 * 128 + ((ch ^ (r2 & 7)) << 4));
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint4 rr = rs[h][g * 4 + k];
+                            // bf16 residual: 4 values in rr.x / rr.y (low half first); fp32: rr.x .. rr.w
+                            const float a0 = __uint_as_float(r16 ? rr.x << 16 : rr.x), a1 = __uint_as_float(r16 ? rr.x & 0xffff0000u : rr.y);
+                            const float a2 = __uint_as_float(r16 ? rr.y << 16 : rr.z), a3 = __uint_as_float(r16 ? rr.y & 0xffff0000u : rr.w);
+                            o[k].x = __fadd_rn(__fadd_rn(__fmul_rn(o[k].x, s4.x), b4.x), a0);
+                            o[k].y = __fadd_rn(__fadd_rn(__fmul_rn(o[k].y, s4.y), b4.y), a1);
+                            o[k].z = __fadd_rn(__fadd_rn(__fmul_rn(o[k].z, s4.z), b4.z), a2);
+                            o[k].w = __fadd_rn(__fadd_rn(__fmul_rn(o[k].w, s4.w), b4.w), a3);
+                            if (relu) { o[k].x = fmaxf(o[k].x, 0.f); o[k].y = fmaxf(o[k].y, 0.f); o[k].z = fmaxf(o[k].z, 0.f); o[k].w = fmaxf(o[k].w, 0.f); }
+                        }
+                        if (p.out_bf16) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const __nv_bfloat162 q0 = __floats2bfloat162_rn(o[k].x, o[k].y), q1 = __floats2bfloat162_rn(o[k].z, o[k].w);
+                                uint2 pk;
+                                pk.x = *reinterpret_cast<const uint32_t *>(&q0); pk.y = *reinterpret_cast<const uint32_t *>(&q1);
+                                if (oi[k] >= 0) *reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(p.y) + (size_t)oi[k] * p.Cout + n) = pk;
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (oi[k] >= 0) *reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.y) + (size_t)oi[k] * p.Cout + n) = o[k];
+                        }
+                        // the next half's residual: issued once half of this half's registers are free again
+                        if (g == 0 && h + 1 < HALVES) load_res(h + 1, rs[h + 1 < HALVES ? h + 1 : h]);
+                    }
+                    __syncwarp();
+                }
+                if (threadIdx.x == 0) TC_TRACE(li, 6);
+                continue;
+            }
+            if (ok && p.res_mode) {
+                // this thread's residual row segment towards L2 while the MMAs of the tile are still running: the loads below
+                // are a chain of round trips (the compiler may not hoist them over the stores)
+                const size_t pix0 = ((size_t)img * p.Ho + ho) * p.Wo + wo;
+                const size_t rpix0 = p.res_mode == 2 ? (((size_t)img * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) : pix0;
+                const int esz = p.res_bf16 ? 2 : 4;
+                const char *rb = reinterpret_cast<const char *>(p.residual) + (rpix0 * p.Cout + n0 + col0) * esz;
+#pragma unroll
+                for (int b = 0; b < Cfg::EPI_COLS * 4; b += 128)
+                    if (b < Cfg::EPI_COLS * esz) asm volatile("prefetch.global.L2 [%0];" ::"l"(rb + b));
+            }
             float acc[Cfg::EPI_COLS];
             tc_drain<Cfg>(sm, tmem_base, KB, p.chunk, q, col0, acc, gc);
             if (ok) {
@@ -477,12 +665,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                     return o;
                 };
+                // fp32 residual: the loads run one iteration ahead of the stores (issued by hand - see above)
+                float4 rn0 = make_float4(0.f, 0.f, 0.f, 0.f), rn1 = rn0;
+                if (rrow) { rn0 = *reinterpret_cast<const float4 *>(rrow); rn1 = *reinterpret_cast<const float4 *>(rrow + 4); }
 #pragma unroll
                 for (int j = 0; j < Cfg::EPI_COLS; j += 8) {
                     float4 o0 = finish(j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
                     float4 o1 = finish(j + 4, make_float4(acc[j + 4], acc[j + 5], acc[j + 6], acc[j + 7]));
                     if (rrow) {
-                        const float4 r0 = *reinterpret_cast<const float4 *>(rrow + j), r1 = *reinterpret_cast<const float4 *>(rrow + j + 4);
+                        const float4 r0 = rn0, r1 = rn1;
+                        if (j + 8 < Cfg::EPI_COLS) { rn0 = *reinterpret_cast<const float4 *>(rrow + j + 8); rn1 = *reinterpret_cast<const float4 *>(rrow + j + 12); }
                         o0.x += r0.x; o0.y += r0.y; o0.z += r0.z; o0.w += r0.w; o1.x += r1.x; o1.y += r1.y; o1.z += r1.z; o1.w += r1.w;
                     }
                     if (rrow16) {
@@ -540,6 +732,7 @@ struct WgCfg {
     static constexpr int STAGE_BYTES = A_BYTES + (PRECISE ? 2 : 1) * B_BYTES;
     static constexpr int TX_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = PRECISE ? (BN_TILE == 128 ? 4 : 6) : (BN_TILE == 128 ? 6 : 8);
+    static constexpr int EPI_BYTES = 0;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
     static constexpr int ACC_COLS = 2 * BN_TILE;
     static constexpr int A_COLS = 64;                    // TMEM columns of one stage's X operand: 32 pixels hi + 32 lo
@@ -571,14 +764,15 @@ __device__ __forceinline__ void wg_split_loop(const TcSmem &sm, uint32_t tmem_ba
         mbar_wait(&sm.full[stage], (uint32_t)(kb / Cfg::STAGES) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         unsigned char *st = sm.tiles + stage * Cfg::STAGE_BYTES;
-        const float *xa = reinterpret_cast<const float *>(st + (t >> 5) * 4096) + (t & 31);
+        const uint32_t xa = smem_u32(st) + (t >> 5) * 4096 + (t & 31) * 4;
         const uint32_t trow = lane_base + (uint32_t)(stage * Cfg::A_COLS);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-                const float x = xa[(half * 16 + q) * 32];
+                float x;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(xa + (half * 16 + q) * 128) : "memory");
                 uint32_t u;
                 asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
                 hi[q] = u;
@@ -681,19 +875,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         // staged like the conv epilogue: thread = input-channel row in phase 1, a warp per row in phase 2, so that each
         // reduction instruction adds 32 consecutive floats of dW (was: 32 rows Cout * 4 bytes apart)
         constexpr int PITCH = BN_TILE + 4;
-        float *stg = reinterpret_cast<float *>(sm.tiles);
+        const uint32_t stg = smem_u32(sm.tiles);
         {
-            float *srow = stg + row * PITCH + col0;
+            const uint32_t srow = stg + (row * PITCH + col0) * 4;
 #pragma unroll
             for (int jj = 0; jj < Cfg::EPI_COLS; jj += 4)
-                *reinterpret_cast<float4 *>(srow + jj) = make_float4(acc[jj], acc[jj + 1], acc[jj + 2], acc[jj + 3]);
+                sts128(srow + jj * 4, make_float4(acc[jj], acc[jj + 1], acc[jj + 2], acc[jj + 3]));
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
         if (KB > 0) {
             for (int r2 = warp; r2 < TC_BM; r2 += TC_EPI_WARPS) {
                 float *dst = p.dw + ((size_t)tap * p.Cin + ci0 + r2) * p.Cout + n0;
 #pragma unroll
-                for (int c = 0; c < BN_TILE; c += 32) atomicAdd(dst + c + lane, stg[r2 * PITCH + c + lane]);
+                for (int c = 0; c < BN_TILE; c += 32) {
+                    float v;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(stg + (r2 * PITCH + c + lane) * 4) : "memory");
+                    atomicAdd(dst + c + lane, v);
+                }
             }
         }
     }
@@ -837,6 +1035,21 @@ static int tc_chunk() {
     return c;
 }
 
+// epilogue of conv_tc_kernel (TTDG_TC_EPI): 1 = warp-transposed, coalesced; 0 = one pixel row per thread; 2 (default) = per
+// layer: transposed unless the layer adds a residual
+static int g_tc_epi = -1;
+static int tc_epi() {
+    if (g_tc_epi < 0) {
+        const char *e = getenv("TTDG_TC_EPI");
+        const int v = e ? atoi(e) : 2;
+        g_tc_epi = (v >= 0 && v <= 2) ? v : 2;
+    }
+    return g_tc_epi;
+}
+
+static long long *g_tc_trace = nullptr;
+static int g_tc_trace_items = 0;
+
 static int tc_sm_count() {
     static int n = 0;
     if (!n) {
@@ -971,6 +1184,8 @@ extern "C" int ttdg_stem_tc2(const float *x_pad, int Wp, const float *wk_hi, con
     p.tilesW = ceil_div(p.Wo, p.BW); p.tilesH = ceil_div(p.Ho, p.BH); p.tilesI = ceil_div(N, p.BI);
     p.a_tx = p.BW * p.BH * p.BI * 128;
     p.chunk = tc_chunk();
+    p.epi = tc_epi() == 2 ? (p.res_mode == 0 ? 1 : 0) : tc_epi();
+    p.trace = g_tc_trace; p.trace_items = g_tc_trace_items;
     CUtensorMap ma, mb, mblo;
     const cuuint64_t adims[4] = {32, (cuuint64_t)p.Wo, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t astr[3] = {32, (cuuint64_t)Wp * 16, (cuuint64_t)H * Wp * 16};
@@ -1008,6 +1223,19 @@ extern "C" int ttdg_conv_tc_set_cluster(int cl) {
     const int prev = ttdg::tc_cluster_size();
     ttdg::g_tc_cluster = cl;
     return prev;
+}
+
+extern "C" int ttdg_conv_tc_set_epilogue(int mode) {
+    if (mode < 0 || mode > 2) return TTDG_E_ARG;
+    const int prev = ttdg::tc_epi();
+    ttdg::g_tc_epi = mode;
+    return prev;
+}
+
+extern "C" int ttdg_conv_tc_set_trace(long long *dev_buf, int items) {
+    ttdg::g_tc_trace = items > 0 ? dev_buf : nullptr;
+    ttdg::g_tc_trace_items = ttdg::g_tc_trace ? items : 0;
+    return 0;
 }
 
 extern "C" int ttdg_conv_tc_supported(int Cin, int Cout, int stride) {
@@ -1060,6 +1288,8 @@ static int conv_tc_impl(const void *x, const void *wk_hi, const void *wk_lo, con
     }
     p.a_tx = p.BW * p.BH * p.BI * 128;
     p.chunk = tc_chunk();
+    p.epi = tc_epi() == 2 ? (p.res_mode == 0 ? 1 : 0) : tc_epi();
+    p.trace = g_tc_trace; p.trace_items = g_tc_trace_items;
     CUtensorMap ma, mb, mblo;
     const cuuint64_t adims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint32_t abox[4] = {(cuuint32_t)KCH, (cuuint32_t)(p.BW * in_stride), (cuuint32_t)(p.BH * in_stride), (cuuint32_t)p.BI};

@@ -54,6 +54,8 @@ SIGNATURES = {
     "ttdg_stem_tc": (c_int, [P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
     "ttdg_conv_tc_supported": (c_int, [c_int, c_int, c_int]),
     "ttdg_conv_tc_set_cluster": (c_int, [c_int]),
+    "ttdg_conv_tc_set_epilogue": (c_int, [c_int]),
+    "ttdg_conv_tc_set_trace": (c_int, [c_void_p, c_int]),
     "ttdg_conv_tc": (c_int, [P, P, P, P, P, P] + [c_int] * 15 + [P, P]),
     "ttdg_wgrad_tc_supported": (c_int, [c_int, c_int, c_int]),
     "ttdg_wgrad_tc": (c_int, [P, P] + [c_int] * 10 + [P, P]),
