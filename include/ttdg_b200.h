@@ -368,6 +368,16 @@ int ttdg_sort_candidates(const float *boxes, const float *scores, const unsigned
 int ttdg_gather_kept(const float *boxes, const float *scores, const int32_t *cats, const int32_t *keep, const int32_t *n_keep,
                      const int32_t *n_valid, int n_img, int n, int max_keep, float pad_score, float *boxes_out, float *scores_out,
                      int64_t *cats_out, int32_t *counts, void *stream);
+/* RPN NMS without the cross-level sweep (find_top_rpn_proposals applies batched_nms with the level as category, so levels never
+ * interact): ttdg_rpn_nms_levels runs one shared-memory greedy NMS per (image, level) on ttdg_rpn_select's output (every level's
+ * segment of k_h[l] candidates is sorted by score; invalid candidates are skipped) and writes kept[img][pos] (uint8);
+ * ttdg_top_candidates orders the candidates with valid[] != 0 by (score descending, position ascending) and writes the first
+ * n_out of them, padded with a zero box / pad_score, plus counts[img] = min(number valid, n_out).  Together they equal
+ * ttdg_sort_candidates + ttdg_nms + ttdg_gather_kept on the level-concatenated list. */
+int ttdg_rpn_nms_levels(const float *boxes, const unsigned char *valid, const int32_t *k_h, int n_levels, int n_img,
+                        float iou_thresh, int max_keep, unsigned char *kept, void *stream);
+int ttdg_top_candidates(const float *boxes, const float *scores, const unsigned char *valid, int n_img, int n, int n_out,
+                        float pad_score, float *boxes_out, float *scores_out, int32_t *counts, void *stream);
 int ttdg_rois_from_padded(const float *boxes, const int32_t *counts, int n_img, int P, float *rois, void *stream);
 int ttdg_mask_padded_candidates(float *cand_scores, const int32_t *counts, int n_img, int P, int K, void *stream);
 

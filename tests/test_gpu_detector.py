@@ -403,11 +403,21 @@ def test_rpn_device_side_selection_vs_torch(model_and_sd, training):
     bs, ss, cats, nv = det.sort_candidates(boxes, scores, valid, lvl, 0, -float("inf"))
     keep, nk = det.nms_sorted(bs, cats, rpn.nms_thresh, rpn.post_topk)
     ob, os_, _, counts = det.gather_kept(bs, ss, cats, keep, nk, nv, rpn.post_topk, -float("inf"), False)
+    # the production path: one shared-memory NMS per (image, level) + one ordering pass (levels never interact in batched_nms)
+    kept = torch.empty(N, Kt, dtype=torch.uint8, device="cuda")
+    det.check(_C.lib().ttdg_rpn_nms_levels(_p(boxes), _p(valid), ip(ks), 5, N, float(rpn.nms_thresh), int(rpn.post_topk), _p(kept), _stream()),
+              "rpn_nms_levels")
+    ob2 = torch.empty(N, rpn.post_topk, 4, device="cuda"); os2 = torch.empty(N, rpn.post_topk, device="cuda")
+    counts2 = torch.empty(N, dtype=torch.int32, device="cuda")
+    det.check(_C.lib().ttdg_top_candidates(_p(boxes), _p(scores), _p(kept), N, Kt, int(rpn.post_topk), -float("inf"), _p(ob2), _p(os2),
+                                           _p(counts2), _stream()), "top_candidates")
     for n in range(N):
         c = int(counts[n])
         assert c == len(ref[n][0])
         assert torch.equal(os_[n, :c], ref[n][1]) and torch.equal(ob[n, :c], ref[n][0])
         assert bool(torch.isinf(os_[n, c:]).all())
+        assert int(counts2[n]) == c
+        assert torch.equal(os2[n], os_[n]) and torch.equal(ob2[n], ob[n])
 
 
 def test_rpn_topk_ties_take_the_lowest_indices():

@@ -63,6 +63,8 @@ SIGNATURES = {
     "ttdg_weight_refresh": (c_int, [P, c_int, c_int64, P]),
     "ttdg_rpn_select": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, c_int, P, P, P, P, P]),
     "ttdg_sort_candidates": (c_int, [P, P, P, P, c_int, c_int, c_int, c_float, P, P, P, P, P]),
+    "ttdg_rpn_nms_levels": (c_int, [P, P, P, c_int, c_int, c_float, c_int, P, P]),
+    "ttdg_top_candidates": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P, P, P, P]),
     "ttdg_gather_kept": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_float, P, P, P, P, P]),
     "ttdg_rois_from_padded": (c_int, [P, P, c_int, c_int, P, P]),
     "ttdg_mask_padded_candidates": (c_int, [P, P, c_int, c_int, c_int, P]),

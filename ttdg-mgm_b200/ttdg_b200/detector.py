@@ -139,6 +139,9 @@ def refresh_weight_copies(modules):
         m._wk_cache[key] = (stamp,) + tuple(ent[1:])
 
 
+RPN_NMS_PER_LEVEL = [True]     # False: the level-concatenated ordering + ttdg_nms sweep (the reference formulation; tests compare)
+
+
 def _tc_ok(Cin, Cout, stride, R=1, pad=0):
     """Tensor-core kernel coverage: stride 1, or the strided 1x1 convs (TMA element strides)."""
     if CONV_MODE[0] == "simt" or Cin % 32 or Cout % 64:
@@ -641,6 +644,18 @@ class RPN(nn.Module):
         check(L.ttdg_rpn_select(vp(logits_l), vp(deltas_l), ip(hw), ip(list(STRIDES[:nl])), ip(ks), nl, logits_l[0].shape[-1],
                                 deltas_l[0].shape[-1], A, fp(self._cell.reshape(-1).tolist()), N,
                                 fp([float(v) for s_ in sizes for v in s_]), _p(boxes), _p(scores), _p(valid), _stream()), "rpn_select")
+        if RPN_NMS_PER_LEVEL[0]:
+            # batched_nms with the level as category = independent problems of <= 2000 boxes per (image, level), each in shared
+            # memory (40 CTAs) instead of one 8960-box sweep per image; then one ordering pass picks the first post_topk kept
+            kept = torch.empty(N, Kt, dtype=torch.uint8, device=dev)
+            check(L.ttdg_rpn_nms_levels(_p(boxes), _p(valid), ip(ks), nl, N, float(self.nms_thresh), int(self.post_topk), _p(kept),
+                                        _stream()), "rpn_nms_levels")
+            out_b = torch.empty(N, self.post_topk, 4, dtype=torch.float32, device=dev)
+            out_s = torch.empty(N, self.post_topk, dtype=torch.float32, device=dev)
+            counts = torch.empty(N, dtype=torch.int32, device=dev)
+            check(L.ttdg_top_candidates(_p(boxes), _p(scores), _p(kept), N, Kt, int(self.post_topk), -float("inf"), _p(out_b), _p(out_s),
+                                        _p(counts), _stream()), "top_candidates")
+            return out_b, out_s, counts
         key = (tuple(ks), dev)
         lvl = self.__dict__.setdefault("_lvl_cache", {}).get(key)
         if lvl is None:                                                 # level of every candidate position: the NMS category
