@@ -78,6 +78,10 @@ def test_from_config_dispatches_by_name():
     m = arch.from_config(cfg)                              # CPU construction: parameters only, no kernel runs
     assert type(m.proposal_generator).__name__ == "PseudoLabRPN" and type(m.roi_heads).__name__ == "StandardROIHeadsPseudoLab"
     assert m.roi_heads.num_classes == cfg.MODEL.ROI_HEADS.NUM_CLASSES
+    with pytest.raises(AttributeError):                    # setup() freezes the config, like the reference's (train_net.py:31)
+        cfg.MODEL.ROI_HEADS.NAME = "NoSuchHeads"
+    cfg = cfg.clone()
+    cfg.defrost()
     cfg.MODEL.ROI_HEADS.NAME = "NoSuchHeads"
     with pytest.raises(KeyError):
         arch.from_config(cfg)
@@ -104,3 +108,35 @@ def test_image_list_keeps_per_image_sizes():
     from ttdg_b200.structures import ImageList
     il = ImageList(None, [(96, 128), (128, 160)])
     assert len(il) == 2 and il.image_sizes == [(96, 128), (128, 160)]
+
+
+def test_cfgnode_mirrors_the_yacs_calls_of_the_reference_entry_point(tmp_path):
+    """get_cfg / add_ateacher_config(cfg) / merge_from_file (with _BASE_) / merge_from_list / freeze / clone / defrost:
+    the calls of reference train_net.py:23-33, on this package's CfgNode."""
+    from adapteacher.config import CfgNode, add_ateacher_config, get_cfg
+    base = tmp_path / "base.yaml"
+    base.write_text("MODEL:\n  META_ARCHITECTURE: GeneralizedRCNN\n  ROI_HEADS:\n    NUM_CLASSES: 7\nSOLVER:\n  BASE_LR: 0.02\n")
+    top = tmp_path / "top.yaml"
+    top.write_text("_BASE_: base.yaml\nMODEL:\n  ROI_HEADS:\n    NAME: StandardROIHeadsPseudoLab\nTEST:\n  BATCH: 5\nDATASETS:\n  TEST: (\"a\", \"b\")\n")
+    cfg = get_cfg()
+    assert add_ateacher_config(cfg) is cfg
+    assert cfg.TEST.TTT is True and cfg.TEST.BATCH == 1 and cfg.TEST.MIN_BATCH_NUM is None and cfg.SEMISUPNET.Trainer == "ateacher"
+    cfg.merge_from_file(str(top))
+    assert cfg.MODEL.ROI_HEADS.NUM_CLASSES == 7 and cfg.MODEL.ROI_HEADS.NAME == "StandardROIHeadsPseudoLab"     # _BASE_ then override
+    assert cfg.SOLVER.BASE_LR == 0.02 and cfg.SOLVER.MOMENTUM == 0.9 and cfg.TEST.BATCH == 5 and cfg.DATASETS.TEST == ("a", "b")
+    cfg.merge_from_list(["SOLVER.BASE_LR", "0.005", "SEMISUPNET.Trainer", "baseline", "OUTPUT_DIR", "out/x", "NEW.KEY", "(1, 2)"])
+    assert cfg.SOLVER.BASE_LR == 0.005 and cfg.SEMISUPNET.Trainer == "baseline" and cfg.OUTPUT_DIR == "out/x" and cfg.NEW.KEY == (1, 2)
+    with pytest.raises(ValueError):
+        cfg.merge_from_list(["A"])
+    cfg.freeze()
+    assert cfg.is_frozen() and cfg.MODEL.is_frozen()
+    with pytest.raises(AttributeError):
+        cfg.TEST.BATCH = 3
+    with pytest.raises(AttributeError):
+        cfg["TEST"] = 1
+    c2 = cfg.clone()
+    c2.defrost()
+    c2.TEST.BATCH = 3
+    assert c2.TEST.BATCH == 3 and cfg.TEST.BATCH == 5
+    assert isinstance(c2.MODEL, CfgNode) and hasattr(c2.MODEL, "WEIGHTS") and not hasattr(c2.MODEL, "NOPE")
+    assert "BATCH: 5" in cfg.dump()

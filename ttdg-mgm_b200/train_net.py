@@ -14,7 +14,6 @@ import ast
 import json
 import os
 import sys
-from types import SimpleNamespace
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 if HERE not in sys.path:
@@ -24,7 +23,7 @@ import torch  # noqa: E402
 import yaml  # noqa: E402
 
 from adapteacher.checkpoint import DetectionCheckpointer  # noqa: E402
-from adapteacher.config import add_ateacher_config  # noqa: E402
+from adapteacher.config import add_ateacher_config, get_cfg  # noqa: E402
 from adapteacher.data import build_detection_test_loader  # noqa: E402
 from adapteacher.engine.trainer import BaselineTrainer  # noqa: E402
 
@@ -35,64 +34,14 @@ from adapteacher.modeling.roi_heads.roi_heads import StandardROIHeadsPseudoLab  
 from ttdg_b200.registry import META_ARCH_REGISTRY  # noqa: E402
 
 
-def _literal(v):
-    if isinstance(v, str):
-        try:
-            return ast.literal_eval(v)                          # yacs: '("a", "b")' -> tuple, '0.5' -> float
-        except (ValueError, SyntaxError):
-            return v
-    return v
-
-
-def _merge(ns, d):
-    for k, v in d.items():
-        if isinstance(v, dict):
-            sub = getattr(ns, k, None)
-            if not isinstance(sub, SimpleNamespace):
-                sub = SimpleNamespace()
-                setattr(ns, k, sub)
-            _merge(sub, v)
-        else:
-            setattr(ns, k, _literal(v))
-
-
-def _load_yaml(path):
-    with open(path) as f:
-        d = yaml.safe_load(f) or {}
-    base = d.pop("_BASE_", None)
-    out = _load_yaml(os.path.join(os.path.dirname(path), base)) if base else {}
-
-    def deep(a, b):
-        for k, v in b.items():
-            if isinstance(v, dict) and isinstance(a.get(k), dict):
-                deep(a[k], v)
-            else:
-                a[k] = v
-    deep(out, d)
-    return out
-
-
 def setup(args):
-    cfg = add_ateacher_config()
-    cfg.MODEL = SimpleNamespace(WEIGHTS="", META_ARCHITECTURE="DAobjTwoStagePseudoLabGeneralizedRCNN",
-                                BACKBONE=SimpleNamespace(NAME="build_resnet_fpn_backbone"),
-                                PROPOSAL_GENERATOR=SimpleNamespace(NAME="PseudoLabRPN"),
-                                ROI_HEADS=SimpleNamespace(NAME="StandardROIHeadsPseudoLab", NUM_CLASSES=2))
-    cfg.INPUT = SimpleNamespace(FORMAT="BGR", MIN_SIZE_TEST=800, MAX_SIZE_TEST=1333)
-    cfg.OUTPUT_DIR = "./output"
+    """Create configs and perform basic setups - the reference's own sequence (reference train_net.py:23-33)."""
+    cfg = get_cfg()
+    add_ateacher_config(cfg)
     if args.config_file:
-        _merge(cfg, _load_yaml(args.config_file))
-    opts = list(args.opts)
-    if len(opts) % 2:
-        raise ValueError("overrides must be KEY VALUE pairs")
-    for k, v in zip(opts[::2], opts[1::2]):
-        node = cfg
-        *path, leaf = k.split(".")
-        for pth in path:
-            if not hasattr(node, pth):
-                setattr(node, pth, SimpleNamespace())
-            node = getattr(node, pth)
-        setattr(node, leaf, _literal(v))
+        cfg.merge_from_file(args.config_file)
+    cfg.merge_from_list(args.opts)
+    cfg.freeze()
     return cfg
 
 
@@ -123,6 +72,11 @@ class Trainer(BaselineTrainer):
 
 def main(args):
     cfg = setup(args)
+    if cfg.SEMISUPNET.Trainer == "ateacher":                   # reference train_net.py:38-55: mean-teacher ensemble, no test-time adaptation
+        raise NotImplementedError("SEMISUPNET.Trainer 'ateacher' (teacher / student ensemble evaluation) is outside the test-time-"
+                                  "adaptation path; use SEMISUPNET.Trainer baseline (configs/test_segment.yaml)")
+    if cfg.SEMISUPNET.Trainer != "baseline":
+        raise ValueError("Trainer Name is not found.")         # reference train_net.py:43
     if not args.eval_only:
         raise NotImplementedError("only --eval-only (test-time adaptation + evaluation) is implemented")
     world = int(os.environ.get("WORLD_SIZE", "1"))
