@@ -6,6 +6,13 @@ TEST INFRASTRUCTURE (see oracle/__init__.py).  **Parity unpinned**: Detectron2 (
 third-party dependency that is neither vendored under /root/reference nor installable in this image; its operators
 are restated from SURVEY.md Appendix A ([recalled]) on top of torch / torchvision.ops (roi_align aligned=True, nms,
 batched_nms).  Functional style over a state dict with d2's parameter names.  NCHW fp32 throughout.
+
+Cross-check (tests/test_oracle_vs_torchvision.py): where torchvision implements the same published algorithm independently -
+box decoding (BoxCoder.decode), proposal selection (RegionProposalNetwork.filter_proposals), FPN level assignment (LevelMapper),
+box-head inference (RoIHeads.postprocess_detections, background class moved) - this restatement reproduces torchvision's outputs on
+random head outputs (float64, mixed image sizes).  That pins the selection / decoding SEMANTICS to a second implementation; what stays
+unpinned is what Detectron2 does differently from torchvision on purpose (unrounded anchors, aligned RoIAlign, grid_sample mask
+pasting), restated from SURVEY Appendix A.
 """
 import contextlib
 import math
