@@ -404,6 +404,21 @@ int ttdg_mask_gt_stats(const unsigned char *gt, int G, int H, int W, int64_t *st
 int ttdg_mask_pair_counts(const unsigned char *pred, const unsigned char *gt, const int32_t *pairs, int n_pairs,
                           const int64_t *gt_stats, int H, int W, int64_t *counts, void *stream);
 
+/* ---- test data path: image resize on the device.  Replaces the host-side PIL resize of d2's
+ * DatasetMapper(cfg, False) -> ResizeShortestEdge -> ResizeTransform.apply_image (reference adapteacher/data/build.py:122-154),
+ * bit-exact with PIL.Image.resize((w, h), Image.BILINEAR) on uint8 images (Pillow's 8-bit resampler: antialiasing triangle filter,
+ * 22-bit fixed-point coefficients, horizontal pass then vertical pass, each clipped to uint8).
+ * ttdg_resize_ksize / ttdg_resize_coeffs_u8 are HOST functions (no device work): the coefficient table of one axis, built in
+ * double precision with Pillow's expressions.  bounds_h: 2 * out_size int32 (first input index, count); kk_h: out_size * ksize.
+ * ttdg_resize_bilinear_u8: src H x W x C uint8 interleaved (C = 1, 3, 4) -> dst nh x nw interleaved (planar = 0) or as C planes
+ * (planar = 1: the uint8 C x H x W tensor ttdg_preprocess reads), channels reversed when flip (INPUT.FORMAT "BGR").  The x tables
+ * (device copies for (W, nw)) are ignored when nw == W, the y tables when nh == H; tmp: H * nw * C bytes of device scratch. */
+int ttdg_resize_ksize(int in_size, int out_size);
+int ttdg_resize_coeffs_u8(int in_size, int out_size, int32_t *bounds_h, int32_t *kk_h);
+int ttdg_resize_bilinear_u8(const unsigned char *src, int H, int W, int C, const int32_t *bounds_x, const int32_t *kk_x, int ksize_x,
+                            const int32_t *bounds_y, const int32_t *kk_y, int ksize_y, int nh, int nw, unsigned char *tmp,
+                            unsigned char *dst, int planar, int flip, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,8 @@ restated: ``DatasetMapper(cfg, False)`` (read image, ``INPUT.FORMAT``, ResizeSho
 CHW uint8 tensor), ``InferenceSampler`` (contiguous shard per rank) and the polygon rasteriser of pycocotools
 (``frPyObjects`` + ``decode``, used by dice_metric.py:94-108 for the ground-truth masks).  Detectron2 / pycocotools are
 absent offline: these restatements are PARITY UNPINNED."""
+import os
+
 import numpy as np
 import torch
 
@@ -90,11 +92,17 @@ class DatasetMapper:
     """d2 DatasetMapper(cfg, is_train=False): image in ``INPUT.FORMAT``, shortest edge resized to MIN_SIZE_TEST (max
     MAX_SIZE_TEST), uint8 CHW tensor; 'height' / 'width' keep the ORIGINAL size (the masks are pasted back to it)."""
 
-    def __init__(self, cfg, is_train=False):
+    def __init__(self, cfg, is_train=False, device_resize=None):
         inp = getattr(cfg, "INPUT", None)
         self.format = getattr(inp, "FORMAT", "BGR")
         self.min_size = getattr(inp, "MIN_SIZE_TEST", 800)
         self.max_size = getattr(inp, "MAX_SIZE_TEST", 1333)
+        # device_resize: the decoded image goes to the GPU at its ORIGINAL size and is resized there (csrc/resize.cu, bit-exact with
+        # PIL's bilinear resampler) - the host does the JPEG / PNG decode only.  Default: on when CUDA is available
+        # (TTDG_DEVICE_RESIZE=0 keeps PIL's resize on the host).
+        if device_resize is None:
+            device_resize = torch.cuda.is_available() and os.environ.get("TTDG_DEVICE_RESIZE", "1") != "0"
+        self.device_resize = bool(device_resize)
 
     def _resize_shape(self, h, w):
         if not self.min_size:
@@ -115,6 +123,14 @@ class DatasetMapper:
             with Image.open(d["file_name"]) as im:
                 im = im.convert("RGB")
                 nh, nw = self._resize_shape(im.height, im.width)
+                if self.device_resize:
+                    from ttdg_b200 import ops
+                    raw = torch.from_numpy(np.ascontiguousarray(np.asarray(im)))                  # H x W x 3, original size
+                    raw = (raw.pin_memory() if torch.cuda.is_available() else raw).to("cuda", non_blocking=True)
+                    img = ops.resize_bilinear_u8(raw, nh, nw, planar=True, flip=self.format == "BGR")     # 3 x nh x nw on the device
+                    d["image"] = img
+                    d.pop("annotations", None)
+                    return d
                 if (nh, nw) != (im.height, im.width):
                     im = im.resize((nw, nh), Image.BILINEAR)   # d2 ResizeTransform: PIL bilinear on uint8 images
                 arr = np.asarray(im)
@@ -157,7 +173,7 @@ class _TestLoader:
         cur = []
         for i in self.sampler:
             d = self.mapper(self.dicts[i])
-            if self.pin and torch.cuda.is_available():
+            if self.pin and torch.cuda.is_available() and not d["image"].is_cuda:
                 d["image"] = d["image"].pin_memory()
             cur.append(d)
             if len(cur) == self.batch:

@@ -65,6 +65,9 @@ SIGNATURES = {
     "ttdg_sort_candidates": (c_int, [P, P, P, P, c_int, c_int, c_int, c_float, P, P, P, P, P]),
     "ttdg_rpn_nms_levels": (c_int, [P, P, P, c_int, c_int, c_float, c_int, P, P]),
     "ttdg_top_candidates": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P, P, P, P]),
+    "ttdg_resize_ksize": (c_int, [c_int, c_int]),
+    "ttdg_resize_coeffs_u8": (c_int, [c_int, c_int, P, P]),
+    "ttdg_resize_bilinear_u8": (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, P, c_int, c_int, c_int, P, P, c_int, c_int, P]),
     "ttdg_gather_kept": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_float, P, P, P, P, P]),
     "ttdg_rois_from_padded": (c_int, [P, P, c_int, c_int, P, P]),
     "ttdg_mask_padded_candidates": (c_int, [P, P, c_int, c_int, c_int, P]),

@@ -504,3 +504,52 @@ def mask_pair_counts(pred, gt, pairs, gt_stats):
     out = torch.zeros(len(pt), 16, dtype=torch.int64, device=pred.device)
     check(_C.lib().ttdg_mask_pair_counts(_p(pred), _p(gt), _p(pt), len(pt), _p(gt_stats), H, W, _p(out), _stream()), "mask_pair_counts")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ test data path
+_RESIZE_TABLES = {}
+
+
+def resize_tables(in_size, out_size, device):
+    """Device copy of Pillow's fixed-point coefficient table of one axis (built on the host by the library, cached per
+    (in, out, device)): (bounds int32 [out, 2], kk int32 [out, ksize], ksize)."""
+    key = (int(in_size), int(out_size), str(device))
+    hit = _RESIZE_TABLES.get(key)
+    if hit is None:
+        L = _C.lib()
+        ks = L.ttdg_resize_ksize(int(in_size), int(out_size))
+        if ks < 1:
+            raise ValueError("resize: sizes must be positive")
+        bounds = torch.empty(out_size, 2, dtype=torch.int32)
+        kk = torch.empty(out_size, ks, dtype=torch.int32)
+        got = L.ttdg_resize_coeffs_u8(int(in_size), int(out_size), _p(bounds), _p(kk))
+        if got != ks:
+            raise _C.TTDGError(f"ttdg_resize_coeffs_u8 failed ({got})")
+        if len(_RESIZE_TABLES) > 256:
+            _RESIZE_TABLES.clear()
+        hit = (bounds.to(device), kk.to(device), ks)
+        _RESIZE_TABLES[key] = hit
+    return hit
+
+
+def resize_bilinear_u8(img_hwc, new_h, new_w, planar=True, flip=False):
+    """PIL.Image.resize((new_w, new_h), Image.BILINEAR) on the device, bit-exact (d2 ResizeTransform.apply_image for uint8 images).
+    img_hwc: uint8 H x W x C CUDA tensor (C = 1, 3, 4) -> uint8 C x new_h x new_w (planar) or new_h x new_w x C; flip reverses the
+    channel order (INPUT.FORMAT 'BGR')."""
+    _need_cuda(img_hwc)
+    if img_hwc.dtype != torch.uint8 or img_hwc.dim() != 3:
+        raise ValueError("resize_bilinear_u8 expects a uint8 H x W x C tensor")
+    img_hwc = img_hwc.contiguous()
+    H, W, C = img_hwc.shape
+    dev = img_hwc.device
+    bx = kx = by = ky = tmp = None
+    ksx = ksy = 0
+    if new_w != W:
+        bx, kx, ksx = resize_tables(W, new_w, dev)
+        tmp = torch.empty(H, new_w, C, dtype=torch.uint8, device=dev)
+    if new_h != H:
+        by, ky, ksy = resize_tables(H, new_h, dev)
+    out = torch.empty((C, new_h, new_w) if planar else (new_h, new_w, C), dtype=torch.uint8, device=dev)
+    check(_C.lib().ttdg_resize_bilinear_u8(_p(img_hwc), H, W, C, _p(bx), _p(kx), int(ksx), _p(by), _p(ky), int(ksy), int(new_h), int(new_w),
+                                           _p(tmp), _p(out), int(bool(planar)), int(bool(flip)), _stream()), "resize_bilinear_u8")
+    return out
