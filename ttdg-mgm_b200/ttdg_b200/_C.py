@@ -8,7 +8,7 @@ import os
 from ctypes import c_int, c_int64, c_uint64, c_float, c_double, c_void_p, c_char_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "lib", "libttdg_sm100.so")
+SO_PATH = os.environ.get("TTDG_LIB") or os.path.join(_HERE, "lib", "libttdg_sm100.so")     # TTDG_LIB: A/B builds of the same ABI (tools/)
 _lib = None
 
 P = c_void_p
