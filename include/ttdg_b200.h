@@ -268,10 +268,12 @@ int ttdg_conv_tc_supported(int Cin, int Cout, int stride);
  * loads 1/cl of it and TMA multicasts the slice to all of them.  cl = 1 (default; also env TTDG_TC_CLUSTER), 2 or 4.
  * Results do not depend on it.  Returns the previous value, or TTDG_E_ARG. */
 int ttdg_conv_tc_set_cluster(int cl);
-/* Epilogue of ttdg_conv_tc / ttdg_conv_tc_bf16 / ttdg_stem_tc (env TTDG_TC_EPI): 1 = each epilogue warp transposes its 32
- * pixel rows through 4 KB of shared memory so that global loads (residual) and stores are 128-byte row segments; 0 = every
- * thread stores its own pixel row (32 lines per warp access); 2 (default) = chosen per layer.  Same arithmetic in the same
- * order: results are bit-identical.  Returns the previous value, or TTDG_E_ARG. */
+/* Epilogue of ttdg_conv_tc / ttdg_conv_tc_bf16 / ttdg_stem_tc (env TTDG_TC_EPI): 0 = every thread stores its own pixel row (32
+ * lines per warp access); 1 = each epilogue warp transposes its 32 pixel rows through 4 KB of shared memory so that global
+ * loads (residual) and stores are 128-byte row segments; 2 = 1 unless the layer adds a residual; 3 (default) = the tile goes
+ * through shared memory as TMA boxes (TMA store, TMA residual load) where the layer allows it - fp32 output at stride 1,
+ * residual absent or fp32 at the output's resolution - else as 2.  Same arithmetic in the same order: results are
+ * bit-identical.  Returns the previous value, or TTDG_E_ARG. */
 int ttdg_conv_tc_set_epilogue(int mode);
 /* Diagnostics: while dev_buf != NULL, CTA 0 of every ttdg_conv_tc* launch records clock64() at 8 points of its first `items`
  * tiles into dev_buf[item * 8 + slot] (slot 0 / 1: first / last k-block's TMA issue, 2: MMA warp owns the accumulator,

@@ -273,6 +273,8 @@ def test_conv_tc_cluster_multicast(cl, cin, cout, k, pad, H, W, N):
     (256, 256, 3, 1, 1, 14, 14, 7, 0),       # 14 x 14 boxes: 126 of the 128 tile rows, partial last image group
     (256, 512, 1, 0, 2, 26, 38, 1, 0),       # strided 1x1 (TMA element strides), ragged tiles
     (128, 128, 3, 1, 1, 19, 23, 3, 1),       # ragged tiles with residual
+    (64, 256, 1, 0, 1, 64, 64, 9, 1),        # many tiles per SM: the residual / store pipeline of the TMA epilogue wraps around
+    (256, 128, 1, 0, 1, 128, 128, 3, 0),     # the same without a residual (stores only)
 ])
 def test_conv_tc_transposed_epilogue_is_bit_identical(mode, cin, cout, k, pad, stride, H, W, N, res):
     """The warp-transposed (coalesced) epilogue performs the same operations per element as the row-per-thread one: both
@@ -296,11 +298,17 @@ def test_conv_tc_transposed_epilogue_is_bit_identical(mode, cin, cout, k, pad, s
                 y0 = layer(x, relu=True, residual=r, res_mode=int(res))
                 assert L.ttdg_conv_tc_set_epilogue(1) == 0
                 y1 = layer(x, relu=True, residual=r, res_mode=int(res))
+                assert L.ttdg_conv_tc_set_epilogue(3) == 1              # TMA store / TMA residual load where the layer allows it
+                y3 = layer(x, relu=True, residual=r, res_mode=int(res))
+                y3b = layer(x, relu=False, residual=r, res_mode=int(res))
+                L.ttdg_conv_tc_set_epilogue(0)
+                y0b = layer(x, relu=False, residual=r, res_mode=int(res))
             torch.cuda.synchronize()
         finally:
             L.ttdg_conv_tc_set_epilogue(prev)
         assert y0.dtype == y1.dtype and torch.equal(y0, y1)
+        assert y0.dtype == y3.dtype and torch.equal(y0, y3) and torch.equal(y0b, y3b)
         assert float(y0.float().abs().sum()) > 0
-        assert L.ttdg_conv_tc_set_epilogue(3) == -1
+        assert L.ttdg_conv_tc_set_epilogue(4) == -1
     finally:
         det.set_conv_mode("tf32x3")

@@ -57,9 +57,11 @@ struct TcParams {
     int out_stride, outH, outW;      // output pixel (ho, wo) is stored at (ho, wo) * out_stride of an outH x outW map
     int a_tx;                        // bytes one activation box delivers: BW * BH * BI rows of 128 B (<= A_BYTES)
     int chunk;                       // k-blocks per TMEM accumulation chunk (see TcCfg::CHUNK)
-    int epi;                         // 1: warp-transposed (coalesced) epilogue, 0: one pixel row per thread straight to global
+    int epi;                         // 1: warp-transposed (coalesced) epilogue, 0: one pixel row per thread straight to global,
+                                     // 3: whole tile through shared memory, TMA store (and TMA residual load) - see the epilogue
     long long *trace;                // optional: CTA 0 records clock64() at 8 points of its first trace_items tiles
     int trace_items;
+    alignas(64) CUtensorMap tmY, tmR;   // epi == 3: the output / residual tensors as TMA maps, box {32 ch (fp32) | 64 ch (bf16), BW, BH, BI}
 };
 #define TC_TRACE(li, slot) do { if (p.trace && blockIdx.x == 0 && (li) < p.trace_items) p.trace[(li) * 8 + (slot)] = clock64(); } while (0)
 
@@ -91,6 +93,19 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// TMA store of a shared-memory box + bulk async-group bookkeeping (the epilogue's output tile)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+template <int ID>
+__device__ __forceinline__ void bar_sync128() { asm volatile("bar.sync %0, 128;" ::"n"(ID) : "memory"); }
+
 // multicast variants (thread-block cluster along the pixel tiles: the CTAs of a cluster share the weight tile, each loads
 // 1 / CL of it and TMA delivers the slice to every CTA of the cluster at the same shared-memory offset, signalling each
 // CTA's own mbarrier - one L2 read feeds CL SMs)
@@ -256,10 +271,14 @@ struct TcCfg {
     // nothing back to it (~110 KB per k-block).
     static constexpr int STAGE_BYTES = A_BYTES + (PRECISE ? 2 : 1) * B_BYTES;
     static constexpr int TX_BYTES = STAGE_BYTES;                                     // what TMA delivers per stage
-    static constexpr int STAGES = PRECISE ? (BN_TILE == 128 ? 4 : 6) : (BN_TILE == 128 ? 6 : 8);
-    // epilogue staging: 4 KB per epilogue warp (32 pixel rows x 32 fp32 channels, 128-byte swizzled) - see the epilogue
-    static constexpr int EPI_BYTES = TC_EPI_WARPS * 4096;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+    // 3 instead of 4 stages of the 3xTF32 ring cost the compute-bound layers nothing (650.2 vs 651.3 us on the 3x3 256 -> 256 layer at
+    // 128^2, profiles/r02_summary) and make room for a whole output tile in shared memory
+    static constexpr int STAGES = PRECISE ? (BN_TILE == 128 ? 3 : 4) : (BN_TILE == 128 ? 4 : 6);
+    // epilogue staging: the fp32 output tile, 128 rows x BN_TILE channels as BN_TILE / 32 slabs of [128 rows][128 B] (128-byte
+    // swizzle = the layout of a TMA box {32 channels, BW, BH, BI}); the warp-transposed epilogue uses the first 4 KB per warp of it
+    static constexpr int EPI_BYTES = TC_BM * BN_TILE * 4;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + 1024 /* scale | bias */;
+    static_assert(EPI_BYTES >= TC_EPI_WARPS * 4096, "room for the per-warp transposition buffers");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static constexpr int ACC_COLS = 2 * BN_TILE;         // two accumulator buffers (ping-pong between MMA and epilogue)
     static constexpr int A_COLS = 2 * TC_BK;             // TMEM columns of one stage's A operand: 32 hi + 32 lo
@@ -275,8 +294,9 @@ struct TcCfg {
 
 struct TcSmem {
     unsigned char *tiles, *epi;
-    uint64_t *full, *empty, *conv, *tmem_full, *tmem_empty;
+    uint64_t *full, *empty, *conv, *tmem_full, *tmem_empty, *res_full;
     uint32_t *tmem_slot;
+    float *sb;                                           // [2 column halves][64 scale | 64 bias] of the current tile (TMA epilogue)
 };
 
 // carve the dynamic shared memory, initialise the barriers, allocate TMEM; returns the TMEM base address
@@ -290,12 +310,16 @@ __device__ __forceinline__ uint32_t tc_prologue(TcSmem &sm, unsigned char *raw_s
     sm.tmem_full = sm.conv + Cfg::STAGES;                // [2]
     sm.tmem_empty = sm.tmem_full + 2;                    // [2]
     sm.tmem_slot = reinterpret_cast<uint32_t *>(sm.tmem_empty + 2);
+    sm.res_full = reinterpret_cast<uint64_t *>(sm.tmem_slot + 2);                                      // [2][2] (conv kernel only)
+    sm.sb = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(sm.full) + 256);
+    static_assert(Cfg::EPI_BYTES == 0 || (3 * Cfg::STAGES + 4) * 8 + 8 + 32 <= 256, "barrier block layout");
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         // empty[s]: one arrival per CTA of the cluster (a slot is refilled by multicast only when every CTA has consumed it)
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], CL); mbar_init(&sm.conv[s], TC_CVT_THREADS); }
         mbar_init(&sm.tmem_full[0], 1); mbar_init(&sm.tmem_full[1], 1);
         mbar_init(&sm.tmem_empty[0], TC_EPI_WARPS); mbar_init(&sm.tmem_empty[1], TC_EPI_WARPS);      // one arrival per epilogue warp
+        if (Cfg::EPI_BYTES > 0) for (int s = 0; s < 4; ++s) mbar_init(&sm.res_full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -397,7 +421,7 @@ __device__ __forceinline__ void tc_drain(const TcSmem &sm, uint32_t tmem_base, i
 template <int BN_TILE, bool PRECISE, int CL, bool BF16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ TcParams p) {
     static_assert(!(BF16 && PRECISE), "bf16 is a single-pass mode");
     using Cfg = TcCfg<BN_TILE, PRECISE>;
     constexpr int KCH = BF16 ? 64 : TC_BK;                                        // channels per k-block
@@ -520,11 +544,82 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int bh = rem / p.BW, bw = rem - bh * p.BW;
         const int nchunks = (KB + p.chunk - 1) / p.chunk;
         uint32_t gc = 0;
+        if (p.epi == 3 && p.res_mode != 0 && (threadIdx.x & 127) == 0 && clus < nitems) {
+            // TMA epilogue: the residual boxes of this group's first tile
+            constexpr int SLABS = Cfg::EPI_COLS / 32;
+            const int hh = warp >> 2;
+            int w1, h1, i1, n1;
+            decode(clus, w1, h1, i1, n1);
+#pragma unroll
+            for (int s = 0; s < SLABS; ++s) {
+                mbar_expect_tx(&sm.res_full[hh * 2 + s], (uint32_t)p.a_tx);
+                tma_load_4d(sm.epi + (size_t)(hh * SLABS + s) * 16384, &p.tmR, &sm.res_full[hh * 2 + s], n1 + col0 + s * 32, w1, h1, i1);
+            }
+        }
         for (int item = clus; item < nitems; item += nclus, gc += nchunks) {
             int w0, h0, i0, n0;
             decode(item, w0, h0, i0, n0);
             const int img = i0 + bi, ho = h0 + bh, wo = w0 + bw;
             const bool ok = bi < p.BI && img < p.N && ho < p.Ho && wo < p.Wo;       // bi >= BI: rows past a box of < 128 pixels
+            if (p.epi == 3) {
+                // ---- TMA epilogue: the tile leaves (and its residual arrives) as TMA boxes.  The 8 epilogue warps form two groups of
+                // 128 threads (column halves); a group owns SLABS slabs of [128 pixel rows][32 channels] in the 128-byte-swizzled
+                // layout of a TMA box {32, BW, BH, BI}.  Per slab: (residual box landed | previous store read out) -> every thread
+                // finishes its row in place (FrozenBN scale / bias from shared memory, + residual, ReLU) -> fence.proxy.async ->
+                // named barrier -> one thread issues the TMA store.  No per-row addresses, no global loads / stores by the warps,
+                // edge tiles are clipped by TMA.  The residual box of the group's NEXT tile is requested as soon as the stores of
+                // this one have been read out of the slabs, i.e. a whole accumulator drain ahead of its use.
+                constexpr int SLABS = Cfg::EPI_COLS / 32;
+                const int hh = warp >> 2, gt = threadIdx.x & 127;
+                const bool elected = gt == 0, has_res = p.res_mode != 0, relu = p.relu != 0;
+                unsigned char *slab_p = sm.epi + (size_t)(hh * SLABS) * 16384;
+                const uint32_t slab_a = smem_u32(slab_p), sb_a = smem_u32(sm.sb + hh * 128);
+                const int li = (item - clus) / nclus;
+                const int nb = n0 + col0;
+                if (gt < Cfg::EPI_COLS) sm.sb[hh * 128 + gt] = p.scale ? __ldg(p.scale + nb + gt) : 1.f;
+                else if (gt >= 64 && gt < 64 + Cfg::EPI_COLS) sm.sb[hh * 128 + gt] = p.bias ? __ldg(p.bias + nb + gt - 64) : 0.f;
+                if (threadIdx.x == 0) TC_TRACE(li, 7);
+                float acc[Cfg::EPI_COLS];
+                tc_drain<Cfg>(sm, tmem_base, KB, p.chunk, q, col0, acc, gc);
+                if (threadIdx.x == 0) TC_TRACE(li, 5);
+#pragma unroll
+                for (int s = 0; s < SLABS; ++s) {
+                    if (has_res) mbar_wait(&sm.res_full[hh * 2 + s], (uint32_t)li & 1u);
+                    else if (elected) tma_wait_read<SLABS - 1>();             // the previous store of this slab has been read out
+                    if (hh == 0) bar_sync128<1>(); else bar_sync128<2>();       // publishes that, and the scale | bias block
+                    const uint32_t rowa = slab_a + (uint32_t)s * 16384u + (uint32_t)gt * 128u;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int j = s * 32 + c * 4;
+                        const uint32_t a = rowa + (uint32_t)((c ^ (gt & 7)) << 4);
+                        const float4 s4 = lds128(sb_a + j * 4), b4 = lds128(sb_a + (64 + j) * 4);
+                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (has_res) r = lds128(a);
+                        float4 o;
+                        o.x = __fadd_rn(__fadd_rn(__fmul_rn(acc[j], s4.x), b4.x), r.x);
+                        o.y = __fadd_rn(__fadd_rn(__fmul_rn(acc[j + 1], s4.y), b4.y), r.y);
+                        o.z = __fadd_rn(__fadd_rn(__fmul_rn(acc[j + 2], s4.z), b4.z), r.z);
+                        o.w = __fadd_rn(__fadd_rn(__fmul_rn(acc[j + 3], s4.w), b4.w), r.w);
+                        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        sts128(a, o);
+                    }
+                    fence_async_smem();
+                    if (hh == 0) bar_sync128<1>(); else bar_sync128<2>();
+                    if (elected) { tma_store_4d(&p.tmY, slab_p + (size_t)s * 16384, nb + s * 32, w0, h0, i0); tma_commit(); }
+                }
+                if (has_res && elected && item + nclus < nitems) {
+                    int w1, h1, i1, n1;
+                    decode(item + nclus, w1, h1, i1, n1);
+#pragma unroll
+                    for (int s = 0; s < SLABS; ++s) {
+                        if (s + 1 < SLABS) tma_wait_read<SLABS - 1>(); else tma_wait_read<0>();
+                        mbar_expect_tx(&sm.res_full[hh * 2 + s], (uint32_t)p.a_tx);
+                        tma_load_4d(slab_p + (size_t)s * 16384, &p.tmR, &sm.res_full[hh * 2 + s], n1 + col0 + s * 32, w1, h1, i1);
+                    }
+                }
+                if (threadIdx.x == 0) TC_TRACE(li, 6);
+                continue;
+            }
             if (p.epi) {
                 // ---- warp-transposed epilogue.  tcgen05.ld hands each thread one pixel ROW of the accumulator; a thread that
                 // stores its row straight to global makes every 16-byte access of a warp touch 32 different 128-byte lines
@@ -700,6 +795,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
+        if (p.epi == 3 && (threadIdx.x & 127) == 0) tma_wait_all();          // this thread's TMA stores are complete before the CTA retires
     }
     tc_epilogue_end<Cfg, CL>(tmem_base);
 }
@@ -1035,20 +1131,37 @@ static int tc_chunk() {
     return c;
 }
 
-// epilogue of conv_tc_kernel (TTDG_TC_EPI): 1 = warp-transposed, coalesced; 0 = one pixel row per thread; 2 (default) = per
-// layer: transposed unless the layer adds a residual
+// epilogue of conv_tc_kernel (TTDG_TC_EPI): 0 = one pixel row per thread; 1 = warp-transposed, coalesced; 2 = per layer
+// (transposed unless the layer adds a residual); 3 (default) = TMA store / TMA residual load where the layer allows it (fp32
+// output at stride 1, residual absent or fp32 at the output's resolution), else as 2
 static int g_tc_epi = -1;
 static int tc_epi() {
     if (g_tc_epi < 0) {
         const char *e = getenv("TTDG_TC_EPI");
-        const int v = e ? atoi(e) : 2;
-        g_tc_epi = (v >= 0 && v <= 2) ? v : 2;
+        const int v = e ? atoi(e) : 3;
+        g_tc_epi = (v >= 0 && v <= 3) ? v : 3;
     }
     return g_tc_epi;
 }
 
 static long long *g_tc_trace = nullptr;
 static int g_tc_trace_items = 0;
+
+// picks the epilogue of one launch (see tc_epi) and, for the TMA epilogue, encodes the output / residual tensor maps
+static int tc_setup_epilogue(TcParams &p) {
+    const int mode = tc_epi();
+    if (mode <= 1) { p.epi = mode; return 0; }
+    p.epi = p.res_mode == 0 ? 1 : 0;
+    if (mode == 3 && !p.out_bf16 && p.out_stride == 1 && (p.res_mode == 0 || (p.res_mode == 1 && !p.res_bf16))) {
+        const cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
+        const cuuint32_t box[4] = {32, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BI};
+        int rc = make_map(&p.tmY, p.y, 4, dims, box, CU_TENSOR_MAP_SWIZZLE_128B, 1, nullptr, false);
+        if (!rc && p.res_mode) rc = make_map(&p.tmR, p.residual, 4, dims, box, CU_TENSOR_MAP_SWIZZLE_128B, 1, nullptr, false);
+        if (rc) return rc;
+        p.epi = 3;
+    }
+    return 0;
+}
 
 static int tc_sm_count() {
     static int n = 0;
@@ -1184,7 +1297,7 @@ extern "C" int ttdg_stem_tc2(const float *x_pad, int Wp, const float *wk_hi, con
     p.tilesW = ceil_div(p.Wo, p.BW); p.tilesH = ceil_div(p.Ho, p.BH); p.tilesI = ceil_div(N, p.BI);
     p.a_tx = p.BW * p.BH * p.BI * 128;
     p.chunk = tc_chunk();
-    p.epi = tc_epi() == 2 ? (p.res_mode == 0 ? 1 : 0) : tc_epi();
+    { const int erc = tc_setup_epilogue(p); if (erc) return erc; }
     p.trace = g_tc_trace; p.trace_items = g_tc_trace_items;
     CUtensorMap ma, mb, mblo;
     const cuuint64_t adims[4] = {32, (cuuint64_t)p.Wo, (cuuint64_t)H, (cuuint64_t)N};
@@ -1226,7 +1339,7 @@ extern "C" int ttdg_conv_tc_set_cluster(int cl) {
 }
 
 extern "C" int ttdg_conv_tc_set_epilogue(int mode) {
-    if (mode < 0 || mode > 2) return TTDG_E_ARG;
+    if (mode < 0 || mode > 3) return TTDG_E_ARG;
     const int prev = ttdg::tc_epi();
     ttdg::g_tc_epi = mode;
     return prev;
@@ -1288,7 +1401,7 @@ static int conv_tc_impl(const void *x, const void *wk_hi, const void *wk_lo, con
     }
     p.a_tx = p.BW * p.BH * p.BI * 128;
     p.chunk = tc_chunk();
-    p.epi = tc_epi() == 2 ? (p.res_mode == 0 ? 1 : 0) : tc_epi();
+    { const int erc = tc_setup_epilogue(p); if (erc) return erc; }
     p.trace = g_tc_trace; p.trace_items = g_tc_trace_items;
     CUtensorMap ma, mb, mblo;
     const cuuint64_t adims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
