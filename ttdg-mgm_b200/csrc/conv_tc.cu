@@ -550,10 +550,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int hh = warp >> 2;
             int w1, h1, i1, n1;
             decode(clus, w1, h1, i1, n1);
+            if (p.out_bf16) {
+                mbar_expect_tx(&sm.res_full[hh * 2], (uint32_t)p.a_tx);
+                tma_load_4d(sm.epi + (size_t)hh * 16384, &p.tmR, &sm.res_full[hh * 2], n1 + col0, w1, h1, i1);
+            } else {
 #pragma unroll
-            for (int s = 0; s < SLABS; ++s) {
-                mbar_expect_tx(&sm.res_full[hh * 2 + s], (uint32_t)p.a_tx);
-                tma_load_4d(sm.epi + (size_t)(hh * SLABS + s) * 16384, &p.tmR, &sm.res_full[hh * 2 + s], n1 + col0 + s * 32, w1, h1, i1);
+                for (int s = 0; s < SLABS; ++s) {
+                    mbar_expect_tx(&sm.res_full[hh * 2 + s], (uint32_t)p.a_tx);
+                    tma_load_4d(sm.epi + (size_t)(hh * SLABS + s) * 16384, &p.tmR, &sm.res_full[hh * 2 + s], n1 + col0 + s * 32, w1, h1, i1);
+                }
             }
         }
         for (int item = clus; item < nitems; item += nclus, gc += nchunks) {
@@ -582,6 +587,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float acc[Cfg::EPI_COLS];
                 tc_drain<Cfg>(sm, tmem_base, KB, p.chunk, q, col0, acc, gc);
                 if (threadIdx.x == 0) TC_TRACE(li, 5);
+                if (p.out_bf16) {
+                    // bf16 output (and residual): the group's 64 channels are ONE slab of [128 rows][64 x 2 B]; a 16-byte chunk = 8 channels
+                    if (Cfg::EPI_COLS == 64) {
+                        unsigned char *slab16 = sm.epi + (size_t)hh * 16384;
+                        if (has_res) mbar_wait(&sm.res_full[hh * 2], (uint32_t)li & 1u);
+                        else if (elected) tma_wait_read<0>();
+                        if (hh == 0) bar_sync128<1>(); else bar_sync128<2>();
+                        const uint32_t rowa = smem_u32(slab16) + (uint32_t)gt * 128u;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const int j = (c * 8) % Cfg::EPI_COLS;
+                            const uint32_t a = rowa + (uint32_t)((c ^ (gt & 7)) << 4);
+                            const float4 sA = lds128(sb_a + j * 4), sB = lds128(sb_a + (j + 4) * 4);
+                            const float4 bA = lds128(sb_a + (64 + j) * 4), bB = lds128(sb_a + (64 + j + 4) * 4);
+                            float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                            if (has_res) {
+                                const float4 rr = lds128(a);
+                                const uint32_t w[4] = {__float_as_uint(rr.x), __float_as_uint(rr.y), __float_as_uint(rr.z), __float_as_uint(rr.w)};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) { r[2 * k] = __uint_as_float(w[k] << 16); r[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
+                            }
+                            const float sv[8] = {sA.x, sA.y, sA.z, sA.w, sB.x, sB.y, sB.z, sB.w};
+                            const float bv[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+                            float o[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                o[k] = __fadd_rn(__fadd_rn(__fmul_rn(acc[j + k], sv[k]), bv[k]), r[k]);
+                                if (relu) o[k] = fmaxf(o[k], 0.f);
+                            }
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const __nv_bfloat162 q2 = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
+                                pk[k] = *reinterpret_cast<const uint32_t *>(&q2);
+                            }
+                            sts128(a, make_float4(__uint_as_float(pk[0]), __uint_as_float(pk[1]), __uint_as_float(pk[2]), __uint_as_float(pk[3])));
+                        }
+                        fence_async_smem();
+                        if (hh == 0) bar_sync128<1>(); else bar_sync128<2>();
+                        if (elected) {
+                            tma_store_4d(&p.tmY, slab16, nb, w0, h0, i0);
+                            tma_commit();
+                            if (has_res && item + nclus < nitems) {
+                                int w1, h1, i1, n1;
+                                decode(item + nclus, w1, h1, i1, n1);
+                                tma_wait_read<0>();
+                                mbar_expect_tx(&sm.res_full[hh * 2], (uint32_t)p.a_tx);
+                                tma_load_4d(slab16, &p.tmR, &sm.res_full[hh * 2], n1 + col0, w1, h1, i1);
+                            }
+                        }
+                    }
+                    if (threadIdx.x == 0) TC_TRACE(li, 6);
+                    continue;
+                }
 #pragma unroll
                 for (int s = 0; s < SLABS; ++s) {
                     if (has_res) mbar_wait(&sm.res_full[hh * 2 + s], (uint32_t)li & 1u);
@@ -1152,11 +1211,14 @@ static int tc_setup_epilogue(TcParams &p) {
     const int mode = tc_epi();
     if (mode <= 1) { p.epi = mode; return 0; }
     p.epi = p.res_mode == 0 ? 1 : 0;
-    if (mode == 3 && !p.out_bf16 && p.out_stride == 1 && (p.res_mode == 0 || (p.res_mode == 1 && !p.res_bf16))) {
+    const bool res_ok = p.res_mode == 0 || (p.res_mode == 1 && (p.res_bf16 != 0) == (p.out_bf16 != 0));      // same storage type as the output
+    const bool b16 = p.out_bf16 != 0;
+    if (mode == 3 && p.out_stride == 1 && res_ok && (!b16 || p.Cout % 128 == 0)) {
+        // one slab row = 128 bytes: 32 fp32 channels, or 64 bf16 channels (then only the 128-wide N tile: a group owns 64 channels)
         const cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
-        const cuuint32_t box[4] = {32, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BI};
-        int rc = make_map(&p.tmY, p.y, 4, dims, box, CU_TENSOR_MAP_SWIZZLE_128B, 1, nullptr, false);
-        if (!rc && p.res_mode) rc = make_map(&p.tmR, p.residual, 4, dims, box, CU_TENSOR_MAP_SWIZZLE_128B, 1, nullptr, false);
+        const cuuint32_t box[4] = {b16 ? 64u : 32u, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BI};
+        int rc = make_map(&p.tmY, p.y, 4, dims, box, CU_TENSOR_MAP_SWIZZLE_128B, 1, nullptr, b16);
+        if (!rc && p.res_mode) rc = make_map(&p.tmR, p.residual, 4, dims, box, CU_TENSOR_MAP_SWIZZLE_128B, 1, nullptr, b16);
         if (rc) return rc;
         p.epi = 3;
     }
