@@ -198,8 +198,11 @@ def sinkhorn_microbench(device, n=1024, batch=128, iters=50, launches=5, warm=3)
 
 # ------------------------------------------------------------------------------------------------ live per-launch timing
 @contextlib.contextmanager
-def timed_lib(names):
-    """Wraps the named C-ABI entry points with CUDA events (torch's current stream = the launch stream); yields the records."""
+def timed_lib(names, lead_cycles=0):
+    """Wraps the named C-ABI entry points with CUDA events (torch's current stream = the launch stream); yields the records.
+    lead_cycles > 0: a device-side spin of that many cycles is enqueued before the first event of every timed call, so that the
+    launch is already queued when the first event is stamped - the pair then brackets the kernel alone and not the host's launch
+    latency (~4 us per call when the stream has run dry, ~1 ms over the 263 conv launches of a step)."""
     from ttdg_b200 import _C
     lib = _C.lib()
     rec = []
@@ -210,6 +213,8 @@ def timed_lib(names):
 
         def __call__(self, *a):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if lead_cycles:
+                torch.cuda._sleep(lead_cycles)
             e0.record()
             rc = self.fn(*a)
             e1.record()
@@ -233,7 +238,7 @@ def conv_roofline(step_fn, conv, steps=2):
     SURVEY 8d) / summed kernel time; in the 3xTF32 parity mode the tensor pipe executes three TF32 MMAs per product, reported
     as `mma_tflops`.  `peak` = the measured dense bf16 rate (sustained: the kernels run inside a long step), halved for the
     TF32 modes (TF32 runs at half the 16-bit rate)."""
-    with timed_lib(("ttdg_conv_tc", "ttdg_wgrad_tc", "ttdg_stem_tc", "ttdg_stem_tc2", "ttdg_conv_tc_bf16")) as rec:
+    with timed_lib(("ttdg_conv_tc", "ttdg_wgrad_tc", "ttdg_stem_tc", "ttdg_stem_tc2", "ttdg_conv_tc_bf16"), lead_cycles=100000) as rec:
         for _ in range(steps):
             step_fn()
         torch.cuda.synchronize()
@@ -264,7 +269,8 @@ def conv_roofline(step_fn, conv, steps=2):
             "launches_per_step": len(rec) // steps, "ms_per_step": round(ms / steps, 3),
             "algorithmic_tflop_per_step": round(flops / steps / 1e12, 3),
             "note": ("3xTF32 parity mode: 3 TF32 MMAs per fp32-grade product; frac = algorithmic, frac_mma = tensor-pipe work"
-                     if conv == "tf32x3" else "frac = algorithmic flops / measured dense peak")}
+                     if conv == "tf32x3" else "frac = algorithmic flops / measured dense peak") +
+                    "; CUDA events around every launch, each preceded by a ~50 us device-side spin so that the pair brackets the kernel only"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU leg (oracle port)
