@@ -877,6 +877,8 @@ struct WgParams {
     int stride;                                  // 1, or 2 (1x1 convs): X is read through element strides {1, 2, 2, 1}
     int chunk;                                   // k-blocks per TMEM accumulation chunk
     uint64_t desc_hi;                            // shared-memory descriptor without the start address (see umma_desc_mn)
+    int nbx, nby;                                // work items: (tap, 128-channel block) x N tiles x pixel splits, x fastest
+    alignas(64) CUtensorMap tmW;                 // dW as {Cout, Cin, taps}, box {32, 128, 1}: the TMA reduce-add target
 };
 
 template <int BN_TILE, bool PRECISE>
@@ -886,9 +888,12 @@ struct WgCfg {
     // and dY is split in place: [X raw | dY hi | dY lo].  (Shared-memory traffic per k-block 224 KB -> 144 KB.)
     static constexpr int STAGE_BYTES = A_BYTES + (PRECISE ? 2 : 1) * B_BYTES;
     static constexpr int TX_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = PRECISE ? (BN_TILE == 128 ? 4 : 6) : (BN_TILE == 128 ? 6 : 8);
-    static constexpr int EPI_BYTES = 0;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+    // one stage fewer than the one-tile-per-CTA version: the room holds the 128 x BN fp32 result tile as BN / 32 slabs of
+    // [128 rows][128 B] (128-byte swizzle), the source of the TMA reduce-add into dW
+    static constexpr int STAGES = PRECISE ? (BN_TILE == 128 ? 3 : 4) : (BN_TILE == 128 ? 4 : 6);
+    static constexpr int EPI_BYTES = 128 * BN_TILE * 4;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256 + 1024;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static constexpr int ACC_COLS = 2 * BN_TILE;
     static constexpr int A_COLS = 64;                    // TMEM columns of one stage's X operand: 32 pixels hi + 32 lo
     static constexpr int TMEM_COLS = PRECISE ? 512 : ACC_COLS;
@@ -944,41 +949,56 @@ __device__ __forceinline__ void wg_split_loop(const TcSmem &sm, uint32_t tmem_ba
     }
 }
 
+// PERSISTENT like conv_tc_kernel: one CTA per SM walks the work items (tap / 128-channel block, N tile, pixel split); all roles keep
+// their ring / ping-pong counters running across items, so barrier + TMEM set-up is paid once per SM and the epilogue of item t
+// overlaps the loads / MMAs of item t + 1 (one item per CTA spent more time in set-up + epilogue than in its 8-k-block MMA loop on
+// the small layers).  The epilogue stages the 128 x BN tile in shared memory as swizzled slabs and ONE thread per column half adds
+// it to dW with a TMA reduce (cp.reduce.async.bulk.tensor .add, fp32) - no per-element atomics issued by the warps.
 template <int BN_TILE, bool PRECISE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, const WgParams p) {
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, const __grid_constant__ WgParams p) {
     using Cfg = WgCfg<BN_TILE, PRECISE>;
     extern __shared__ unsigned char tc_smem_raw[];
     TcSmem sm;
     const uint32_t tmem_base = tc_prologue<Cfg>(sm, tc_smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cblocks = p.Cin / 128;
-    const int tap = blockIdx.x / cblocks, ci0 = (blockIdx.x - tap * cblocks) * 128;
-    const int r = tap / p.S, s = tap - r * p.S;
-    const int n0 = blockIdx.y * BN_TILE;
+    const int nitems = p.nbx * p.nby * p.splits;
     const int per = (p.kblocks + p.splits - 1) / p.splits;
-    const int kb0 = blockIdx.z * per, kb1 = min(p.kblocks, kb0 + per);
-    const int KB = max(0, kb1 - kb0);
+    // item -> (tap, input-channel block, N tile, k-block range)
+    auto decode = [&](int item, int &tap, int &ci0, int &n0, int &kb0, int &kb1) {
+        const int bx = item % p.nbx, t = item / p.nbx;
+        const int by = t % p.nby, bz = t / p.nby;
+        tap = bx / cblocks; ci0 = (bx - tap * cblocks) * 128;
+        n0 = by * BN_TILE;
+        kb0 = bz * per; kb1 = min(p.kblocks, kb0 + per);
+        if (kb1 < kb0) kb1 = kb0;
+    };
 
     if (warp == TC_WARP_TMA) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = kb0; kb < kb1; ++kb) {
-                int t = kb;
-                const int tw = t % p.tilesW; t /= p.tilesW;
-                const int th = t % p.tilesH; t /= p.tilesH;
-                const int w0 = tw * p.BW, h0 = th * p.BH, i0 = t * p.BI;
-                mbar_wait(&sm.empty[stage], phase ^ 1);
-                unsigned char *st = sm.tiles + stage * Cfg::STAGE_BYTES;
-                mbar_expect_tx(&sm.full[stage], Cfg::TX_BYTES);
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                int tap, ci0, n0, kb0, kb1;
+                decode(item, tap, ci0, n0, kb0, kb1);
+                const int r = tap / p.S, s = tap - r * p.S;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    int t = kb;
+                    const int tw = t % p.tilesW; t /= p.tilesW;
+                    const int th = t % p.tilesH; t /= p.tilesH;
+                    const int w0 = tw * p.BW, h0 = th * p.BH, i0 = t * p.BI;
+                    mbar_wait(&sm.empty[stage], phase ^ 1);
+                    unsigned char *st = sm.tiles + stage * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(&sm.full[stage], Cfg::TX_BYTES);
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb)
-                    tma_load_4d(st + cb * 4096, &tmX, &sm.full[stage], ci0 + 32 * cb, (w0 + s - p.pad) * p.stride, (h0 + r - p.pad) * p.stride, i0);
+                    for (int cb = 0; cb < 4; ++cb)
+                        tma_load_4d(st + cb * 4096, &tmX, &sm.full[stage], ci0 + 32 * cb, (w0 + s - p.pad) * p.stride, (h0 + r - p.pad) * p.stride, i0);
 #pragma unroll
-                for (int nb = 0; nb < BN_TILE / 32; ++nb)
-                    tma_load_4d(st + Cfg::A_BYTES + nb * 4096, &tmD, &sm.full[stage], n0 + 32 * nb, w0, h0, i0);
-                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    for (int nb = 0; nb < BN_TILE / 32; ++nb)
+                        tma_load_4d(st + Cfg::A_BYTES + nb * 4096, &tmD, &sm.full[stage], n0 + 32 * nb, w0, h0, i0);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == TC_WARP_MMA) {
@@ -988,67 +1008,90 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (PRECISE ? 0u : (1u << 15)) | (1u << 16) |
                                    ((uint32_t)(BN_TILE >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             int stage = 0;
-            uint32_t phase = 0;
-            const int CHK = p.chunk, nchunks = (KB + CHK - 1) / CHK;
-            for (int ch = 0; ch < nchunks; ++ch) {
-                const int buf = ch & 1;
-                mbar_wait(&sm.tmem_empty[buf], ((ch >> 1) & 1) ^ 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tacc = tmem_base + (uint32_t)(buf * BN_TILE);
-                const int kend = min(KB, (ch + 1) * CHK);
-                for (int kb = ch * CHK; kb < kend; ++kb) {
-                    mbar_wait(PRECISE ? &sm.conv[stage] : &sm.full[stage], phase);
+            uint32_t phase = 0, gc = 0;                              // gc: accumulation chunks issued so far (ping-pong position)
+            const int CHK = p.chunk;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                int tap, ci0, n0, kb0, kb1;
+                decode(item, tap, ci0, n0, kb0, kb1);
+                const int KB = kb1 - kb0, nchunks = (KB + CHK - 1) / CHK;
+                for (int ch = 0; ch < nchunks; ++ch, ++gc) {
+                    const int buf = (int)(gc & 1u);
+                    mbar_wait(&sm.tmem_empty[buf], ((gc >> 1) & 1u) ^ 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a = smem_u32(sm.tiles + stage * Cfg::STAGE_BYTES), b = a + Cfg::A_BYTES;
-                    const uint32_t blo = b + Cfg::B_BYTES;
-                    const uint32_t ta = tmem_base + (uint32_t)(Cfg::ACC_COLS + stage * Cfg::A_COLS);
+                    const uint32_t tacc = tmem_base + (uint32_t)(buf * BN_TILE);
+                    const int kend = min(KB, (ch + 1) * CHK);
+                    for (int kb = ch * CHK; kb < kend; ++kb) {
+                        mbar_wait(PRECISE ? &sm.conv[stage] : &sm.full[stage], phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a = smem_u32(sm.tiles + stage * Cfg::STAGE_BYTES), b = a + Cfg::A_BYTES;
+                        const uint32_t blo = b + Cfg::B_BYTES;
+                        const uint32_t ta = tmem_base + (uint32_t)(Cfg::ACC_COLS + stage * Cfg::A_COLS);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {                            // 32 pixels = 4 MMAs of K = 8
-                        const uint32_t koff = k * 1024;
-                        const uint32_t first = (kb != ch * CHK) || k != 0;
-                        if (PRECISE) {
-                            umma_tf32_ts(tacc, ta + k * 8, umma_desc_mn(b + koff, p.desc_hi), idesc, first);
-                            umma_tf32_ts(tacc, ta + 32 + k * 8, umma_desc_mn(b + koff, p.desc_hi), idesc, 1);
-                            umma_tf32_ts(tacc, ta + k * 8, umma_desc_mn(blo + koff, p.desc_hi), idesc, 1);
-                        } else {
-                            umma_tf32(tacc, umma_desc_mn(a + koff, p.desc_hi), umma_desc_mn(b + koff, p.desc_hi), idesc, first);
+                        for (int k = 0; k < 4; ++k) {                            // 32 pixels = 4 MMAs of K = 8
+                            const uint32_t koff = k * 1024;
+                            const uint32_t first = (kb != ch * CHK) || k != 0;
+                            if (PRECISE) {
+                                umma_tf32_ts(tacc, ta + k * 8, umma_desc_mn(b + koff, p.desc_hi), idesc, first);
+                                umma_tf32_ts(tacc, ta + 32 + k * 8, umma_desc_mn(b + koff, p.desc_hi), idesc, 1);
+                                umma_tf32_ts(tacc, ta + k * 8, umma_desc_mn(blo + koff, p.desc_hi), idesc, 1);
+                            } else {
+                                umma_tf32(tacc, umma_desc_mn(a + koff, p.desc_hi), umma_desc_mn(b + koff, p.desc_hi), idesc, first);
+                            }
                         }
+                        umma_commit(&sm.empty[stage]);
+                        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&sm.empty[stage]);
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(&sm.tmem_full[buf]);
                 }
-                umma_commit(&sm.tmem_full[buf]);
             }
         }
     } else if (warp >= TC_WARP_CVT0) {
-        if (PRECISE) wg_split_loop<Cfg>(sm, tmem_base, KB);
-    } else {
-        const int q = warp & 3, col0 = (warp >> 2) * Cfg::EPI_COLS;
-        const int row = q * 32 + lane;                                       // input channel inside the tile
-        float acc[Cfg::EPI_COLS];
-        tc_drain<Cfg>(sm, tmem_base, KB, p.chunk, q, col0, acc);
-        // staged like the conv epilogue: thread = input-channel row in phase 1, a warp per row in phase 2, so that each
-        // reduction instruction adds 32 consecutive floats of dW (was: 32 rows Cout * 4 bytes apart)
-        constexpr int PITCH = BN_TILE + 4;
-        const uint32_t stg = smem_u32(sm.tiles);
-        {
-            const uint32_t srow = stg + (row * PITCH + col0) * 4;
-#pragma unroll
-            for (int jj = 0; jj < Cfg::EPI_COLS; jj += 4)
-                sts128(srow + jj * 4, make_float4(acc[jj], acc[jj + 1], acc[jj + 2], acc[jj + 3]));
+        if (PRECISE) {
+            int total = 0;                                           // k-blocks of all of this CTA's items
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                int tap, ci0, n0, kb0, kb1;
+                decode(item, tap, ci0, n0, kb0, kb1);
+                total += kb1 - kb0;
+            }
+            wg_split_loop<Cfg>(sm, tmem_base, total);
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
-        if (KB > 0) {
-            for (int r2 = warp; r2 < TC_BM; r2 += TC_EPI_WARPS) {
-                float *dst = p.dw + ((size_t)tap * p.Cin + ci0 + r2) * p.Cout + n0;
+    } else {
+        // ===================== epilogue: warps 0..7; warp w owns TMEM lanes (= input channels) 32 * (w % 4) .. and column half w / 4
+        constexpr int SLABS = Cfg::EPI_COLS / 32;
+        const int q = warp & 3, hh = warp >> 2, col0 = hh * Cfg::EPI_COLS;
+        const int gt = threadIdx.x & 127;                            // row of the tile = input channel
+        const bool elected = gt == 0;
+        unsigned char *slab_p = sm.epi + (size_t)(hh * SLABS) * 16384;
+        const uint32_t slab_a = smem_u32(slab_p);
+        uint32_t gc = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            int tap, ci0, n0, kb0, kb1;
+            decode(item, tap, ci0, n0, kb0, kb1);
+            const int KB = kb1 - kb0, nchunks = (KB + p.chunk - 1) / p.chunk;
+            if (KB <= 0) continue;                                   // an empty pixel split: nothing was accumulated (uniform per CTA)
+            float acc[Cfg::EPI_COLS];
+            tc_drain<Cfg>(sm, tmem_base, KB, p.chunk, q, col0, acc, gc);
+            gc += (uint32_t)nchunks;
 #pragma unroll
-                for (int c = 0; c < BN_TILE; c += 32) {
-                    float v;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(stg + (r2 * PITCH + c + lane) * 4) : "memory");
-                    atomicAdd(dst + c + lane, v);
+            for (int s = 0; s < SLABS; ++s) {
+                if (elected) tma_wait_read<SLABS - 1>();             // the previous reduce of this slab has been read out
+                if (hh == 0) bar_sync128<1>(); else bar_sync128<2>();
+                const uint32_t rowa = slab_a + (uint32_t)s * 16384u + (uint32_t)gt * 128u;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int j = s * 32 + c * 4;
+                    sts128(rowa + (uint32_t)((c ^ (gt & 7)) << 4), make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+                }
+                fence_async_smem();
+                if (hh == 0) bar_sync128<1>(); else bar_sync128<2>();
+                if (elected) {
+                    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                 ::"l"(&p.tmW), "r"(slab_a + (uint32_t)s * 16384u), "r"(n0 + col0 + s * 32), "r"(ci0), "r"(tap) : "memory");
+                    tma_commit();
                 }
             }
         }
+        if (elected) tma_wait_all();
     }
     tc_epilogue_end<Cfg>(tmem_base);
 }
@@ -1278,7 +1321,9 @@ static int launch_wg(const CUtensorMap &x, const CUtensorMap &d, const WgParams 
     using Cfg = WgCfg<BN_TILE, PRECISE>;
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN_TILE, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return (int)e;
-    dim3 grid((p.Cin / 128) * p.R * p.S, p.Cout / BN_TILE, p.splits);
+    const int items = p.nbx * p.nby * p.splits;
+    int grid = tc_sm_count();
+    if (grid > items) grid = items;
     count_launches(1);
     wgrad_tc_kernel<BN_TILE, PRECISE><<<grid, TC_THREADS, Cfg::SMEM, st>>>(x, d, p);
     return (int)cudaGetLastError();
@@ -1312,8 +1357,15 @@ extern "C" int ttdg_wgrad_tc(const float *x, const float *dy, int precise, int N
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     p.splits = splits;
+    p.nbx = (Cin / 128) * R * S; p.nby = Cout / bn_tile;
     p.chunk = tc_chunk();
     p.desc_hi = umma_desc_mn_hi(4096 >> 4, 512 >> 4, 1);
+    {   // dW [taps][Cin][Cout] as a TMA map: the epilogue adds 32-channel x 128-row slabs of the result tile to it
+        const cuuint64_t wdims[3] = {(cuuint64_t)Cout, (cuuint64_t)Cin, (cuuint64_t)(R * S)};
+        const cuuint32_t wbox[3] = {32, 128, 1};
+        const int rcw = make_map(&p.tmW, dw, 3, wdims, wbox);
+        if (rcw) return rcw;
+    }
     CUtensorMap mx, md;
     const cuuint64_t xdims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t ddims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
