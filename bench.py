@@ -465,6 +465,7 @@ def main():
 
     # ---- where the time goes, per rank (3 extra instrumented steps: CUDA events at the stage boundaries + around the solver)
     marks = []
+    barrier()                                                # ranks enter the instrumented steps together (allreduce_wait = skew of the step only)
     with timed_lib(("ttdg_gagm_solve",)) as grec:
         for _ in range(3):
             flush.zero_()
