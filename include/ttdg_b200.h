@@ -145,7 +145,9 @@ int ttdg_gagm_set_lap_fast(int on);
  * info (int32[16], device): {iterations, sinkhorn-stage iterations, hungarian-stage iterations, LAP calls,
  *                           sinkhorn stages, Dijkstra steps / path hops / certificate fall-backs of graph 0's LAPs,
  *                           cycle accounting of CTA 0 in units of 1024 cycles: whole kernel, Hungarian-stage iterations,
- *                           inside the LAP, waiting at cluster barriers, 0, 0, 0, 0}.
+ *                           inside the LAP, waiting at cluster barriers; Sinkhorn-stage iterations: phase 1, V products, projector;
+ *                           [15] = 1 if a Hungarian projection met a NaN / inf cost (zeroed so that the solve ends; SciPy raises
+ *                           "matrix contains invalid numeric entries" there, the host mirror does the same in check_flags())}.
  * scratch: ttdg_gagm_scratch_bytes(M, G).
  * trace (optional, may be NULL): fp64[(trace_cap + 1)][M][32] receives U_t of every iteration t <= trace_cap
  * (U_0 = U0) and trace_meta fp64[trace_cap][2] = {projector, tau} - lets a test verify EVERY iteration of the

@@ -199,8 +199,8 @@ elif what == "gagm_fixed":
                     ms += e0.elapsed_time(e1) / reps
             _C.lib().ttdg_gagm_set_lap_fast(prev)
             inf = info.tolist()
-            print("gagm_fixed lap_fast %d sizes %s: %.3f ms, iterations %d (sinkhorn %d, hungarian %d), %.1f us / hungarian iteration incl. everything, graph-0 LAP steps %d, fast-path fall-backs %d; CTA-0 kcycles: kernel %d, hungarian stage %d, in LAP %d, barrier wait %d"
-                  % (mode, sizes, ms, inf[0], inf[1], inf[2], 1e3 * ms / max(inf[2], 1), inf[5], inf[7], inf[8], inf[9], inf[10], inf[11]))
+            print("gagm_fixed lap_fast %d sizes %s: %.3f ms, iterations %d (sinkhorn %d, hungarian %d), %.1f us / hungarian iteration incl. everything, graph-0 LAP steps %d, fast-path fall-backs %d; CTA-0 kcycles: kernel %d, hungarian stage %d, in LAP %d, barrier wait %d; sinkhorn stage: phase 1 %d, V %d, projector %d"
+                  % (mode, sizes, ms, inf[0], inf[1], inf[2], 1e3 * ms / max(inf[2], 1), inf[5], inf[7], inf[8], inf[9], inf[10], inf[11], inf[12], inf[13], inf[14]))
 elif what == "gagm_bench":
     # the GA-GM solver on the BENCH workload's own problems: run the bench step a few times (the weights drift), then time the
     # solver alone on the step's (A, Wds, U0) under every LAP mode
@@ -216,7 +216,7 @@ elif what == "gagm_bench":
         if step_i in (3, 9, 15):
             aux = m.multi_matching_unsup.last_aux
             sizes = list(aux["sizes"])
-            for mode in (0, 3, 4):
+            for mode in (3,):
                 prev = _C.lib().ttdg_gagm_set_lap_fast(mode)
                 ms = 0.0
                 for r in range(reps + 1):
@@ -229,8 +229,8 @@ elif what == "gagm_bench":
                 _C.lib().ttdg_gagm_set_lap_fast(prev)
                 inf = info.tolist()
                 print("gagm_bench step %d lap_fast %d sizes %s: %.3f ms, iterations %d (sinkhorn %d, hungarian %d), graph-0 LAP steps %d, fall-backs %d; "
-                      "CTA-0 kcycles: kernel %d, hungarian stage %d, in LAP %d, barrier wait %d" %
-                      (step_i, mode, sizes, ms, inf[0], inf[1], inf[2], inf[5], inf[7], inf[8], inf[9], inf[10], inf[11]))
+                      "CTA-0 kcycles: kernel %d, hungarian stage %d, in LAP %d, barrier wait %d; sinkhorn stage: phase 1 %d, V %d, projector %d" %
+                      (step_i, mode, sizes, ms, inf[0], inf[1], inf[2], inf[5], inf[7], inf[8], inf[9], inf[10], inf[11], inf[12], inf[13], inf[14]))
 elif what == "busy":
     # hot (not cold-cache) per-kernel device time of the full step and the GPU-busy fraction, from CUPTI via torch.profiler
     sys.path.insert(0, ROOT)

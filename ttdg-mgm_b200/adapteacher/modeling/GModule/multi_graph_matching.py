@@ -147,3 +147,5 @@ class MGM3_unsup(nn.Module):
         """Deferred form of the reference's range assertions (losses.py:437-442): one host sync, on demand."""
         if self.last_aux is not None and int(self.last_aux["flags"].item()) != 0:
             raise AssertionError("matching loss inputs left [0, 1]")
+        if self.last_aux is not None and int(self.last_aux["info"][15].item()) != 0:
+            raise ValueError("matrix contains invalid numeric entries")       # SciPy's linear_sum_assignment (utils/hungarian.py:34)

@@ -101,7 +101,9 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
     double *T = Z + GAGM_MAX_N * ZP;                       // NU x NU
     double *padv = T + NU * NU;                            // GAGM_MAX_N
     double *red = padv + GAGM_MAX_N;                       // 2 * GAGM_WARPS
-    LapWork *lapw = reinterpret_cast<LapWork *>(red + 2 * GAGM_WARPS);
+    double *avec = red + 2 * GAGM_WARPS;                   // NU + 8: row scalings of the Sinkhorn projector (+ the dummy rows' one)
+    double *bvec = avec + NU + 8;                          // GAGM_MAX_N: its column scalings
+    LapWork *lapw = reinterpret_cast<LapWork *>(bvec + GAGM_MAX_N);
     int *nodeof_s = reinterpret_cast<int *>(lapw + 1);      // G x NU: node_of of every graph (Hungarian stage)
     int *slot_s = nodeof_s + GAGM_MAX_G * NU;               // GAGM_MAX_N: universe slot of each node of the current graph
 
@@ -125,6 +127,7 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
     // cycle accounting of CTA 0 / thread 0 (info[8..12], units of 1024 cycles): whole kernel, Hungarian-stage iterations, LAP, cluster-barrier waits
     const long long ck_start = clock64();
     long long ck_hung = 0, ck_lap = 0, ck_bar = 0;
+    long long ck_p1 = 0, ck_v = 0, ck_proj = 0;             // Sinkhorn-stage iterations: phase 1 + its barrier, V = chain + W U, projector
     int cur = 0, last = 1, last2 = 2;
     double tau = p.init_tau;
     int projector = (p.mode == 1) ? p.step_projector : 0;   // 0 sinkhorn, 1 hungarian
@@ -136,6 +139,7 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
         for (int i = 0; i < p.max_iter; ++i) {
             { const int nxt = last2; last2 = last; last = cur; cur = nxt; }   // lastU2 = lastU; lastU = U (mgm:313-314)
             const long long ck_it = clock64();
+            long long ck_ph2 = ck_it;
             const double *Ul = p.Ubuf + (size_t)last * UB;      // U_t
             const double *Ul2 = p.Ubuf + (size_t)last2 * UB;    // U_{t-1}
             double *Un = p.Ubuf + (size_t)cur * UB;             // U_{t+1}
@@ -183,6 +187,8 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
             p.Tpart[(size_t)c * NU * NU + e0 + 1] = t1;
             __threadfence();
             cluster_sync_all();
+            ck_p1 += clock64() - ck_it;
+            ck_ph2 = clock64();
 
             // ================= phase 2
             {
@@ -266,6 +272,8 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                     }
                 }
                 __syncthreads();
+                const long long ck_pj = clock64();
+                if (projector == 0) ck_v += ck_pj - ck_ph2;
                 // ---- projector -> U_new_g in Ug
                 if (projector == 0) {
                     // working matrix = transpose (rows = universe) for n > 32, and for n == 32 inside a ragged batch
@@ -274,16 +282,74 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                     const int nr = tr ? NU : n, nq = tr ? n : NU;
                     const int ldr = tr ? 1 : ZP, ldq = tr ? ZP : 1;
                     const int mult = nq - nr;                      // dummy_row = True (mgm:333-349)
+                    // The reference normalises in the log domain: z -= logsumexp over rows / columns, alternately, sk_iter times, then
+                    // exp - one fp64 exp per element per step: the projector was FP64-pipe bound (~100 k cycles per iteration, a third
+                    // of the solver on the bench workload).  Here only the first TWO steps (a row and a column normalisation) run in
+                    // the log domain; they bring every entry to <= 0 with column sums 1 and row sums >= 1 / 33, so K = exp(z_2) cannot
+                    // lose a row or a column to underflow (entries that do underflow are < 1e-300 of their row's and column's mass:
+                    // the log form's own final exp returns 0 for them too).  The remaining steps use the SCALING form of the same
+                    // iteration: exp(z_k)_rq = a_r K_rq b_q, row step a_r = 1 / sum_q K_rq b_q (dummy rows, all alike: a_d = 1 /
+                    // sum_q kd_q b_q), column step b_q = 1 / (sum_r a_r K_rq + mult a_d kd_q) - multiply-adds, one thread per line, no
+                    // cross-lane reductions.  Identical in exact arithmetic; ~1e-15 relative apart in fp64.
                     for (int q = tid; q < nq; q += GAGM_THREADS) padv[q] = -100.0;
                     __syncthreads();
-                    for (int k = 0; k < p.sk_iter; ++k) {
+                    const int klog = p.sk_iter < 2 ? p.sk_iter : 2;
+                    for (int k = 0; k < klog; ++k) {
                         sinkhorn_step(Z, ldr, ldq, nr, nq, padv, mult, k, nullptr, warp, GAGM_WARPS, lane);
                         __syncthreads();
                     }
-                    for (int e = tid; e < n * NU; e += GAGM_THREADS) Ug[e] = exp(Z[(e / NU) * ZP + (e % NU)]);
-                } else {
-                    for (int e = tid; e < n * NU; e += GAGM_THREADS) Ug[e] = 0.0;
+                    for (int e = tid; e < n * NU; e += GAGM_THREADS) Z[(e / NU) * ZP + (e % NU)] = exp(Z[(e / NU) * ZP + (e % NU)]);   // K (or the result)
+                    for (int q = tid; q < nq; q += GAGM_THREADS) { padv[q] = exp(padv[q]); bvec[q] = 1.0; }                          // kd, b
+                    if (tid <= nr && tid < NU + 8) avec[tid] = 1.0;
                     __syncthreads();
+                    for (int k = klog; k < p.sk_iter; ++k) {
+                        if ((k & 1) == 0) {
+                            if (tid < nr) {
+                                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                                const double *zr = Z + tid * ldr;
+                                int q = 0;
+                                for (; q + 3 < nq; q += 4) {
+                                    s0 = fma(zr[q * ldq], bvec[q], s0); s1 = fma(zr[(q + 1) * ldq], bvec[q + 1], s1);
+                                    s2 = fma(zr[(q + 2) * ldq], bvec[q + 2], s2); s3 = fma(zr[(q + 3) * ldq], bvec[q + 3], s3);
+                                }
+                                for (; q < nq; ++q) s0 = fma(zr[q * ldq], bvec[q], s0);
+                                avec[tid] = 1.0 / ((s0 + s1) + (s2 + s3));
+                            } else if (tid == 32 && mult > 0) {
+                                double s0 = 0.0;
+                                for (int q = 0; q < nq; ++q) s0 = fma(padv[q], bvec[q], s0);
+                                avec[nr] = 1.0 / s0;
+                            }
+                        } else if (tid < nq) {
+                            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                            const double *zq = Z + tid * ldq;
+                            int r = 0;
+                            for (; r + 3 < nr; r += 4) {
+                                s0 = fma(avec[r], zq[r * ldr], s0); s1 = fma(avec[r + 1], zq[(r + 1) * ldr], s1);
+                                s2 = fma(avec[r + 2], zq[(r + 2) * ldr], s2); s3 = fma(avec[r + 3], zq[(r + 3) * ldr], s3);
+                            }
+                            for (; r < nr; ++r) s0 = fma(avec[r], zq[r * ldr], s0);
+                            bvec[tid] = 1.0 / (((s0 + s1) + (s2 + s3)) + (mult > 0 ? (double)mult * avec[nr] * padv[tid] : 0.0));
+                        }
+                        __syncthreads();
+                    }
+                    // U_new (node-major n x NU) = a K b on the real rows
+                    for (int e = tid; e < n * NU; e += GAGM_THREADS) {
+                        const int node = e / NU, slot = e % NU;
+                        const int r = tr ? slot : node, q = tr ? node : slot;
+                        Ug[e] = avec[r] * Z[node * ZP + slot] * bvec[q];
+                    }
+                    ck_proj += clock64() - ck_pj;
+                } else {
+                    // SciPy refuses a cost matrix with NaN / inf ("matrix contains invalid numeric entries", utils/hungarian.py:34 ->
+                    // linear_sum_assignment); the shortest-path search would not terminate on one.  Non-finite entries are zeroed so
+                    // that the solve ends, and info[15] tells the host to raise the same error.
+                    int bad = 0;
+                    for (int e = tid; e < n * NU; e += GAGM_THREADS) {
+                        Ug[e] = 0.0;
+                        double &zv = Z[(e / NU) * ZP + (e % NU)];
+                        if (!(fabs(zv) <= 1.79e308)) { zv = 0.0; bad = 1; }
+                    }
+                    if (__syncthreads_or(bad) && tid == 0 && p.info) p.info[15] = 1;
                     if (warp == 0) {
                         const long long ck_l = clock64();
                         const double *Zc = Z;
@@ -365,11 +431,12 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
         p.info[5] = lapw->stat_steps; p.info[6] = lapw->stat_hops; p.info[7] = lapw->stat_fast_fallback;     // graph 0's LAPs: Dijkstra steps, path hops
         p.info[8] = (int)((clock64() - ck_start) >> 10); p.info[9] = (int)(ck_hung >> 10); p.info[10] = (int)(ck_lap >> 10);
         p.info[11] = (int)(ck_bar >> 10);
+        p.info[12] = (int)(ck_p1 >> 10); p.info[13] = (int)(ck_v >> 10); p.info[14] = (int)(ck_proj >> 10);
     }
 }
 
 static size_t gagm_smem_bytes() {
-    return (size_t)(3 * GAGM_MAX_N * NU + GAGM_MAX_N * ZP + NU * NU + GAGM_MAX_N + 2 * GAGM_WARPS) * sizeof(double) +
+    return (size_t)(3 * GAGM_MAX_N * NU + GAGM_MAX_N * ZP + NU * NU + 2 * GAGM_MAX_N + 2 * GAGM_WARPS + NU + 8) * sizeof(double) +
            sizeof(LapWork) + (size_t)(GAGM_MAX_G * NU + GAGM_MAX_N) * sizeof(int) + 16;
 }
 
