@@ -133,6 +133,12 @@ int ttdg_gemm_f64acc(int transA, int transB, int m, int n, int k, const void *A,
  * solve otherwise.  Same results by
  * construction (mgm:324-328 -> utils/hungarian.py:58-65).  Returns the previous setting. */
 int ttdg_gagm_set_lap_fast(int on);
+/* Diagnostic (tools/run_kernels.py gagm_*): cycles CTA 0 spent in the segments of the Hungarian-stage iterations of the last
+ * ttdg_gagm_solve - out24 = {T build, Q gather, V1 = A Q, V2 = W U, V store, projection, U store + norms, norm reduce,
+ * cluster barrier, tail; inside graph 0's lean LAPs: auction scans, bid resolution, augmentations, certificate, its
+ * reachability part, its Kahn part}, [16..23] = free rows at the start of each auction round / after the last, summed over
+ * graph 0's LAPs.  Synchronises the device. */
+int ttdg_gagm_read_profile(int64_t *out24);
 /* ---------------------------------------------------------------------------------------------
  * GA-GM solver.  Replaces GA_GM.forward + gagm (multi_graph_matching.py:223-244, 300-389) for the
  * configuration the hot path uses (num_clusters = 1, projector0 = 'sinkhorn', hung_iter = True) including

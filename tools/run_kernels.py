@@ -187,7 +187,7 @@ elif what == "gagm_fixed":
             m([n.to(dev) for n in nodes], [l.to(dev) for l in labels], U)
         aux = m.last_aux
         from ttdg_b200 import _C
-        for mode in (0, 3, 4):
+        for mode in ((3,) if os.environ.get('TTDG_FIXED_MODE3') else (0, 3, 4)):
             prev = _C.lib().ttdg_gagm_set_lap_fast(mode)
             ms = 0.0
             for _ in range(reps + 1):
@@ -201,6 +201,13 @@ elif what == "gagm_fixed":
             inf = info.tolist()
             print("gagm_fixed lap_fast %d sizes %s: %.3f ms, iterations %d (sinkhorn %d, hungarian %d), %.1f us / hungarian iteration incl. everything, graph-0 LAP steps %d, fast-path fall-backs %d; CTA-0 kcycles: kernel %d, hungarian stage %d, in LAP %d, barrier wait %d; sinkhorn stage: phase 1 %d, V %d, projector %d"
                   % (mode, sizes, ms, inf[0], inf[1], inf[2], 1e3 * ms / max(inf[2], 1), inf[5], inf[7], inf[8], inf[9], inf[10], inf[11], inf[12], inf[13], inf[14]))
+            if mode == 3:
+                import ctypes
+                seg = (ctypes.c_int64 * 24)()
+                _C.lib().ttdg_gagm_read_profile(seg)
+                print("gagm_fixed lap_fast 3   hungarian-stage kcycles of CTA 0: T build %d, Q gather %d, V1 %d, V2 %d, V store %d, projection %d, U store + norms %d, "
+                      "norm reduce %d, barrier %d, tail %d; LAP: auction scans %d, bids %d, augmentations %d, certificate %d (reach %d, Kahn %d); free rows per round %s"
+                      % (tuple(int(v) >> 10 for v in seg[:16]) + (str([int(v) for v in seg[16:21]]),)))
 elif what == "gagm_bench":
     # the GA-GM solver on the BENCH workload's own problems: run the bench step a few times (the weights drift), then time the
     # solver alone on the step's (A, Wds, U0) under every LAP mode
@@ -231,6 +238,11 @@ elif what == "gagm_bench":
                 print("gagm_bench step %d lap_fast %d sizes %s: %.3f ms, iterations %d (sinkhorn %d, hungarian %d), graph-0 LAP steps %d, fall-backs %d; "
                       "CTA-0 kcycles: kernel %d, hungarian stage %d, in LAP %d, barrier wait %d; sinkhorn stage: phase 1 %d, V %d, projector %d" %
                       (step_i, mode, sizes, ms, inf[0], inf[1], inf[2], inf[5], inf[7], inf[8], inf[9], inf[10], inf[11], inf[12], inf[13], inf[14]))
+                import ctypes
+                seg = (ctypes.c_int64 * 24)()
+                _C.lib().ttdg_gagm_read_profile(seg)
+                print("gagm_bench   hungarian-stage kcycles of CTA 0: T build %d, Q gather %d, V1 %d, V2 %d, V store %d, projection %d, U store + norms %d, "
+                      "norm reduce %d, barrier %d, tail %d; LAP: auction scans %d, bids %d, augmentations %d, certificate %d (reach %d, Kahn %d); free rows per round %s" % (tuple(int(v) >> 10 for v in seg[:16]) + (str([int(v) for v in seg[16:21]]),)))
 elif what == "busy":
     # hot (not cold-cache) per-kernel device time of the full step and the GPU-busy fraction, from CUPTI via torch.profiler
     sys.path.insert(0, ROOT)

@@ -52,9 +52,17 @@ struct GagmParams {
     int G, M, C;
     double init_tau, min_tau, sk_gamma, tol, quad_weight;
     int max_iter, sk_iter, mode, step_projector, sq_transposed;
+    int uall;            // shared memory holds U of all graphs (M * NU doubles fit)
+    int hfast;           // G <= cluster size (one graph per CTA): Hungarian-stage iterations exchange node_of / norms through DSMEM,
+                         // count the norms, keep an fp64 copy of the CTA's own block of A in shared memory
+    int hcache;          // hfast and the diagonal blocks of A + this CTA's rows of W fit in shared memory as fp32 copies (the region
+                         // U-all used during the Sinkhorn stage): the gathers of T and W U read them instead of global memory
+    int aoff[GAGM_MAX_C + 1];   // hfast: float offset of graph h's n_h x n_h block in the shared copy
     int lap_fast;        // TTDG_LAP_FAST=1: certified row-reduction LAP first, SciPy-order solve as the fall-back (lap.cuh)
     int node_off[GAGM_MAX_G + 1];
 };
+
+__device__ long long g_gagm_prof[24];      // CTA 0 / thread 0: cycles per segment of the Hungarian-stage iterations (ttdg_gagm_read_profile)
 
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
@@ -72,24 +80,48 @@ __device__ __forceinline__ void rows_times_tile_r(const float *__restrict__ Mg, 
         const int i = warp + GAGM_WARPS * r;
         rp[r] = Mg + (size_t)(i < nrows ? i : 0) * ld;
     }
-#pragma unroll 4
+    // 8 columns per batch for the narrow variant: the rows of W come from L2 (~700 cycles), the batch's loads are in flight together
+#pragma unroll(R <= 3 ? 8 : 4)
     for (int j = 0; j < ncols; ++j) {
         const double sv = S[j * NU + lane];
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = fma((double)__ldg(rp[r] + j), sv, acc[r]);
     }
 }
-__device__ __forceinline__ void rows_times_tile(const float *__restrict__ Mg, int ld, int nrows, int ncols,
-                                                const double *__restrict__ S, double (&acc)[RPW], int warp, int lane) {
-    switch ((nrows + GAGM_WARPS - 1) / GAGM_WARPS) {
-        case 1: rows_times_tile_r<1>(Mg, ld, nrows, ncols, S, acc, warp, lane); break;
-        case 2: rows_times_tile_r<2>(Mg, ld, nrows, ncols, S, acc, warp, lane); break;
-        case 3: rows_times_tile_r<3>(Mg, ld, nrows, ncols, S, acc, warp, lane); break;
-        case 4: rows_times_tile_r<4>(Mg, ld, nrows, ncols, S, acc, warp, lane); break;
-        case 5: rows_times_tile_r<5>(Mg, ld, nrows, ncols, S, acc, warp, lane); break;
-        default: rows_times_tile_r<6>(Mg, ld, nrows, ncols, S, acc, warp, lane); break;
+// the same product with an fp64 copy of the matrix in shared memory (pitch = nrows = ncols = n): no widening at all
+template <int R>
+__device__ __forceinline__ void rows_times_tile_d_r(const double *Md, int n, const double *S, double (&acc)[RPW], int warp, int lane) {
+    const double *rp[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { const int i = warp + GAGM_WARPS * r; rp[r] = Md + (i < n ? i : 0) * n; }
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+        const double sv = S[j * NU + lane];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = fma(rp[r][j], sv, acc[r]);
     }
 }
+__device__ __forceinline__ void rows_times_tile_d(const double *Md, int n, const double *S, double (&acc)[RPW], int warp, int lane) {
+    switch ((n + GAGM_WARPS - 1) / GAGM_WARPS) {
+        case 1: rows_times_tile_d_r<1>(Md, n, S, acc, warp, lane); break;
+        case 2: rows_times_tile_d_r<2>(Md, n, S, acc, warp, lane); break;
+        case 3: rows_times_tile_d_r<3>(Md, n, S, acc, warp, lane); break;
+        default: rows_times_tile_d_r<4>(Md, n, S, acc, warp, lane); break;      // n * n <= GAGM_MAX_N * NU: n <= 55
+    }
+}
+// Two row-count variants only (<= 48 and <= 96 nodes; surplus rows repeat row 0 and are dropped): with six variants inlined at four
+// call sites the kernel's code grew enough to slow the LAP's loops down (measured), and an out-of-line copy keeps the accumulators
+// in local memory (3x slower).
+__device__ __forceinline__ void rows_times_tile(const float *__restrict__ Mg, int ld, int nrows, int ncols,
+                                                const double *__restrict__ S, double (&acc)[RPW], int warp, int lane) {
+    if (nrows <= 3 * GAGM_WARPS) rows_times_tile_r<3>(Mg, ld, nrows, ncols, S, acc, warp, lane);
+    else rows_times_tile_r<6>(Mg, ld, nrows, ncols, S, acc, warp, lane);
+}
+
+// bytes of the fixed part of the dynamic shared memory (everything before the U-all / Hungarian-stage cache region), 16-aligned
+constexpr size_t GAGM_FIXED_SMEM =
+    (((size_t)(3 * GAGM_MAX_N * NU + GAGM_MAX_N * ZP + NU * NU + 2 * GAGM_MAX_N + 2 * GAGM_WARPS + NU + 8 + 4 * GAGM_MAX_C) * sizeof(double) +
+      sizeof(LapWork) + (size_t)(GAGM_MAX_G * NU + GAGM_MAX_N) * sizeof(int)) + 15) & ~(size_t)15;
 
 __global__ void __launch_bounds__(GAGM_THREADS, 1)
 gagm_kernel(const __grid_constant__ GagmParams p) {
@@ -103,9 +135,16 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
     double *red = padv + GAGM_MAX_N;                       // 2 * GAGM_WARPS
     double *avec = red + 2 * GAGM_WARPS;                   // NU + 8: row scalings of the Sinkhorn projector (+ the dummy rows' one)
     double *bvec = avec + NU + 8;                          // GAGM_MAX_N: its column scalings
-    LapWork *lapw = reinterpret_cast<LapWork *>(bvec + GAGM_MAX_N);
+    double *normx = bvec + GAGM_MAX_N;                     // 2 x 2 GAGM_MAX_C (hfast): every CTA's norm partials, by iteration parity
+    LapWork *lapw = reinterpret_cast<LapWork *>(normx + 4 * GAGM_MAX_C);
     int *nodeof_s = reinterpret_cast<int *>(lapw + 1);      // G x NU: node_of of every graph (Hungarian stage)
     int *slot_s = nodeof_s + GAGM_MAX_G * NU;               // GAGM_MAX_N: universe slot of each node of the current graph
+    // optional: U_t of ALL graphs (M x NU fp64) for the dense W U product of the Sinkhorn-stage iterations, when it fits
+    // (carved at a compile-time offset: pointer arithmetic through an integer would hide the shared address space - generic loads)
+    double *Uall = reinterpret_cast<double *>(gsm + GAGM_FIXED_SMEM);
+    // hfast, Hungarian stage (U-all is not needed any more): the diagonal blocks of A and this CTA's rows of W as fp32 copies
+    float *Ad_s = reinterpret_cast<float *>(Uall);
+    float *W_s = Ad_s + ((p.aoff[p.G <= GAGM_MAX_C ? p.G : 0] + 3) & ~3);
 
     const int c = blockIdx.x, C = p.C, G = p.G, M = p.M;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -123,16 +162,29 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
     __threadfence();
     cluster_sync_all();
 
-    if (tid == 0) { lapw->stat_steps = 0; lapw->stat_hops = 0; lapw->stat_fast_ok = 0; lapw->stat_fast_fallback = 0; }
+    if (tid == 0) {
+        lapw->stat_steps = 0; lapw->stat_hops = 0; lapw->stat_fast_ok = 0; lapw->stat_fast_fallback = 0;
+        for (int i = 0; i < 6; ++i) lapw->stat_ck[i] = 0;
+        for (int i = 0; i < 8; ++i) lapw->stat_free[i] = 0;
+    }
     // cycle accounting of CTA 0 / thread 0 (info[8..12], units of 1024 cycles): whole kernel, Hungarian-stage iterations, LAP, cluster-barrier waits
     const long long ck_start = clock64();
     long long ck_hung = 0, ck_lap = 0, ck_bar = 0;
     long long ck_p1 = 0, ck_v = 0, ck_proj = 0;             // Sinkhorn-stage iterations: phase 1 + its barrier, V = chain + W U, projector
+    long long hs[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};      // Hungarian-stage segments
+    long long hk = 0;
+#define HSEG(i) do { const long long now_ = clock64(); if (binU) hs[i] += now_ - hk; hk = now_; } while (0)
     int cur = 0, last = 1, last2 = 2;
     double tau = p.init_tau;
     int projector = (p.mode == 1) ? p.step_projector : 0;   // 0 sinkhorn, 1 hungarian
     int it_total = 0, it_sk = 0, it_hg = 0, n_lap = 0, n_stage = 0;
     bool binU = false;                                      // U_t came from a Hungarian projection: node_of[it_total & 1] is valid
+    const bool hf = p.hfast != 0;                           // then g == c is this CTA's only graph
+    const bool gp2 = (G & (G - 1)) == 0;
+    const double invG = 1.0 / (double)G;
+    bool cache_ready = false, last_lean = false;
+    int nd_cur = -1, nd_prev = -1;                          // hfast, tid < NU: node of this CTA's graph in slot tid under U_t / U_{t-1}
+    cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
 
     while (true) {
         bool stop_all = false;
@@ -147,7 +199,47 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
             const int e0 = 2 * tid, u1 = e0 / NU, u2 = e0 % NU;
             const int32_t *nodeof_cur = p.nodeof + (size_t)(it_total & 1) * GAGM_MAX_G * NU;
             int32_t *nodeof_nxt = p.nodeof + (size_t)((it_total + 1) & 1) * GAGM_MAX_G * NU;
-            if (binU) {
+            // hfast: node_of of every graph arrives in shared memory (written by its owner through DSMEM before the last barrier)
+            const int *nos = hf ? nodeof_s + (it_total & 1) * (GAGM_MAX_C * NU) : nodeof_s;
+            if (binU && hf) {
+                // ================= Hungarian stage without global memory
+                const int o_c = p.node_off[c], n_c = p.node_off[c + 1] - o_c;
+                const bool a64 = n_c * n_c <= GAGM_MAX_N * NU;     // fp64 copy of the own block of A in the (idle) U_h tile
+                if (!cache_ready) {
+                    if (p.hcache) {
+                        for (int h = 0; h < G; ++h) {
+                            const int oh = p.node_off[h], nh = p.node_off[h + 1] - oh;
+                            for (int e = tid; e < nh * nh; e += GAGM_THREADS)
+                                Ad_s[p.aoff[h] + e] = __ldg(p.A + (size_t)(oh + e / nh) * M + oh + e % nh);
+                        }
+                        for (int e = tid; e < n_c * M; e += GAGM_THREADS) W_s[e] = __ldg(p.W + (size_t)o_c * M + e);
+                    }
+                    if (a64)
+                        for (int e = tid; e < n_c * n_c; e += GAGM_THREADS)
+                            Uo[e] = (double)__ldg(p.A + (size_t)(o_c + e / n_c) * M + o_c + e % n_c);
+                    cache_ready = true;
+                    __syncthreads();
+                }
+                double t0 = 0.0, t1 = 0.0;
+                float a2v[GAGM_MAX_C], a3v[GAGM_MAX_C];            // branch-free: the eight gathers overlap; absent terms add + 0.0 (exact)
+#pragma unroll
+                for (int h = 0; h < GAGM_MAX_C; ++h) {
+                    a2v[h] = 0.f; a3v[h] = 0.f;
+                    if (h < G) {
+                        const int oh = p.node_off[h], nh = p.node_off[h + 1] - oh;
+                        const int n1 = nos[h * NU + u1], n2 = nos[h * NU + u2], n3 = nos[h * NU + u2 + 1];
+                        float a2, a3;
+                        if (p.hcache) { const float *arow = Ad_s + p.aoff[h] + max(n1, 0) * nh; a2 = arow[max(n2, 0)]; a3 = arow[max(n3, 0)]; }
+                        else { const float *arow = p.A + (size_t)(oh + max(n1, 0)) * M + oh; a2 = __ldg(arow + max(n2, 0)); a3 = __ldg(arow + max(n3, 0)); }
+                        a2v[h] = (n1 >= 0 && n2 >= 0) ? a2 : 0.f;
+                        a3v[h] = (n1 >= 0 && n3 >= 0) ? a3 : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < GAGM_MAX_C; ++h) { t0 += (double)a2v[h]; t1 += (double)a3v[h]; }
+                T[e0] = t0; T[e0 + 1] = t1;
+                hk = ck_it; HSEG(0);
+            } else if (binU) {
                 // ================= Hungarian stage: T from the permutation description, no barrier
                 for (int e = tid; e < G * NU; e += GAGM_THREADS) nodeof_s[e] = __ldcg(nodeof_cur + e);
                 __syncthreads();
@@ -162,6 +254,7 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                     }
                 }
                 T[e0] = t0; T[e0 + 1] = t1;
+                hk = ck_it; HSEG(0);
             } else {
             // ================= phase 1: X_g = A_gg U_g, partial T = sum_g U_g^T X_g
             double t0 = 0.0, t1 = 0.0;
@@ -193,10 +286,12 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
             // ================= phase 2
             {
                 double s0 = 0.0, s1 = 0.0;
-                for (int cc = 0; cc < C; ++cc) {
-                    s0 += __ldcg(p.Tpart + (size_t)cc * NU * NU + e0);
-                    s1 += __ldcg(p.Tpart + (size_t)cc * NU * NU + e0 + 1);
-                }
+                double2 tp[GAGM_MAX_C];                               // all partial products in flight, summed in CTA order
+#pragma unroll
+                for (int cc = 0; cc < GAGM_MAX_C; ++cc)
+                    tp[cc] = cc < C ? __ldcg(reinterpret_cast<const double2 *>(p.Tpart + (size_t)cc * NU * NU + e0)) : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int cc = 0; cc < GAGM_MAX_C; ++cc) if (cc < C) { s0 += tp[cc].x; s1 += tp[cc].y; }
                 T[e0] = s0; T[e0 + 1] = s1;
             }
             }
@@ -206,7 +301,7 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                 if (binU) {
                     for (int r = tid; r < n; r += GAGM_THREADS) slot_s[r] = -1;
                     __syncthreads();                               // also publishes T
-                    if (tid < NU) { const int nd = nodeof_s[g * NU + tid]; if (nd >= 0) slot_s[nd] = tid; }
+                    if (tid < NU) { const int nd = nos[g * NU + tid]; if (nd >= 0) slot_s[nd] = tid; }
                     __syncthreads();
                     // Q = U_g T = rows of T picked by the node's slot
 #pragma unroll
@@ -229,13 +324,38 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                 }
                 }
                 __syncthreads();
+                HSEG(1);
                 // V1 = A_gg Q
                 double v1[RPW], v2[RPW];
 #pragma unroll
                 for (int r = 0; r < RPW; ++r) { v1[r] = 0.0; v2[r] = 0.0; }
-                rows_times_tile(p.A + (size_t)o * M + o, M, n, n, X, v1, warp, lane);
+                if (binU && hf && n * n <= GAGM_MAX_N * NU) rows_times_tile_d(Uo, n, X, v1, warp, lane);
+                else rows_times_tile(p.A + (size_t)o * M + o, M, n, n, X, v1, warp, lane);
+                HSEG(2);
                 // V2 = W[g rows, :] U   (Hungarian stage: one entry of W per graph h; else tile by graph h)
-                if (binU) {
+                if (binU && hf) {
+#pragma unroll
+                    for (int r = 0; r < RPW; ++r) {
+                        const int row = warp + GAGM_WARPS * r;
+                        if (row < n) {
+                            const float *wrow_s = W_s + row * M, *wrow_g = p.W + (size_t)(o + row) * M;
+                            double acc = 0.0;
+                            float wv[GAGM_MAX_C];
+#pragma unroll
+                            for (int h = 0; h < GAGM_MAX_C; ++h) {
+                                wv[h] = 0.f;
+                                if (h < G) {
+                                    const int nd = nos[h * NU + lane];
+                                    const float w = p.hcache ? wrow_s[p.node_off[h] + max(nd, 0)] : __ldg(wrow_g + p.node_off[h] + max(nd, 0));
+                                    wv[h] = nd >= 0 ? w : 0.f;
+                                }
+                            }
+#pragma unroll
+                            for (int h = 0; h < GAGM_MAX_C; ++h) acc += (double)wv[h];
+                            v2[r] = acc;
+                        }
+                    }
+                } else if (binU) {
 #pragma unroll
                     for (int r = 0; r < RPW; ++r) {
                         const int row = warp + GAGM_WARPS * r;
@@ -249,6 +369,21 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                             v2[r] = acc;
                         }
                     }
+                } else if (p.uall) {
+                    // all graphs' U_t in shared memory: ONE pass over the M columns of W (same accumulation order as the per-graph
+                    // tiles below, without 2 G block barriers and G tile loads; 8 L2 loads in flight per thread - one round trip is
+                    // ~700 cycles, a plain loop pays it per element).  What remains is bound by load-instruction issue: per column
+                    // one warp-uniform load of W per row and one of U for 3 DFMAs (fp64 itself runs at 62 FMA / clk / SM here,
+                    // tools/fp64_rate.cu).
+                    for (int e0_ = tid; e0_ < M * NU; e0_ += 8 * GAGM_THREADS) {
+                        double uv[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) { const int e = e0_ + q * GAGM_THREADS; uv[q] = e < M * NU ? __ldcg(Ul + e) : 0.0; }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) { const int e = e0_ + q * GAGM_THREADS; if (e < M * NU) Uall[e] = uv[q]; }
+                    }
+                    __syncthreads();
+                    rows_times_tile(p.W + (size_t)o * M, M, n, M, Uall, v2, warp, lane);
                 } else
                 for (int h = 0; h < G; ++h) {
                     const int oh = p.node_off[h], nh = p.node_off[h + 1] - oh;
@@ -262,16 +397,19 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                     }
                     rows_times_tile(p.W + (size_t)o * M + oh, M, n, nh, Us, v2, warp, lane);
                 }
+                HSEG(3);
                 // V = (V1 * qw * 2 + V2) / G
 #pragma unroll
                 for (int r = 0; r < RPW; ++r) {
                     const int row = warp + GAGM_WARPS * r;
                     if (row < n) {
-                        const double v = (v1[r] * p.quad_weight * 2.0 + v2[r]) / (double)G;
+                        const double vs = v1[r] * p.quad_weight * 2.0 + v2[r];
+                        const double v = gp2 ? vs * invG : vs / (double)G;     // a power of two: the reciprocal is exact
                         Z[row * ZP + lane] = projector == 0 ? v / tau : v;
                     }
                 }
                 __syncthreads();
+                HSEG(4);
                 const long long ck_pj = clock64();
                 if (projector == 0) ck_v += ck_pj - ck_ph2;
                 // ---- projector -> U_new_g in Ug
@@ -368,15 +506,30 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                     }
                 }
                 __syncthreads();
+                HSEG(5);
                 if (G == 2 && g == 0) {                            // mgm:358-359
                     for (int e = tid; e < n * NU; e += GAGM_THREADS) Ug[e] = (e / NU == e % NU) ? 1.0 : 0.0;
                     __syncthreads();
                 }
+                const bool lean = hf && projector == 1 && it_hg >= 2;      // U_t and U_{t-1} are permutations too: norms by counting
+                last_lean = lean;
                 if (projector == 1 && tid < NU) {                  // node_of of U_{t+1} for the next (Hungarian-stage) iteration
                     int nd = -1;
                     for (int r = 0; r < n; ++r) if (Ug[r * NU + tid] != 0.0) nd = r;
-                    nodeof_nxt[g * NU + tid] = nd;
+                    if (hf) {
+                        int *dst = nodeof_s + ((it_total + 1) & 1) * (GAGM_MAX_C * NU) + g * NU + tid;
+                        for (int cc = 0; cc < C; ++cc) *cluster.map_shared_rank(dst, cc) = nd;
+                        if (lean) {                                // entries are 0 / 1: ||U' - U||^2 = slots whose node changed, per side
+                            d1 += nd != nd_cur ? (double)((nd >= 0) + (nd_cur >= 0)) : 0.0;
+                            d2 += nd != nd_prev ? (double)((nd >= 0) + (nd_prev >= 0)) : 0.0;
+                        }
+                        nd_prev = nd_cur; nd_cur = nd;
+                    } else nodeof_nxt[g * NU + tid] = nd;
                 }
+                if (lean) {
+                    if (p.trace && it_total < p.trace_cap)
+                        for (int e = tid; e < n * NU; e += GAGM_THREADS) p.trace[(size_t)(it_total + 1) * UB + (size_t)o * NU + e] = Ug[e];
+                } else
                 for (int e = tid; e < n * NU; e += GAGM_THREADS) {
                     const double un = Ug[e];
                     const double a = un - __ldcg(Ul + (size_t)o * NU + e);
@@ -390,18 +543,28 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                     }
                 }
                 __syncthreads();
+                HSEG(6);
             }
             d1 = warp_sum(d1); d2 = warp_sum(d2);
             if (lane == 0) { red[warp] = d1; red[GAGM_WARPS + warp] = d2; }
             __syncthreads();
+            double *nx = normx + (it_total & 1) * (2 * GAGM_MAX_C);
             if (tid == 0) {
                 double a = 0.0, b = 0.0;
                 for (int w = 0; w < GAGM_WARPS; ++w) { a += red[w]; b += red[GAGM_WARPS + w]; }
-                p.normpart[2 * c] = a; p.normpart[2 * c + 1] = b;
+                if (hf) {
+                    for (int cc = 0; cc < C; ++cc) { double *r = cluster.map_shared_rank(nx, cc); r[2 * c] = a; r[2 * c + 1] = b; }
+                } else { p.normpart[2 * c] = a; p.normpart[2 * c + 1] = b; }
             }
-            __threadfence();
+            if (!last_lean) __threadfence();                       // U_{t+1} / norm partials in global memory
+            HSEG(7);
             { const long long ck_b = clock64(); cluster_sync_all(); ck_bar += clock64() - ck_b; }
+            HSEG(8);
             double n1 = 0.0, n2 = 0.0;
+            if (hf) {
+#pragma unroll
+                for (int cc = 0; cc < GAGM_MAX_C; ++cc) if (cc < C) { n1 += nx[2 * cc]; n2 += nx[2 * cc + 1]; }
+            } else
             for (int cc = 0; cc < C; ++cc) { n1 += __ldcg(p.normpart + 2 * cc); n2 += __ldcg(p.normpart + 2 * cc + 1); }
             if (p.trace_meta && c == 0 && tid == 0 && it_total < p.trace_cap) {
                 p.trace_meta[2 * it_total] = (double)projector; p.trace_meta[2 * it_total + 1] = tau;
@@ -411,6 +574,7 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
             binU = (projector == 1);
             if (projector == 0) ++it_sk; else { ++it_hg; n_lap += G; }
             if (p.mode == 1) { stop_all = true; break; }
+            HSEG(9);
             if (sqrt(n1) < p.tol || n2 == 0.0) break;              // mgm:361
         }
         if (stop_all) break;
@@ -422,6 +586,12 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
     }
 
     const double *Uf = p.Ubuf + (size_t)cur * UB;
+    if (last_lean) {                                           // the last iterations kept U only as node_of
+        const int o = p.node_off[c], n = p.node_off[c + 1] - o;
+        for (int e = tid; e < n * NU; e += GAGM_THREADS) p.U_out[(size_t)o * NU + e] = 0.f;
+        __syncthreads();
+        if (tid < NU && nd_cur >= 0) p.U_out[(size_t)(o + nd_cur) * NU + tid] = 1.f;
+    } else
     for (int g = c; g < G; g += C) {
         const int o = p.node_off[g], n = p.node_off[g + 1] - o;
         for (int e = tid; e < n * NU; e += GAGM_THREADS) p.U_out[(size_t)o * NU + e] = (float)Uf[(size_t)o * NU + e];
@@ -432,13 +602,13 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
         p.info[8] = (int)((clock64() - ck_start) >> 10); p.info[9] = (int)(ck_hung >> 10); p.info[10] = (int)(ck_lap >> 10);
         p.info[11] = (int)(ck_bar >> 10);
         p.info[12] = (int)(ck_p1 >> 10); p.info[13] = (int)(ck_v >> 10); p.info[14] = (int)(ck_proj >> 10);
+        for (int i = 0; i < 10; ++i) g_gagm_prof[i] = hs[i];
+        for (int i = 0; i < 6; ++i) g_gagm_prof[10 + i] = lapw->stat_ck[i];
+        for (int i = 0; i < 8; ++i) g_gagm_prof[16 + i] = lapw->stat_free[i];
     }
 }
 
-static size_t gagm_smem_bytes() {
-    return (size_t)(3 * GAGM_MAX_N * NU + GAGM_MAX_N * ZP + NU * NU + 2 * GAGM_MAX_N + 2 * GAGM_WARPS + NU + 8) * sizeof(double) +
-           sizeof(LapWork) + (size_t)(GAGM_MAX_G * NU + GAGM_MAX_N) * sizeof(int) + 16;
-}
+static size_t gagm_smem_bytes() { return GAGM_FIXED_SMEM; }
 
 }  // namespace ttdg
 
@@ -453,6 +623,18 @@ extern "C" int ttdg_gagm_set_lap_fast(int on) {
     const int prev = g_lap_fast < 0 ? 3 : g_lap_fast;
     g_lap_fast = (on >= 1 && on <= 4) ? on : 0;              // 2: Jacobi-auction start instead of the row reduction; 3: lean certified solve
     return prev;
+}
+
+// Diagnostic: cycles CTA 0 spent in the segments of the Hungarian-stage iterations of the last solve (synchronises the device):
+// {T build, Q gather, V1 = A Q, V2 = W U, V store, projection, U store + norms, norm reduce, cluster barrier, tail} and, inside the
+// lean LAPs of graph 0, {auction scans, bid resolution, augmentations, certificate, its reachability part, its Kahn part} and
+// [16..23] the free rows at the start of each auction round / after the last, summed over graph 0's LAPs.
+extern "C" int ttdg_gagm_read_profile(int64_t *out24) {
+    long long h[24];
+    cudaError_t e = cudaMemcpyFromSymbol(h, g_gagm_prof, sizeof(h));
+    if (e != cudaSuccess) return (int)e;
+    for (int i = 0; i < 24; ++i) out24[i] = (int64_t)h[i];
+    return 0;
 }
 
 extern "C" int64_t ttdg_gagm_scratch_bytes(int M, int G) {
@@ -493,7 +675,27 @@ extern "C" int ttdg_gagm_solve(const float *A, const float *W, const float *U0, 
     if (g_lap_fast < 0) { const char *e = getenv("TTDG_LAP_FAST"); g_lap_fast = (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 3; }
     p.lap_fast = g_lap_fast;
 
-    const size_t smem = gagm_smem_bytes();
+    size_t smem = gagm_smem_bytes();
+    p.uall = 0;
+    static int s_uall = -1;
+    if (s_uall < 0) { const char *ev = getenv("TTDG_GAGM_UALL"); s_uall = (ev && ev[0] == '0') ? 0 : 1; }
+    if (s_uall && smem + (size_t)M * NU * sizeof(double) <= 227 * 1024) { p.uall = 1; smem += (size_t)M * NU * sizeof(double); }
+    // Hungarian-stage cache (reuses the U-all region): diagonal blocks of A for all graphs + one graph's rows of W, fp32
+    static int s_hfast = -1;
+    if (s_hfast < 0) { const char *ev = getenv("TTDG_GAGM_HFAST"); s_hfast = (ev && ev[0] >= '0' && ev[0] <= '2') ? ev[0] - '0' : 1; }   // 2: without the fp32 cache
+    p.hfast = 0; p.hcache = 0;
+    for (int h = 0; h <= GAGM_MAX_C; ++h) p.aoff[h] = 0;
+    if (s_hfast && G <= GAGM_MAX_C) {
+        p.hfast = 1;
+        int mx = 0;
+        for (int g = 0; g < G; ++g) { p.aoff[g + 1] = p.aoff[g] + ms_h[g] * ms_h[g]; mx = ms_h[g] > mx ? ms_h[g] : mx; }
+        const size_t need = ((size_t)((p.aoff[G] + 3) & ~3) + (size_t)mx * M) * sizeof(float);
+        const size_t base = gagm_smem_bytes();
+        if (s_hfast != 2 && base + need <= 227 * 1024) {
+            p.hcache = 1;
+            if (base + need > smem) smem = base + need;
+        }
+    }
     cudaError_t e = cudaFuncSetAttribute(gagm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     cudaLaunchConfig_t cfg = {};

@@ -28,6 +28,9 @@ struct LapWork {                     // per-warp shared-memory workspace (state 
     int stat_steps, stat_hops;       // running totals (lane 0): Dijkstra steps and augmenting-path hops, for profiling
     int stat_fast_ok, stat_fast_fallback;      // certified fast solves / fall-backs to the SciPy-order solve
     int fast_mode;                   // 1: row-reduction start, 2: Jacobi auction start (set by the caller)
+    int stat_free[8];                // lean solve: free rows at the start of each auction round and after the last (running totals)
+    long long stat_ck[6];            // lean solve (lane 0): cycles in the auction scans / bid resolution / augmentations / certificate
+                                     // (all / reachability / Kahn)
     unsigned long long bidkey[LAP_MAX_DIM];    // auction: best bid per column of the current round
 };
 
@@ -306,6 +309,15 @@ struct LapSmemNegCostP {             // cost(i, j) = -z[i * si + j * sj], plain 
     __device__ __forceinline__ double operator()(int i, int j) const { return -z[i * si + j * sj]; }
 };
 
+// (first, second) smallest of a stream with the index of the first: v joins.  Strict '<' keeps the earliest index on ties.
+__device__ __forceinline__ void lap_min2(double v, int j, double &m1, double &m2, int &j1) {
+    const bool l1 = v < m1;
+    const double mx = l1 ? m1 : v;          // max(m1, v)
+    m1 = l1 ? v : m1;
+    j1 = l1 ? j : j1;
+    m2 = mx < m2 ? mx : m2;
+}
+
 constexpr int LAP_ARR_ROUNDS = 4;
 
 // Proves optimality and uniqueness of w.col4row from the duals w.u / w.v (fp64).  c̄ = (c - u) - v.
@@ -321,22 +333,33 @@ __device__ bool lap_certificate(int nr, int nc, Cost cost, LapWork &w) {
     unsigned adj = 0u;
     bool free_hit = false, bad = false;
     if (lane < nr) scale = fabs(w.u[lane]);
-    for (int o = 16; o > 0; o >>= 1) scale = fmax(scale, __shfl_xor_sync(TTDG_FULL, scale, o));
+    // max |u| to ~2^-20 relative (it only sets the margins): one redux on the high words instead of ten shuffles
+    scale = __hiloint2double((int)__reduce_max_sync(TTDG_FULL, (unsigned)__double2hiint(scale)), 0);
     const double delta = 1e-9 * (1.0 + scale), eps = 1e-11 * (1.0 + scale);
+    for (int j = lane; j < nc; j += 32) {                        // column properties, lane = column
+        const double vj = w.v[j];
+        bad = bad || vj > eps || (w.row4col[j] < 0 && vj != 0.0);
+    }
     if (lane < nr) {
         const double ui = w.u[lane];
         const int mine = w.col4row[lane];
-        bad = mine < 0 || mine >= nc || w.row4col[mine] != lane;
+        bad = bad || mine < 0 || mine >= nc || w.row4col[mine] != lane;
+        // branch-free (the lanes would diverge on every column) and unrolled (independent columns: the loads overlap); what depends
+        // on the column alone (v <= eps, v == 0 on free columns) was checked by the column's lane above
+        if (mine >= 0 && mine < nc) bad = bad || fabs((cost(lane, mine) - ui) - w.v[mine]) > eps;
+#pragma unroll 4
         for (int j = 0; j < nc; ++j) {
-            const double vj = w.v[j];
-            const double cb = (cost(lane, j) - ui) - vj;
+            const double cb = (cost(lane, j) - ui) - w.v[j];
             const int r = w.row4col[j];
-            if (j == mine) { bad = bad || fabs(cb) > eps; continue; }
-            bad = bad || cb < -eps || vj > eps || (r < 0 && vj != 0.0);
-            if (cb <= delta) { if (r < 0) free_hit = true; else adj |= 1u << r; }
+            const bool other = j != mine;
+            bad = bad || (other && cb < -eps);
+            const bool tight = other && cb <= delta;
+            free_hit = free_hit || (tight && r < 0);
+            adj |= (tight && r >= 0) ? (1u << (r & 31)) : 0u;
         }
     }
     if (__any_sync(TTDG_FULL, bad)) return false;
+    const long long ckc0 = clock64();
     unsigned reach = __ballot_sync(TTDG_FULL, free_hit);
     while (true) {
         const unsigned nxt = __ballot_sync(TTDG_FULL, lane < nr && (free_hit || (adj & reach) != 0u));
@@ -346,6 +369,7 @@ __device__ bool lap_certificate(int nr, int nc, Cost cost, LapWork &w) {
     bool zero_start = false;
     if (lane < nr && ((reach >> lane) & 1u)) zero_start = fabs(w.v[w.col4row[lane]]) <= delta;
     if (__any_sync(TTDG_FULL, zero_start)) return false;
+    const long long ckc1 = clock64();
     unsigned alive = nr >= 32 ? 0xFFFFFFFFu : ((1u << nr) - 1u);
     while (alive) {                                             // Kahn: drop the rows no alive row points to
         const unsigned pointed = __reduce_or_sync(TTDG_FULL, ((alive >> lane) & 1u) ? (adj & alive) : 0u);
@@ -353,6 +377,7 @@ __device__ bool lap_certificate(int nr, int nc, Cost cost, LapWork &w) {
         if (next == alive) break;
         alive = next;
     }
+    if (lane == 0) { w.stat_ck[4] += ckc1 - ckc0; w.stat_ck[5] += clock64() - ckc1; }
     return alive == 0u;
 }
 
@@ -360,18 +385,23 @@ template <int SLOTS, bool BF, class Cost>
 __device__ bool lap_lean_warp_t(int nr, int nc, Cost cost, LapWork &w) {
     const int lane = threadIdx.x & 31;
     for (int k = lane; k < nr; k += 32) { w.u[k] = 0.0; w.col4row[k] = -1; }
-    for (int k = lane; k < nc; k += 32) { w.row4col[k] = -1; w.v[k] = 0.0; w.bidkey[k] = 0ull; }
+    unsigned *bid32 = reinterpret_cast<unsigned *>(w.bidkey);        // auction: best bid per column of the current round
+    for (int k = lane; k < nc; k += 32) { w.row4col[k] = -1; w.v[k] = 0.0; bid32[k] = 0u; }
     __syncwarp();
+    const long long ck0 = clock64();
+    long long ck_res = 0;
     // ---- (A) Jacobi auction rounds, lane = row
     int steps = 0, hops = 0;
     {
         int myc = -1;
         for (int round = 0; round < LAP_ARR_ROUNDS; ++round) {
             const bool isfree = lane < nr && myc == -1;
-            if (!__any_sync(TTDG_FULL, isfree)) break;
+            const unsigned freemask = __ballot_sync(TTDG_FULL, isfree);
+            if (lane == 0) w.stat_free[round] += __popc(freemask);
+            if (freemask == 0u) break;
             double m1 = INFINITY, m2 = INFINITY;
             int j1 = 0;
-            unsigned long long mykey = 0ull;
+            unsigned mykey = 0u;
             if (isfree) {
                 // two independent half scans (even / odd columns) halve the compare-select dependency chain
                 double a1 = INFINITY, a2 = INFINITY, b1 = INFINITY, b2 = INFINITY;
@@ -379,18 +409,23 @@ __device__ bool lap_lean_warp_t(int nr, int nc, Cost cost, LapWork &w) {
                 int j = 0;
                 for (; j + 1 < nc; j += 2) {
                     const double va = cost(lane, j) - w.v[j], vb = cost(lane, j + 1) - w.v[j + 1];
-                    if (va < a1) { a2 = a1; a1 = va; ja = j; } else if (va < a2) a2 = va;
-                    if (vb < b1) { b2 = b1; b1 = vb; jb = j + 1; } else if (vb < b2) b2 = vb;
+                    // branch-free with plain compare + select (fmin / fmax carry NaN handling: 30 instructions per column instead of 13)
+                    lap_min2(va, j, a1, a2, ja);
+                    lap_min2(vb, j + 1, b1, b2, jb);
                 }
-                if (j < nc) { const double va = cost(lane, j) - w.v[j]; if (va < a1) { a2 = a1; a1 = va; ja = j; } else if (va < a2) a2 = va; }
+                if (j < nc) lap_min2(cost(lane, j) - w.v[j], j, a1, a2, ja);
                 if (b1 < a1) { m1 = b1; j1 = jb; m2 = fmin(a1, b2); } else { m1 = a1; j1 = ja; m2 = fmin(b1, a2); }
                 const double cut = (m2 < INFINITY) ? m2 - m1 : 0.0;
-                mykey = ((lap_ord(cut) & ~31ull) | (unsigned long long)(31 - lane)) | (1ull << 63);
-                atomicMax(&w.bidkey[j1], mykey);
+                mykey = (((unsigned)(lap_ord(cut) >> 32) & ~31u) | (unsigned)(31 - lane)) | 0x80000000u;
             }
+            // the winner of a column = the largest key among its bidders: ONE native 32-bit shared-memory atomicMax per bidder (a 64-bit
+            // key needs a CAS loop; match.any + redux per group was measured slower still).  Any bidder may win - the price falls by the
+            // winner's own cut, the duals stay feasible - so the 27 leading bits of the cut + the lane are key enough; deterministic.
+            const long long cka = clock64();
+            if (isfree) atomicMax(&bid32[j1], mykey);
             __syncwarp();
             if (isfree) {
-                if (w.bidkey[j1] == mykey) {                      // winner of column j1
+                if (bid32[j1] == mykey) {                         // winner of column j1
                     const int old = w.row4col[j1];
                     if (old >= 0) w.col4row[old] = -1;
                     w.row4col[j1] = lane; w.col4row[lane] = j1;
@@ -401,11 +436,14 @@ __device__ bool lap_lean_warp_t(int nr, int nc, Cost cost, LapWork &w) {
                 }
             }
             __syncwarp();
-            if (isfree) w.bidkey[j1] = 0ull;
+            if (isfree) bid32[j1] = 0u;
             __syncwarp();
             myc = lane < nr ? w.col4row[lane] : 0;
+            ck_res += clock64() - cka;
         }
     }
+    const long long ck1 = clock64();
+    { const unsigned fm = __ballot_sync(TTDG_FULL, lane < nr && w.col4row[lane < nr ? lane : 0] == -1); if (lane == 0) w.stat_free[LAP_ARR_ROUNDS] += __popc(fm); }
     if (BF) {
     // ---- (B) augmentations for the rows still free, lane = column: LABEL-CORRECTING shortest paths instead of Dijkstra.
     // Dijkstra settles one column per step and every step is a ~360-cycle chain of dependent warp-wide operations (load the row,
@@ -592,8 +630,12 @@ __device__ bool lap_lean_warp_t(int nr, int nc, Cost cost, LapWork &w) {
     }
     if (lane == 0) { w.stat_steps += steps; w.stat_hops += hops; }
     __syncwarp();
+    const long long ck2 = clock64();
     const bool ok = lap_certificate(nr, nc, cost, w);
-    if (lane == 0) { if (ok) ++w.stat_fast_ok; else ++w.stat_fast_fallback; }
+    if (lane == 0) {
+        if (ok) ++w.stat_fast_ok; else ++w.stat_fast_fallback;
+        w.stat_ck[0] += ck1 - ck0 - ck_res; w.stat_ck[1] += ck_res; w.stat_ck[2] += ck2 - ck1; w.stat_ck[3] += clock64() - ck2;
+    }
     __syncwarp();
     return ok;
 }

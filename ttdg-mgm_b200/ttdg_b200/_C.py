@@ -34,6 +34,7 @@ SIGNATURES = {
     "ttdg_affinity_pairs_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, c_int64, P, P, P, P, P]),
     "ttdg_gagm_scratch_bytes": (c_int64, [c_int, c_int]),
     "ttdg_gagm_set_lap_fast": (c_int, [c_int]),
+    "ttdg_gagm_read_profile": (c_int, [P]),
     "ttdg_gagm_solve": (c_int, [P, P, P, P, c_int, c_int, c_int, c_double, c_double, c_double, c_int, c_int, c_double,
                                 c_double, c_int, c_int, P, P, P, P, P, c_int, P]),
     "ttdg_matching_loss_scratch_bytes": (c_int64, [c_int]),
