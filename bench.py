@@ -14,6 +14,10 @@ as the reference's test loader batches them (TEST.BATCH, drop_last False):
 --config 1 (default) = BASELINE.json configs[1]: 8 x 512 x 512, 2 classes, TEST.BATCH 8, fp32-grade convolutions;
 --config 2 = configs[2]: the same with the bf16 backbone (fp32 matching stage), meant for --gpus 4;
 --config 3 = configs[3]: 8 x 384 x 384 polyp-like, 1 class, TEST.BATCH 5 (matching problems of 5 + 3 graphs), meant for --gpus 8.
+Schedule (default, TTDG_OVERLAP=0 switches it off): a step is one mini-dataset; pass (2) of step i runs from a weight snapshot on
+a second stream inside the GA-GM solver windows of step i + 1's pass (1) - the product's schedule for consecutive datasets
+(adapteacher/engine/trainer.py OverlappedEval; identical results, tests/test_gpu_overlap.py).  The timed region starts with nothing
+pending and ends with the last pass (2) drained: K steps = K adaptation passes + K evaluation passes, all work inside.
 `value` = adapted images / s with the uint8 images resident in HBM; `e2e` = the same from pinned HOST images through the
 plugin call (model(batched_inputs, branch='TTT') ... model(batched_inputs)) with the loss and a mask checksum read back.
 `roofline` = the step's dominant kernel family (tcgen05 convolutions), timed live; `sinkhorn_microbench` = configs[4].
@@ -81,6 +85,9 @@ def full_state(cfg):
     return sd
 
 
+OVERLAP = [os.environ.get("TTDG_OVERLAP", "1") != "0"]     # the trainer's schedule (TEST.OVERLAP_EVAL); 0 = strictly sequential
+
+
 def build_ours(device, cfg=None):
     from adapteacher.modeling.meta_arch.rcnn import DAobjTwoStagePseudoLabGeneralizedRCNN
     from ttdg_b200.optim import FlatSGD
@@ -113,6 +120,12 @@ def describe(cfg, world, impl):
         d["parallelism"] = (f"image-sharded x{world}; per adaptation step the flat gradient buffer is all-reduced over NCCL in 3 buckets "
                             "(affinity + FPN + res5 | res4 | res3) started from the backward pass as each completes")
         d["l2"] = "flushed before every timed step (256 MiB memset inside the timed region)"
+        d["schedule"] = ("a step = one mini-dataset of the rank's images: pass 1 (adaptation over its batches), then pass 2 (evaluation "
+                         "with the adapted weights), as trainer.py:469-485 orders them per dataset" +
+                         ("; pass 2 of step i runs on a second stream inside the GA-GM solver windows of step i + 1's pass 1 from a weight "
+                          "snapshot (adapteacher.engine.trainer.OverlappedEval, the product's schedule for consecutive datasets): the "
+                          "timed region starts with nothing pending and ends with the last pass 2 drained, so K steps hold exactly K "
+                          "adaptation passes and K evaluation passes" if OVERLAP[0] else "; sequential (TTDG_OVERLAP=0)"))
     else:
         d["implementation"] = "oracle/ttt_port.Trainer: the reference's algorithm restated on torch CPU (fp32), all host threads"
     return d
@@ -374,7 +387,7 @@ def main():
         e.record()
         return e
 
-    def step(batches, readback, marks=None):
+    def pass1(batches, marks=None):
         loss = None
         m.train()                                            # pass 1: adaptation (trainer.py:469-482)
         for inputs in batches:
@@ -396,17 +409,61 @@ def main():
             if t is not None:
                 t.append(ev())
                 marks.append(t)
+        return loss
+
+    def read_back(out, loss):                                # one D2H read of a step's result: per-image mask pixel counts + the loss
+        res = torch.stack([o["instances"].pred_masks.sum().to(torch.float64) for o in out] +
+                          [loss.detach().to(torch.float64) if loss is not None else torch.full((), float("nan"), dtype=torch.float64, device=device)])
+        host_res.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return (float(host_res[-1]) if loss is not None else None), int(host_res[:-1].sum())
+
+    def step(batches, readback, marks=None):
+        """Strictly sequential: pass 1, then pass 2 with the adapted weights (instrumented steps, per-kernel timing, TTDG_OVERLAP=0)."""
+        loss = pass1(batches, marks)
         m.eval()                                             # pass 2: inference with the adapted weights (trainer.py:484-485)
         out = []
         for inputs in batches:
             out += m(inputs)
-        if readback:                                         # one D2H read of the step's result: per-image mask pixel counts + the loss
-            res = torch.stack([o["instances"].pred_masks.sum().to(torch.float64) for o in out] +
-                              [loss.detach().to(torch.float64) if loss is not None else torch.full((), float("nan"), dtype=torch.float64, device=device)])
-            host_res.copy_(res, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return (float(host_res[-1]) if loss is not None else None), int(host_res[:-1].sum())
-        return None
+        return read_back(out, loss) if readback else None
+
+    # ---- the product's schedule (adapteacher/engine/trainer.py): pass 2 of a step inside the solver windows of the next step's pass 1
+    from adapteacher.engine.trainer import OverlappedEval
+    from ttdg_b200 import ops
+
+    class Sink:                                              # the evaluator of the bench: keeps (e2e: reads back) the step's masks
+        def __init__(self):
+            self.readback, self.loss, self.last, self.out = False, None, None, []
+
+        def reset(self):
+            self.out = []
+
+        def process(self, inputs, outputs):
+            self.out += outputs
+
+        def evaluate(self):
+            if self.readback:                                # on the evaluation stream: waits for that stream only
+                self.last = read_back(self.out, self.loss)
+            self.out = []
+            return None
+
+    pipe, sink = OverlappedEval(m), Sink()
+
+    def drain():
+        if pipe.active:
+            with torch.cuda.stream(pipe.stream):
+                pipe.drain()
+
+    def step_overlapped(batches, readback):
+        ops.SOLVER_WINDOW_HOOK[0] = pipe.window if pipe.active else None
+        try:
+            loss = pass1(batches)
+        finally:
+            ops.SOLVER_WINDOW_HOOK[0] = None
+        drain()                                              # what the windows left of the previous step's pass 2 (+ its read-back)
+        sink.readback, sink.loss = readback, loss
+        pipe.begin("bench", batches, sink)                   # snapshot of the adapted weights; evaluated during the next step
+        return sink.last
 
     def barrier():
         torch.cuda.synchronize()
@@ -429,9 +486,11 @@ def main():
                 os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per])
         except (AttributeError, OSError):
             pass
+    run_step = step_overlapped if OVERLAP[0] else step
     warm = max(args.warmup, 3)
     for _ in range(warm):
-        step(batches_dev, False)
+        run_step(batches_dev, False)
+    drain()                                                  # nothing pending when the timed region starts
     barrier()
     clocks = ClockSampler(local_rank) if rank == 0 else None      # one nvidia-smi poller per job, not per rank
     l0 = lib.ttdg_launch_count()
@@ -440,7 +499,8 @@ def main():
     h0 = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()                                        # L2 flush between steps (inside the timed region: 256 MiB memset)
-        step(batches_dev, False)
+        run_step(batches_dev, False)
+    drain()                                                  # the last step's pass 2 belongs to the timed region
     host_ms = (time.perf_counter() - h0) * 1e3 / args.steps  # host time to ENQUEUE a step (no sync inside)
     e1.record()
     barrier()
@@ -451,15 +511,20 @@ def main():
     # ---- end to end through the plugin call with pinned HOST images; loss + mask checksum read back every step
     h2d = sum(d["image"].numel() for b in batches_host for d in b)
     for _ in range(2):
-        step(batches_host, True)
+        run_step(batches_host, True)
+    drain()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         flush.zero_()
-        last = step(batches_host, True)
+        last = run_step(batches_host, True)
+    if OVERLAP[0]:
+        drain()
+        last = sink.last
     e1.record()
     barrier()
+    windows = pipe.windows
     e2e_val = IMAGES_PER_GPU * world * args.steps / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
     clk = clocks.stop() if clocks is not None else None
 
@@ -506,9 +571,12 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"] if conv == cfg["conv"] else "f32", "data": "synthetic",
                 "config": describe(cfg, world, "ours"),
                 "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * (IMAGES_PER_GPU + 1),
-                        "call": "model(batched_inputs, branch='TTT') + backward + FlatSGD.step + model(batched_inputs) from pinned host images",
+                        "call": ("model(batched_inputs, branch='TTT') + backward + FlatSGD.step per batch, then model(batched_inputs) per batch, "
+                                 "from pinned host images" + ("; the second pass runs through OverlappedEval (weight snapshot, second stream) inside the "
+                                                              "next step's solver windows, its result is read back there" if OVERLAP[0] else "")),
                         "last_loss": last[0], "mask_pixels": last[1]},
                 "gpu_launches": int(launches), "skipped_steps": stats["skipped"],
+                "overlap": ({"pass2_batches_in_solver_windows": int(windows), "note": "all timed + warm-up loops of this run"} if OVERLAP[0] else None),
                 "gagm": {"iterations": info[0], "lap_calls": info[3], "lap_fallbacks_graph0": info[7], "graphs": len(aux["sizes"]),
                          "nodes": int(sum(aux["sizes"])), "ms": per_rank["gagm_ms"], "lap_row_relaxations_graph0": info[5],
                          "cta0_kcycles": {"kernel": info[8], "hungarian_stage": info[9], "in_lap": info[10], "barrier_wait": info[11]}},

@@ -283,6 +283,12 @@ int ttdg_conv_tc_set_cluster(int cl);
  * residual absent or fp32 at the output's resolution - else as 2.  Same arithmetic in the same order: results are
  * bit-identical.  Returns the previous value, or TTDG_E_ARG. */
 int ttdg_conv_tc_set_epilogue(int mode);
+/* Persistent tensor-core kernels (ttdg_conv_tc*, ttdg_wgrad_tc*, ttdg_stem_tc*) launch one CTA per SM and give every CTA the same
+ * share of the tiles.  When another kernel holds some SMs for a long time - the GA-GM solver's cluster, 8 SMs for ~10 ms, while the
+ * evaluation pass of the previous dataset runs beside it (adapteacher/engine/trainer.py) - CTAs that find no SM would start only when
+ * others finish and double the kernel's duration; n > 0 caps the grid of the launches that follow at n SMs, 0 (default) = all.
+ * Host-side launch parameter only; returns the previous value. */
+int ttdg_set_sm_limit(int n);
 /* Diagnostics: while dev_buf != NULL, CTA 0 of every ttdg_conv_tc* launch records clock64() at 8 points of its first `items`
  * tiles into dev_buf[item * 8 + slot] (slot 0 / 1: first / last k-block's TMA issue, 2: MMA warp owns the accumulator,
  * 3: last k-block's operands ready, 4: last commit issued, 7 / 5 / 6: epilogue warp 0 starts the tile / has drained the

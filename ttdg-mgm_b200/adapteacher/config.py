@@ -150,7 +150,10 @@ def add_ateacher_config(cfg=None):
         if not isinstance(cfg.MODEL.get(sub), CfgNode):
             cfg.MODEL[sub] = CfgNode()
     cfg.TEST._merge_dict({"VAL_LOSS": True, "EVAL_STU": False, "DRAW": False, "DICE": False, "DICE_THRES": 0.9, "TTT": True,
-                          "BATCH": 1, "MIN_BATCH_NUM": None, "EVALUATOR": "COCOeval"})
+                          "BATCH": 1, "MIN_BATCH_NUM": None, "EVALUATOR": "COCOeval",
+                          # not a reference key: pass 2 of a dataset inside the solver windows of the next dataset's pass 1
+                          # (adapteacher/engine/trainer.py OverlappedEval); same results, different schedule
+                          "OVERLAP_EVAL": True})
     cfg.MODEL.RPN._merge_dict({"UNSUP_LOSS_WEIGHT": 1.0, "LOSS": "CrossEntropy"})
     cfg.MODEL.ROI_HEADS._merge_dict({"LOSS": "CrossEntropy"})
     cfg.SOLVER._merge_dict({"IMG_PER_BATCH_LABEL": 1, "IMG_PER_BATCH_UNLABEL": 1, "FACTOR_LIST": (1,)})

@@ -1268,6 +1268,7 @@ static int tc_setup_epilogue(TcParams &p) {
     return 0;
 }
 
+static int g_tc_sm_limit = 0;       // ttdg_set_sm_limit: persistent grids take at most this many SMs (0 = all)
 static int tc_sm_count() {
     static int n = 0;
     if (!n) {
@@ -1275,7 +1276,7 @@ static int tc_sm_count() {
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
     }
-    return n;
+    return (g_tc_sm_limit > 0 && g_tc_sm_limit < n) ? g_tc_sm_limit : n;
 }
 
 template <int BN_TILE, bool PRECISE, int CL, bool BF16 = false>
@@ -1456,6 +1457,12 @@ extern "C" int ttdg_conv_tc_set_epilogue(int mode) {
     if (mode < 0 || mode > 3) return TTDG_E_ARG;
     const int prev = ttdg::tc_epi();
     ttdg::g_tc_epi = mode;
+    return prev;
+}
+
+extern "C" int ttdg_set_sm_limit(int n) {
+    const int prev = ttdg::g_tc_sm_limit;
+    ttdg::g_tc_sm_limit = n > 0 ? n : 0;
     return prev;
 }
 

@@ -56,6 +56,7 @@ SIGNATURES = {
     "ttdg_conv_tc_supported": (c_int, [c_int, c_int, c_int]),
     "ttdg_conv_tc_set_cluster": (c_int, [c_int]),
     "ttdg_conv_tc_set_epilogue": (c_int, [c_int]),
+    "ttdg_set_sm_limit": (c_int, [c_int]),
     "ttdg_conv_tc_set_trace": (c_int, [c_void_p, c_int]),
     "ttdg_conv_tc": (c_int, [P, P, P, P, P, P] + [c_int] * 15 + [P, P]),
     "ttdg_wgrad_tc_supported": (c_int, [c_int, c_int, c_int]),

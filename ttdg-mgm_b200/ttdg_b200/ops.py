@@ -300,6 +300,13 @@ def affinity_pairs(X, w_sr, w_tg, w0, b0, w1, b1, sizes, pairs):
 
 
 # ------------------------------------------------------------------------------------------------ GA-GM
+# Called (no arguments) right after the solver of a test-time-adaptation step has been launched: the solver keeps a cluster of <= 8
+# SMs busy for ~10 ms while nothing else of the step can run (the loss needs its result), so the caller may put independent work on
+# ANOTHER stream here - adapteacher/engine/trainer.py evaluates a batch of the previous dataset with a weight snapshot.
+SOLVER_WINDOW_HOOK = [None]
+GAGM_CLUSTER_SMS = 8
+
+
 def gagm_solve(A, W, U0, ms, n_univ=NU, init_tau=0.1, min_tau=1e-2, sk_gamma=0.5, max_iter=200, sk_iter=20,
                converge_tol=1e-3, quad_weight=0.5, mode=0, step_projector=0, return_info=False, trace_cap=0):
     """GA_GM.gagm (mgm:300-389) on the device: one persistent cluster, no host round trips."""
@@ -361,6 +368,8 @@ class _MatchingLoss(torch.autograd.Function):
         if U_override is None:
             U, info = gagm_solve(A, Wds, U0, sizes, NU, cfg["ga_tau0"], cfg["ga_min_tau"], cfg["ga_gamma"], cfg["ga_iter"],
                                  cfg["ga_sk_iter"], cfg["ga_tol"], cfg["quad_weight"], return_info=True)
+            if SOLVER_WINDOW_HOOK[0] is not None:
+                SOLVER_WINDOW_HOOK[0]()
         else:
             U = _f32c(U_override)
         node_off = torch.tensor(offs, dtype=torch.int32, device=dev)
