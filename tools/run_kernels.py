@@ -264,6 +264,28 @@ elif what == "busy":
             host_res.copy_(res, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         return out
+    if "overlap" in sys.argv[3:]:
+        # the product's schedule (adapteacher/engine/trainer.py OverlappedEval, as bench.py runs it): pass 2 of the previous
+        # step inside this step's solver window, on a second stream, from a weight snapshot
+        from adapteacher.engine.trainer import OverlappedEval
+        pipe = OverlappedEval(m)
+
+        class Sink:
+            def reset(self): self.out = []
+            def process(self, i, o): self.out += o
+            def evaluate(self): self.out = []
+
+        sink = Sink()
+
+        def step():
+            m.train()
+            ops.SOLVER_WINDOW_HOOK[0] = pipe.window if pipe.active else None
+            loss, _, _, _ = m(inputs, branch="TTT")
+            ops.SOLVER_WINDOW_HOOK[0] = None
+            opt.zero_grad(); loss.backward(); opt.step(1)
+            if pipe.active:
+                pipe.drain()
+            pipe.begin("busy", [inputs], sink)
     for _ in range(3):
         step()
     torch.cuda.synchronize()

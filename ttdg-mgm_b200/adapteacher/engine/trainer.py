@@ -84,9 +84,13 @@ class OverlappedEval:
             if torch.cuda.is_available():
                 self.stream = torch.cuda.Stream()
         else:
-            with torch.no_grad():
-                for pr, p in zip(self.replica.parameters(), self.model.parameters()):
-                    pr.copy_(p)
+            with torch.no_grad():                           # a few multi-tensor launches instead of one small copy per parameter
+                dst, src = list(self.replica.parameters()), list(self.model.parameters())
+                if hasattr(torch, "_foreach_copy_"):
+                    torch._foreach_copy_(dst, src)
+                else:
+                    for pr, p in zip(dst, src):
+                        pr.copy_(p)
         if hasattr(self.replica, "refresh_weight_copies"):
             self.replica.refresh_weight_copies()
         if self.stream is not None:
@@ -179,23 +183,25 @@ class BaselineTrainer:
             loader = data_loaders[name]
             if pipe is not None and pipe.active:
                 ops.SOLVER_WINDOW_HOOK[0] = pipe.window
-            if cfg.TEST.TTT and world_size > 1:            # pass 1 on image shards: every rank takes part in every all-reduce
-                cls._ttt_pass_sharded(cfg, model, optimizer, loader, world_size)
-            elif cfg.TEST.TTT:                             # pass 1: adaptation, model in train mode (:469-482)
-                model.train()
-                for b, inputs in enumerate(loader):
-                    if cfg.TEST.MIN_BATCH_NUM is not None and b >= cfg.TEST.MIN_BATCH_NUM:
-                        break
-                    loss, _, _, _ = model(inputs, branch="TTT")
-                    if loss is None:
-                        continue
-                    optimizer.zero_grad()
-                    loss.backward()
-                    if hasattr(optimizer, "flat_g"):
-                        optimizer.step(world_size)         # fused flat-bucket step (+ gradient all-reduce)
-                    else:
-                        optimizer.step()
-            ops.SOLVER_WINDOW_HOOK[0] = None
+            try:
+                if cfg.TEST.TTT and world_size > 1:            # pass 1 on image shards: every rank takes part in every all-reduce
+                    cls._ttt_pass_sharded(cfg, model, optimizer, loader, world_size)
+                elif cfg.TEST.TTT:                             # pass 1: adaptation, model in train mode (:469-482)
+                    model.train()
+                    for b, inputs in enumerate(loader):
+                        if cfg.TEST.MIN_BATCH_NUM is not None and b >= cfg.TEST.MIN_BATCH_NUM:
+                            break
+                        loss, _, _, _ = model(inputs, branch="TTT")
+                        if loss is None:
+                            continue
+                        optimizer.zero_grad()
+                        loss.backward()
+                        if hasattr(optimizer, "flat_g"):
+                            optimizer.step(world_size)         # fused flat-bucket step (+ gradient all-reduce)
+                        else:
+                            optimizer.step()
+            finally:
+                ops.SOLVER_WINDOW_HOOK[0] = None
             evaluator = evaluators[idx] if evaluators is not None else DiceEvaluator(name, cfg.TEST.DICE_THRES, (dataset_dicts or {}).get(name))
             if pipe is not None:
                 if pipe.active:                            # the previous dataset's pass 2: whatever the windows left over
