@@ -126,3 +126,43 @@ def test_metrics_from_counts_border_centroid_does_not_raise():
             ref = Structure_measure().get_score(pred, gt)
         np.testing.assert_allclose(d, dice(pred, gt), rtol=1e-12)
         assert (np.isnan(s) and np.isnan(ref)) or abs(s - ref) <= 2e-6 * max(1.0, abs(ref)), (s, ref)
+
+
+def test_overlapped_eval_uses_the_snapshot_and_keeps_the_order():
+    """OverlappedEval (adapteacher/engine/trainer.py) on the host: batches queued at begin() are evaluated by window() / drain()
+    with the weights of begin(), in order, whatever happens to the adapting model in between (no GPU: no second stream, no SM cap)."""
+    from adapteacher.engine.trainer import OverlappedEval
+
+    class Lin(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.ones(()))
+
+        def forward(self, inputs):
+            return [float(self.w) * d["x"] for d in inputs]
+
+    class Rec:
+        def reset(self):
+            self.seen = []
+
+        def process(self, inputs, outputs):
+            self.seen += list(zip([d["x"] for d in inputs], outputs))
+
+        def evaluate(self):
+            return {"sum": sum(o for _, o in self.seen)}
+
+    model, rec = Lin(), Rec()
+    pipe = OverlappedEval(model)
+    assert not pipe.active
+    pipe.window()                                            # nothing queued: a no-op
+    pipe.begin("a", [[{"x": 1.0}, {"x": 2.0}], [{"x": 3.0}], [{"x": 4.0}]], rec)
+    with torch.no_grad():
+        model.w.mul_(10.0)                                   # the next dataset's adaptation changes the model ...
+    pipe.window()
+    pipe.window()
+    assert pipe.windows == 2 and rec.seen == [(1.0, 1.0), (2.0, 2.0), (3.0, 3.0)]       # ... the replica keeps the snapshot
+    res, ev = pipe.drain()
+    assert ev is rec and res == {"sum": 10.0} and rec.seen[-1] == (4.0, 4.0) and not pipe.active
+    pipe.begin("b", [[{"x": 1.0}]], rec)                     # second snapshot: the adapted weights
+    res, _ = pipe.drain()
+    assert res == {"sum": 10.0} and rec.seen == [(1.0, 10.0)]
