@@ -52,6 +52,7 @@ class OverlappedEval:
         self.name = None
         self.images = 0
         self.windows = 0            # batches evaluated inside a solver window
+        self._params = None
         self.t0 = 0.0
 
     @property
@@ -85,7 +86,9 @@ class OverlappedEval:
                 self.stream = torch.cuda.Stream()
         else:
             with torch.no_grad():                           # a few multi-tensor launches instead of one small copy per parameter
-                dst, src = list(self.replica.parameters()), list(self.model.parameters())
+                if self._params is None:                    # (the two module trees are walked once)
+                    self._params = (list(self.replica.parameters()), list(self.model.parameters()))
+                dst, src = self._params
                 if hasattr(torch, "_foreach_copy_"):
                     torch._foreach_copy_(dst, src)
                 else:
