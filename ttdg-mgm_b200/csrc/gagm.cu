@@ -52,7 +52,7 @@ struct GagmParams {
     int G, M, C;
     double init_tau, min_tau, sk_gamma, tol, quad_weight;
     int max_iter, sk_iter, mode, step_projector, sq_transposed;
-    int uall;            // shared memory holds U of all graphs (M * NU doubles fit)
+    int uall;            // shared memory holds U of all graphs: 1 = pitch NU (vector product), 2 = pitch GAGM_UP (FP64 tensor-core product)
     int hfast;           // G <= cluster size (one graph per CTA): Hungarian-stage iterations exchange node_of / norms through DSMEM,
                          // count the norms, keep an fp64 copy of the CTA's own block of A in shared memory
     int hcache;          // hfast and the diagonal blocks of A + this CTA's rows of W fit in shared memory as fp32 copies (the region
@@ -116,6 +116,52 @@ __device__ __forceinline__ void rows_times_tile(const float *__restrict__ Mg, in
                                                 const double *__restrict__ S, double (&acc)[RPW], int warp, int lane) {
     if (nrows <= 3 * GAGM_WARPS) rows_times_tile_r<3>(Mg, ld, nrows, ncols, S, acc, warp, lane);
     else rows_times_tile_r<6>(Mg, ld, nrows, ncols, S, acc, warp, lane);
+}
+
+// V2 = W[rows of one graph][0 .. M) (n x M fp32, global) x U (M x 32 fp64, shared, pitch GAGM_UP) on the FP64 tensor cores
+// (mma.sync m8n8k4 f64).  The vector form pays one warp-uniform global load and one F2F per row and column for every DFMA - LSU
+// issue bound, 50-90 k cycles per Sinkhorn-stage iteration, and a temperature stage that does not converge runs 200 of them.
+// Here a warp owns 8 x 8 output tiles: per k-step of 4 each lane loads ONE entry of W (the fragment's, widened once) and ONE of U
+// and the warp issues one DMMA = 256 FMAs; GAGM_UP = 36 makes the U fragment loads conflict-free (row step 288 B: the 16 lanes of
+// a half-warp hit 16 different 8-byte banks).  fp64 accumulation in another order than the vector form: ~1e-16 apart.
+constexpr int GAGM_UP = 36;
+// (c0, c1) += A[8 rows][0 .. K) x B[0 .. K)[8 columns]: wr = this lane's row of the fp32 matrix + its fragment column, ub = the
+// fp64 operand at [fragment row][this lane's column], pitch UPITCH doubles
+template <int UPITCH>
+__device__ __forceinline__ void dmma_tile(const float *__restrict__ wr, int K, const double *ub, int ac, double &c0, double &c1) {
+    constexpr int KB = 8;                                   // k-steps per batch: the batch's global loads are in flight together
+    int k = 0;
+    for (; k + 4 * KB <= K; k += 4 * KB) {
+        float a[KB];
+#pragma unroll
+        for (int q = 0; q < KB; ++q) a[q] = __ldg(wr + k + 4 * q);
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            const double av = (double)a[q], bv = ub[(k + 4 * q) * UPITCH];
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                         : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
+        }
+    }
+    for (; k < K; k += 4) {
+        const bool in = k + ac < K;
+        const double av = in ? (double)__ldg(wr + k) : 0.0, bv = in ? ub[k * UPITCH] : 0.0;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                     : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
+    }
+}
+// out[n x 32, pitch OP] = Mg[n rows][0 .. K) (fp32, global, leading dimension ld) x B (K x 32 fp64, shared, pitch NU): the small
+// products of the Sinkhorn-stage iterations (X = A_gg U_g) as 8 x 8 tiles, one warp per tile
+__device__ __forceinline__ void rows_times_tile_tc(const float *__restrict__ Mg, int ld, int n, int K, const double *B, double *out,
+                                                   int op, int warp, int lane) {
+    const int ar = lane >> 2, ac = lane & 3;                // fragment coordinates: A[ar][ac], B[ac][ar], C[ar][2 ac + {0, 1}]
+    const int ntiles = ((n + 7) >> 3) * (NU / 8);
+    for (int t = warp; t < ntiles; t += GAGM_WARPS) {
+        const int rb = t / (NU / 8), nt = t % (NU / 8);
+        const int row = rb * 8 + ar;
+        double c0 = 0.0, c1 = 0.0;
+        dmma_tile<NU>(Mg + (size_t)(row < n ? row : 0) * ld + ac, K, B + ac * NU + nt * 8 + ar, ac, c0, c1);
+        if (row < n) { out[row * op + nt * 8 + 2 * ac] = c0; out[row * op + nt * 8 + 2 * ac + 1] = c1; }
+    }
 }
 
 // bytes of the fixed part of the dynamic shared memory (everything before the U-all / Hungarian-stage cache region), 16-aligned
@@ -262,12 +308,15 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                 const int o = p.node_off[g], n = p.node_off[g + 1] - o;
                 for (int e = tid; e < n * NU; e += GAGM_THREADS) Ug[e] = __ldcg(Ul + (size_t)o * NU + e);
                 __syncthreads();
-                double acc[RPW];
+                if (p.uall == 2) rows_times_tile_tc(p.A + (size_t)o * M + o, M, n, n, Ug, X, NU, warp, lane);
+                else {
+                    double acc[RPW];
 #pragma unroll
-                for (int r = 0; r < RPW; ++r) acc[r] = 0.0;
-                rows_times_tile(p.A + (size_t)o * M + o, M, n, n, Ug, acc, warp, lane);
+                    for (int r = 0; r < RPW; ++r) acc[r] = 0.0;
+                    rows_times_tile(p.A + (size_t)o * M + o, M, n, n, Ug, acc, warp, lane);
 #pragma unroll
-                for (int r = 0; r < RPW; ++r) { const int row = warp + GAGM_WARPS * r; if (row < n) X[row * NU + lane] = acc[r]; }
+                    for (int r = 0; r < RPW; ++r) { const int row = warp + GAGM_WARPS * r; if (row < n) X[row * NU + lane] = acc[r]; }
+                }
                 __syncthreads();
                 for (int r = 0; r < n; ++r) {
                     const double uv = Ug[r * NU + u1];
@@ -329,11 +378,39 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                 double v1[RPW], v2[RPW];
 #pragma unroll
                 for (int r = 0; r < RPW; ++r) { v1[r] = 0.0; v2[r] = 0.0; }
+                const bool tc = !binU && p.uall == 2;              // dense U_t: both products of V on the FP64 tensor cores
+                if (tc) {
+                    for (int e0_ = tid; e0_ < M * NU; e0_ += 8 * GAGM_THREADS) {       // U_t of all graphs, pitch GAGM_UP
+                        double uv[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) { const int e = e0_ + q * GAGM_THREADS; uv[q] = e < M * NU ? __ldcg(Ul + e) : 0.0; }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) { const int e = e0_ + q * GAGM_THREADS; if (e < M * NU) Uall[(e / NU) * GAGM_UP + e % NU] = uv[q]; }
+                    }
+                    __syncthreads();
+                    const int ar = lane >> 2, ac = lane & 3;
+                    const int ntiles = ((n + 7) >> 3) * (NU / 8);
+                    for (int t = warp; t < ntiles; t += GAGM_WARPS) {
+                        const int rb = t / (NU / 8), nt = t % (NU / 8);
+                        const int row = rb * 8 + ar, rowc = row < n ? row : 0;
+                        double a0 = 0.0, a1 = 0.0, w0 = 0.0, w1 = 0.0;
+                        dmma_tile<NU>(p.A + (size_t)(o + rowc) * M + o + ac, n, X + ac * NU + nt * 8 + ar, ac, a0, a1);          // V1 = A_gg Q
+                        dmma_tile<GAGM_UP>(p.W + (size_t)(o + rowc) * M + ac, M, Uall + ac * GAGM_UP + nt * 8 + ar, ac, w0, w1);  // V2 = W U
+                        if (row < n) {
+                            const double s0 = a0 * p.quad_weight * 2.0 + w0, s1 = a1 * p.quad_weight * 2.0 + w1;
+                            const double q0 = gp2 ? s0 * invG : s0 / (double)G, q1 = gp2 ? s1 * invG : s1 / (double)G;
+                            double *z = Z + row * ZP + nt * 8 + 2 * ac;
+                            z[0] = projector == 0 ? q0 / tau : q0; z[1] = projector == 0 ? q1 / tau : q1;
+                        }
+                    }
+                } else
                 if (binU && hf && n * n <= GAGM_MAX_N * NU) rows_times_tile_d(Uo, n, X, v1, warp, lane);
                 else rows_times_tile(p.A + (size_t)o * M + o, M, n, n, X, v1, warp, lane);
                 HSEG(2);
                 // V2 = W[g rows, :] U   (Hungarian stage: one entry of W per graph h; else tile by graph h)
-                if (binU && hf) {
+                if (tc) {
+                    // done above, V is in place
+                } else if (binU && hf) {
 #pragma unroll
                     for (int r = 0; r < RPW; ++r) {
                         const int row = warp + GAGM_WARPS * r;
@@ -370,11 +447,8 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
                         }
                     }
                 } else if (p.uall) {
-                    // all graphs' U_t in shared memory: ONE pass over the M columns of W (same accumulation order as the per-graph
-                    // tiles below, without 2 G block barriers and G tile loads; 8 L2 loads in flight per thread - one round trip is
-                    // ~700 cycles, a plain loop pays it per element).  What remains is bound by load-instruction issue: per column
-                    // one warp-uniform load of W per row and one of U for 3 DFMAs (fp64 itself runs at 62 FMA / clk / SM here,
-                    // tools/fp64_rate.cu).
+                    // all graphs' U_t in shared memory: ONE pass over the M columns of W (without 2 G block barriers and G tile
+                    // loads; 8 L2 loads in flight per thread - one round trip is ~700 cycles, a plain loop pays it per element)
                     for (int e0_ = tid; e0_ < M * NU; e0_ += 8 * GAGM_THREADS) {
                         double uv[8];
 #pragma unroll
@@ -402,7 +476,7 @@ gagm_kernel(const __grid_constant__ GagmParams p) {
 #pragma unroll
                 for (int r = 0; r < RPW; ++r) {
                     const int row = warp + GAGM_WARPS * r;
-                    if (row < n) {
+                    if (row < n && !tc) {
                         const double vs = v1[r] * p.quad_weight * 2.0 + v2[r];
                         const double v = gp2 ? vs * invG : vs / (double)G;     // a power of two: the reciprocal is exact
                         Z[row * ZP + lane] = projector == 0 ? v / tau : v;
@@ -678,8 +752,10 @@ extern "C" int ttdg_gagm_solve(const float *A, const float *W, const float *U0, 
     size_t smem = gagm_smem_bytes();
     p.uall = 0;
     static int s_uall = -1;
-    if (s_uall < 0) { const char *ev = getenv("TTDG_GAGM_UALL"); s_uall = (ev && ev[0] == '0') ? 0 : 1; }
-    if (s_uall && smem + (size_t)M * NU * sizeof(double) <= 227 * 1024) { p.uall = 1; smem += (size_t)M * NU * sizeof(double); }
+    if (s_uall < 0) { const char *ev = getenv("TTDG_GAGM_UALL"); s_uall = (ev && ev[0] >= '0' && ev[0] <= '2') ? ev[0] - '0' : 2; }
+    // 2: pitch GAGM_UP + FP64 tensor-core product (TTDG_GAGM_UALL=1 keeps the vector form), 1: pitch NU, vector form
+    if (s_uall >= 2 && smem + (size_t)M * GAGM_UP * sizeof(double) <= 227 * 1024) { p.uall = 2; smem += (size_t)M * GAGM_UP * sizeof(double); }
+    else if (s_uall && smem + (size_t)M * NU * sizeof(double) <= 227 * 1024) { p.uall = 1; smem += (size_t)M * NU * sizeof(double); }
     // Hungarian-stage cache (reuses the U-all region): diagonal blocks of A for all graphs + one graph's rows of W, fp32
     static int s_hfast = -1;
     if (s_hfast < 0) { const char *ev = getenv("TTDG_GAGM_HFAST"); s_hfast = (ev && ev[0] >= '0' && ev[0] <= '2') ? ev[0] - '0' : 1; }   // 2: without the fp32 cache
