@@ -275,10 +275,17 @@ def conv_roofline(step_fn, conv, steps=2):
     mult = 3 if conv == "tf32x3" else 1
     achieved = flops / (ms * 1e-3) / 1e12
     kind = "kind::f16 (bf16)" if conv == "bf16" else "kind::tf32"
+    traffic = None                                          # DRAM bytes per launch of the family, from one ncu --set full capture
+    if conv == "tf32x3":
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_conv_tc_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            traffic = None
     return {"bound": "tensor", "kernel": "conv_tc_kernel + wgrad_tc_kernel (tcgen05 %s)" % kind, "achieved": round(achieved, 1),
             "mma_tflops": round(achieved * mult, 1), "peak": round(peak, 1),
             "peak_source": how + (" dense bf16 (sustained)" if conv == "bf16" else " dense bf16 (sustained) / 2 = TF32"),
-            "unit": "TFLOP/s", "frac": round(achieved / peak, 3), "frac_mma": round(achieved * mult / peak, 3), "traffic": None,
+            "unit": "TFLOP/s", "frac": round(achieved / peak, 3), "frac_mma": round(achieved * mult / peak, 3), "traffic": traffic,
             "launches_per_step": len(rec) // steps, "ms_per_step": round(ms / steps, 3),
             "algorithmic_tflop_per_step": round(flops / steps / 1e12, 3),
             "note": ("3xTF32 parity mode: 3 TF32 MMAs per fp32-grade product; frac = algorithmic, frac_mma = tensor-pipe work"
