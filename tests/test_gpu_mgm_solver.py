@@ -182,7 +182,8 @@ def test_gagm_many_graphs_and_extreme_sizes():
     """More graphs than the cluster has CTAs (G = 11 > 8), sizes 1 and 96."""
     gen = torch.Generator().manual_seed(3)
     # (the third case: more graphs than CTAs AND small enough for the tensor-core products of the Sinkhorn stage - two graphs per CTA)
-    for ms in ([96, 1, 33, 32, 31, 64, 5, 17, 40, 2, 50], [96, 96, 96], [12, 20, 9, 15, 30, 7, 18, 25, 11, 16, 1, 33]):
+    for ms in ([96, 1, 33, 32, 31, 64, 5, 17, 40, 2, 50], [96, 96, 96], [12, 20, 9, 15, 30, 7, 18, 25, 11, 16, 1, 33],
+               [1, 5, 33, 2, 57]):                          # one graph per CTA (shared-memory Hungarian path) with 1- and 2-node graphs
         M = sum(ms)
         A = torch.rand(M, M, generator=gen) * 0.05
         W = torch.rand(M, M, generator=gen)
