@@ -22,6 +22,15 @@
 //     Q_g[r][:] = T[slot_g(r)][:],   (W U)[r][u] = sum_h W[r][node_h(u)]
 // and only V1 = A_gg Q_g stays dense: one cluster barrier per iteration, ~1/8 of the FMAs.  Zero terms are skipped in
 // the same order the dense loops add them, so both paths produce the same bits (for G <= 8).
+//
+// Round 2 (cycle accounting through ttdg_gagm_read_profile):
+//   * G <= 8 (one graph per CTA): node_of and the norm partials travel between the CTAs through DSMEM stores before the cluster
+//     barrier (no L2 round trips, no __threadfence), the norms ||U' - U||^2 are counted from node_of (0 / 1 entries: exact), the
+//     diagonal blocks of A and the CTA's rows of W are read from fp32 copies in shared memory when they fit, V1 from an fp64 copy;
+//   * Sinkhorn-stage iterations (dense U): X = A_gg U_g, V1 = A_gg Q and V2 = W U run on the FP64 tensor cores (mma.sync m8n8k4
+//     f64, one 8 x 8 tile per warp) instead of one warp-uniform load + F2F per DFMA;
+//   * ops.SOLVER_WINDOW_HOOK (host side): the ~10 ms this kernel keeps <= 8 SMs busy are filled with the previous dataset's
+//     evaluation pass on another stream (adapteacher/engine/trainer.py).
 #include <cstdlib>
 #include "lap.cuh"
 #include "sinkhorn_small.cuh"
