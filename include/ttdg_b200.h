@@ -127,11 +127,12 @@ int ttdg_gemm_f64acc(int transA, int transB, int m, int n, int k, const void *A,
                      const void *B, int b_is_f64, int ldb, void *C, int c_is_f64, int ldc, int accumulate,
                      void *stream);
 
-/* Certified fast LAP inside ttdg_gagm_solve: 0 (default; also env TTDG_LAP_FAST) = every Hungarian projection walks SciPy's
+/* Hungarian projections inside ttdg_gagm_solve (also env TTDG_LAP_FAST): 0 = every projection walks SciPy's
  * shortest-augmenting-path order; 1 = start from a row reduction (2 = from a Jacobi auction with epsilon 0), certify that the
  * optimum is unique by a margin (no tight edge to a free column, tight-edge digraph acyclic) and fall back to the SciPy-order
- * solve otherwise.  Same results by
- * construction (mgm:324-328 -> utils/hungarian.py:58-65).  Returns the previous setting. */
+ * solve otherwise; 3 (default) = the lean certified solve (auction rounds + Dijkstra without SciPy's bookkeeping + the same
+ * certificate and fall-back), 4 = the same with label-correcting rounds instead of Dijkstra.  Same results by construction
+ * (mgm:324-328 -> utils/hungarian.py:58-65), checked on every iteration of the trajectory.  Returns the previous setting. */
 int ttdg_gagm_set_lap_fast(int on);
 /* Diagnostic (tools/run_kernels.py gagm_*): cycles CTA 0 spent in the segments of the Hungarian-stage iterations of the last
  * ttdg_gagm_solve - out24 = {T build, Q gather, V1 = A Q, V2 = W U, V store, projection, U store + norms, norm reduce,

@@ -699,9 +699,9 @@ using namespace ttdg;
 
 static int g_lap_fast = -1;     // -1: read TTDG_LAP_FAST at first use
 
-// Certified fast LAP inside the GA-GM solver (lap.cuh): 0 = SciPy-order solve only (default), 1 = row-reduction start +
-// uniqueness certificate, SciPy-order solve as the fall-back.  Results are identical by construction; info[7] counts the
-// fall-backs of graph 0.  Returns the previous setting.
+// Hungarian projections inside the GA-GM solver (lap.cuh): 0 = SciPy-order solve only, 1 / 2 = row-reduction / auction start +
+// uniqueness certificate, 3 (default) = lean certified solve, 4 = its label-correcting variant; the SciPy-order solve is the
+// fall-back.  Results are identical by construction; info[7] counts the fall-backs of graph 0.  Returns the previous setting.
 extern "C" int ttdg_gagm_set_lap_fast(int on) {
     const int prev = g_lap_fast < 0 ? 3 : g_lap_fast;
     g_lap_fast = (on >= 1 && on <= 4) ? on : 0;              // 2: Jacobi-auction start instead of the row reduction; 3: lean certified solve
